@@ -1,0 +1,81 @@
+"""ctypes binding of libcpfn_b200.so (the C ABI declared in include/cpfn_b200.h).
+
+There is no fallback: if the shared library is missing or a call fails, a
+RuntimeError is raised.  Build it with ``python -m cpfn_b200.build`` (or
+``__graft_entry__.build()``).
+"""
+import ctypes
+import os
+import re
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcpfn_b200.so")
+HEADER_PATH = os.path.join(_HERE, "..", "include", "cpfn_b200.h")
+
+_lib = None
+
+c_void_p = ctypes.c_void_p
+c_int = ctypes.c_int
+c_float = ctypes.c_float
+c_size_t = ctypes.c_size_t
+
+# name -> (restype, argtypes); must list every symbol of include/cpfn_b200.h
+# (tests/test_abi.py checks this table against the header).
+SIGNATURES = {
+    "cpfn_version": (c_int, []),
+    "cpfn_error_string": (ctypes.c_char_p, [c_int]),
+    "cpfn_last_cuda_error": (ctypes.c_char_p, []),
+    "cpfn_sm_count": (c_int, []),
+    "cpfn_fps_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "cpfn_furthest_point_sampling": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
+                                             c_size_t, c_void_p]),
+    "cpfn_ball_query": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int,
+                                c_void_p, c_void_p]),
+    "cpfn_gather_points": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                   c_void_p]),
+    "cpfn_gather_points_grad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                        c_void_p]),
+    "cpfn_group_points": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                  c_void_p, c_void_p]),
+    "cpfn_group_points_grad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                       c_void_p, c_void_p]),
+    "cpfn_three_nn": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
+                              c_void_p]),
+    "cpfn_three_weighted_sum": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                        c_void_p, c_void_p]),
+    "cpfn_three_weighted_sum_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                             c_int, c_void_p, c_void_p]),
+}
+
+
+def header_symbols():
+    """Every function name declared in include/cpfn_b200.h."""
+    with open(HEADER_PATH) as f:
+        text = f.read()
+    return sorted(set(re.findall(r"CPFN_API[^;(]*?\b(cpfn_\w+)\s*\(", text)))
+
+
+def lib():
+    """Load the shared library once; fail loudly when it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "cpfn_b200: %s is missing -- build it with `python -m cpfn_b200.build`. "
+                "There is no CPU or PyTorch fallback for this path." % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(code, what):
+    if code != 0:
+        L = lib()
+        msg = L.cpfn_error_string(code).decode()
+        if code == -2:
+            msg += ": " + L.cpfn_last_cuda_error().decode()
+        raise RuntimeError("cpfn_b200.%s failed: %s" % (what, msg))

@@ -1,0 +1,114 @@
+/*
+ * cpfn_b200.h -- C ABI of libcpfn_b200.so, the sm_100a implementation of the
+ * CPFN data-parallel hot path (PointNet++ grouping backbone + SPFN weighted
+ * total-least-squares fitters).
+ *
+ * Conventions (all entry points)
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless
+ *     the parameter name ends in _host;
+ *   - tensors are dense, row-major, float32 / int32 exactly as the reference
+ *     pybind module takes them (PointNet2/pointnet2_ops/cuda_ops/src/
+ *     bindings.cpp:6-19, checks in include/utils.h:5-25);
+ *   - outputs and workspaces are caller-allocated; the library never
+ *     allocates device memory, never synchronises and never touches torch;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*; NULL is
+ *     the legacy default stream) and the call returns immediately;
+ *   - the return value is 0 on success or a negative CPFN_E* code.  A failed
+ *     launch is REPORTED (the reference calls exit(-1), include/
+ *     cuda_utils.h:30-39; this library does not);
+ *   - element offsets are computed in 64 bits (the reference overflows int
+ *     past 2^31 elements per tensor).
+ *
+ * Paths in the "replaces" notes are relative to the reference tree.
+ */
+#ifndef CPFN_B200_H_
+#define CPFN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CPFN_OK 0
+#define CPFN_EINVAL (-1)   /* bad size / null pointer / unsupported shape */
+#define CPFN_ELAUNCH (-2)  /* CUDA reported a launch error (see cpfn_last_cuda_error) */
+#define CPFN_EWORKSPACE (-3) /* workspace missing or too small */
+
+#if defined(__GNUC__)
+#define CPFN_API __attribute__((visibility("default")))
+#else
+#define CPFN_API
+#endif
+
+typedef void *cpfn_stream_t;
+
+/* Library identity / diagnostics. */
+CPFN_API int cpfn_version(void);                       /* 100 * major + minor */
+CPFN_API const char *cpfn_error_string(int code);
+CPFN_API const char *cpfn_last_cuda_error(void);       /* cudaGetErrorString of the last failure on this thread */
+CPFN_API int cpfn_sm_count(void);                      /* SMs of the current device (<0 on error) */
+
+/* ---------------------------------------------------------------------------
+ * The nine pointnet2 ops (drop-in for the pybind module `cuda_ops`).
+ * ------------------------------------------------------------------------- */
+
+/* Furthest point sampling.  Replaces farthest_point_sampling
+ * (src/sampling.cpp:65-86, kernel src/sampling_gpu.cu:63-159).
+ * xyz [B,N,3] f32 -> idx [B,nsamples] i32.  Bit-exact with the reference,
+ * including its tie-break (shared-memory tree order of a block of
+ * opt_n_threads(N) threads) and its skip of points with |p|^2 <= 1e-3.
+ * `workspace` is needed only when cpfn_fps_workspace_bytes(B,N) > 0. */
+CPFN_API size_t cpfn_fps_workspace_bytes(int B, int N);
+CPFN_API int cpfn_furthest_point_sampling(const float *xyz, int B, int N, int nsamples,
+                                 int32_t *idx, void *workspace,
+                                 size_t workspace_bytes, cpfn_stream_t stream);
+
+/* Ball query.  Replaces ball_query (src/ball_query.cpp:8-32, kernel
+ * src/ball_query_gpu.cu:9-44).  new_xyz [B,S,3], xyz [B,N,3] -> idx
+ * [B,S,nsample] i32: the first `nsample` points (ascending index) with
+ * d^2 < radius*radius, padded with the first hit; all zeros when no hit. */
+CPFN_API int cpfn_ball_query(const float *new_xyz, const float *xyz, int B, int N, int S,
+                    float radius, int nsample, int32_t *idx,
+                    cpfn_stream_t stream);
+
+/* Gather / group (+ gradients).  Replace gather_points(_grad)
+ * (src/sampling.cpp:15-64, src/sampling_gpu.cu:8-53) and group_points(_grad)
+ * (src/group_points.cpp:12-60, src/group_points_gpu.cu:8-74).
+ * points [B,C,N]; idx [B,M] or [B,S,K]; out [B,C,M] or [B,C,S,K].
+ * The *_grad entry points OVERWRITE grad_points [B,C,N] (zero + scatter-add). */
+CPFN_API int cpfn_gather_points(const float *points, const int32_t *idx, int B, int C,
+                       int N, int M, float *out, cpfn_stream_t stream);
+CPFN_API int cpfn_gather_points_grad(const float *grad_out, const int32_t *idx, int B,
+                            int C, int N, int M, float *grad_points,
+                            cpfn_stream_t stream);
+CPFN_API int cpfn_group_points(const float *points, const int32_t *idx, int B, int C,
+                      int N, int S, int K, float *out, cpfn_stream_t stream);
+CPFN_API int cpfn_group_points_grad(const float *grad_out, const int32_t *idx, int B,
+                           int C, int N, int S, int K, float *grad_points,
+                           cpfn_stream_t stream);
+
+/* Three nearest neighbours.  Replaces three_nn (src/interpolate.cpp:14-40,
+ * kernel src/interpolate_gpu.cu:9-59).  unknown [B,n,3], known [B,m,3] ->
+ * dist2 [B,n,3] f32 (SQUARED distances), idx [B,n,3] i32; ties go to the
+ * lower index; m < 3 leaves index 0 / dist2 = +inf in the unused slots. */
+CPFN_API int cpfn_three_nn(const float *unknown, const float *known, int B, int n, int m,
+                  float *dist2, int32_t *idx, cpfn_stream_t stream);
+
+/* Three-point weighted sum (+ gradient).  Replace three_weighted_sum(_grad)
+ * (src/interpolate.cpp:42-99, kernels src/interpolate_gpu.cu:72-143).
+ * points [B,C,M], idx/weight [B,n,3] -> out [B,C,n];
+ * grad: grad_out [B,C,n] -> grad_points [B,C,M] (overwritten). */
+CPFN_API int cpfn_three_weighted_sum(const float *points, const int32_t *idx,
+                            const float *weight, int B, int C, int M, int n,
+                            float *out, cpfn_stream_t stream);
+CPFN_API int cpfn_three_weighted_sum_grad(const float *grad_out, const int32_t *idx,
+                                 const float *weight, int B, int C, int n,
+                                 int M, float *grad_points,
+                                 cpfn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPFN_B200_H_ */

@@ -1,0 +1,281 @@
+/*
+ * cpfn_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * A plain-C, CPU restatement of the nine pointnet2 index/gather kernels of
+ * erictuanle/CPFN, written to be the bit-exact checker for the sm_100a CUDA
+ * path in cpfn_b200/csrc.  Only tests/, __graft_entry__.smoke() and the
+ * cpu_baseline / --impl reference legs of bench.py may load this library.
+ *
+ * Each function cites the reference kernel it follows (paths relative to the
+ * reference tree, PointNet2/pointnet2_ops/cuda_ops/).  The arithmetic that
+ * decides an index is restated with the exact rounding sequence the reference
+ * SASS uses on sm_100a: dx = a - b (FADD), dx*dx (FMUL), then two FFMA, i.e.
+ *     d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx))
+ * Compile with -ffp-contract=off so the compiler adds no contraction of its
+ * own (see oracle/Makefile).
+ *
+ * Parity pin: the reference has no golden vectors for these ops (it has no
+ * tests at all for them).  The pin is tests/golden/ref_cuda_ops_*.npz, which
+ * holds outputs of the UNMODIFIED reference kernels (oracle/_ref, built from
+ * /root/reference by oracle/build_ref.py) run on a B200 by
+ * tests/golden/make_ref_cuda_ops_golden.py.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* include/cuda_utils.h:13-19 -- opt_n_threads(): 2^floor(log2 n) clamped to
+ * [1, 512], with the floor taken through double log()/log(2.0) exactly as the
+ * reference host code does. */
+int cpfn_oracle_opt_n_threads(int work_size) {
+  const int pow_2 = (int)(log((double)work_size) / log(2.0));
+  int t = 1 << pow_2;
+  if (t > 512) t = 512;
+  if (t < 1) t = 1;
+  return t;
+}
+
+static inline float sqdist3(float ax, float ay, float az, float bx, float by,
+                            float bz) {
+  const float dx = ax - bx, dy = ay - by, dz = az - bz;
+  return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+}
+
+/* src/sampling_gpu.cu:63-159 (kernel) + src/sampling.cpp:65-86 (temp = 1e10,
+ * output zero-initialised).  The block of T threads is simulated literally:
+ * thread t scans k = t, t+T, ...; the shared-memory tree keeps the LOWER slot
+ * on ties (strict '>').  xyz: [b, n, 3]; idx: [b, m]. */
+void cpfn_oracle_fps(int b, int n, int m, const float *xyz, int32_t *idx) {
+  if (m <= 0 || n <= 0) return;
+  const int T = cpfn_oracle_opt_n_threads(n);
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int bi = 0; bi < b; ++bi) {
+    const float *p = xyz + (size_t)bi * n * 3;
+    int32_t *out = idx + (size_t)bi * m;
+    float *temp = (float *)malloc(sizeof(float) * (size_t)n);
+    float *dists = (float *)malloc(sizeof(float) * (size_t)T);
+    int *dists_i = (int *)malloc(sizeof(int) * (size_t)T);
+    for (int k = 0; k < n; ++k) temp[k] = 1e10f; /* sampling.cpp:73-75 */
+    int old = 0;
+    out[0] = 0; /* :76-77 */
+    for (int j = 1; j < m; ++j) {
+      const float x1 = p[old * 3 + 0], y1 = p[old * 3 + 1], z1 = p[old * 3 + 2];
+      for (int tid = 0; tid < T; ++tid) {
+        int besti = 0;
+        float best = -1.0f;
+        for (int k = tid; k < n; k += T) {
+          const float x2 = p[k * 3 + 0], y2 = p[k * 3 + 1], z2 = p[k * 3 + 2];
+          const float mag = fmaf(z2, z2, fmaf(y2, y2, x2 * x2));
+          if ((double)mag <= 1e-3) continue; /* :90-91, double literal */
+          const float d = sqdist3(x2, y2, z2, x1, y1, z1);
+          const float d2 = fminf(d, temp[k]);
+          temp[k] = d2;
+          if (d2 > best) { /* :96-97 */
+            besti = k;
+            best = d2;
+          }
+        }
+        dists[tid] = best;
+        dists_i[tid] = besti;
+      }
+      for (int s = T / 2; s >= 1; s >>= 1) { /* :102-155, __update :53-59 */
+        for (int tid = 0; tid < s; ++tid) {
+          const float v1 = dists[tid], v2 = dists[tid + s];
+          const int i1 = dists_i[tid], i2 = dists_i[tid + s];
+          dists[tid] = fmaxf(v1, v2);
+          dists_i[tid] = v2 > v1 ? i2 : i1;
+        }
+      }
+      old = dists_i[0];
+      out[j] = old;
+    }
+    free(temp);
+    free(dists);
+    free(dists_i);
+  }
+}
+
+/* src/ball_query_gpu.cu:9-44 + src/ball_query.cpp:19-21 (zeros when no hit).
+ * new_xyz: [b, m, 3]; xyz: [b, n, 3]; idx: [b, m, nsample]. */
+void cpfn_oracle_ball_query(int b, int n, int m, float radius, int nsample,
+                            const float *new_xyz, const float *xyz,
+                            int32_t *idx) {
+  const float radius2 = radius * radius; /* :22, fp32 product */
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int bi = 0; bi < b; ++bi) {
+    for (int j = 0; j < m; ++j) {
+      const float *p = xyz + (size_t)bi * n * 3;
+      const float *q = new_xyz + ((size_t)bi * m + j) * 3;
+      int32_t *o = idx + ((size_t)bi * m + j) * nsample;
+      for (int l = 0; l < nsample; ++l) o[l] = 0;
+      const float qx = q[0], qy = q[1], qz = q[2];
+      int cnt = 0;
+      for (int k = 0; k < n && cnt < nsample; ++k) {
+        const float d2 = sqdist3(qx, qy, qz, p[k * 3], p[k * 3 + 1], p[k * 3 + 2]);
+        if (d2 < radius2) {
+          if (cnt == 0)
+            for (int l = 0; l < nsample; ++l) o[l] = k;
+          o[cnt] = k;
+          ++cnt;
+        }
+      }
+    }
+  }
+}
+
+/* src/interpolate_gpu.cu:9-59.  best* are doubles initialised to 1e40 and the
+ * float distance is promoted for the compare; stores narrow back to float
+ * (1e40 -> +inf).  unknown: [b, n, 3]; known: [b, m, 3]. */
+void cpfn_oracle_three_nn(int b, int n, int m, const float *unknown,
+                          const float *known, float *dist2, int32_t *idx) {
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int bi = 0; bi < b; ++bi) {
+    for (int j = 0; j < n; ++j) {
+      const float *kn = known + (size_t)bi * m * 3;
+      const float *u = unknown + ((size_t)bi * n + j) * 3;
+      const float ux = u[0], uy = u[1], uz = u[2];
+      double best1 = 1e40, best2 = 1e40, best3 = 1e40;
+      int besti1 = 0, besti2 = 0, besti3 = 0;
+      for (int k = 0; k < m; ++k) {
+        const float d = sqdist3(ux, uy, uz, kn[k * 3], kn[k * 3 + 1], kn[k * 3 + 2]);
+        if (d < best1) {
+          best3 = best2; besti3 = besti2;
+          best2 = best1; besti2 = besti1;
+          best1 = d;     besti1 = k;
+        } else if (d < best2) {
+          best3 = best2; besti3 = besti2;
+          best2 = d;     besti2 = k;
+        } else if (d < best3) {
+          best3 = d;     besti3 = k;
+        }
+      }
+      float *od = dist2 + ((size_t)bi * n + j) * 3;
+      int32_t *oi = idx + ((size_t)bi * n + j) * 3;
+      od[0] = (float)best1; od[1] = (float)best2; od[2] = (float)best3;
+      oi[0] = besti1; oi[1] = besti2; oi[2] = besti3;
+    }
+  }
+}
+
+/* src/interpolate_gpu.cu:72-101: out = p1*w1 + p2*w2 + p3*w3 contracted to
+ * fma(p3, w3, fma(p2, w2, p1*w1)).  points: [b, c, m]; idx, weight:
+ * [b, n, 3]; out: [b, c, n]. */
+void cpfn_oracle_three_weighted_sum(int b, int c, int m, int n,
+                                    const float *points, const int32_t *idx,
+                                    const float *weight, float *out) {
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int bi = 0; bi < b; ++bi) {
+    for (int l = 0; l < c; ++l) {
+      const float *pt = points + ((size_t)bi * c + l) * m;
+      const int32_t *id = idx + (size_t)bi * n * 3;
+      const float *w = weight + (size_t)bi * n * 3;
+      float *o = out + ((size_t)bi * c + l) * n;
+      for (int j = 0; j < n; ++j) {
+        const float p1 = pt[id[j * 3 + 0]], p2 = pt[id[j * 3 + 1]],
+                    p3 = pt[id[j * 3 + 2]];
+        o[j] = fmaf(p3, w[j * 3 + 2], fmaf(p2, w[j * 3 + 1], p1 * w[j * 3 + 0]));
+      }
+    }
+  }
+}
+
+/* src/interpolate_gpu.cu:116-143: three atomicAdds per (c, j).  The reference
+ * order of the float additions is nondeterministic; this restatement adds in
+ * ascending j (compare with a tolerance, not bit-exactly).  grad_out:
+ * [b, c, n]; grad_points: [b, c, m], overwritten. */
+void cpfn_oracle_three_weighted_sum_grad(int b, int c, int n, int m,
+                                         const float *grad_out,
+                                         const int32_t *idx,
+                                         const float *weight,
+                                         float *grad_points) {
+  memset(grad_points, 0, sizeof(float) * (size_t)b * c * m);
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int bi = 0; bi < b; ++bi) {
+    for (int l = 0; l < c; ++l) {
+      const float *go = grad_out + ((size_t)bi * c + l) * n;
+      const int32_t *id = idx + (size_t)bi * n * 3;
+      const float *w = weight + (size_t)bi * n * 3;
+      float *gp = grad_points + ((size_t)bi * c + l) * m;
+      for (int j = 0; j < n; ++j) {
+        gp[id[j * 3 + 0]] += go[j] * w[j * 3 + 0];
+        gp[id[j * 3 + 1]] += go[j] * w[j * 3 + 1];
+        gp[id[j * 3 + 2]] += go[j] * w[j * 3 + 2];
+      }
+    }
+  }
+}
+
+/* src/sampling_gpu.cu:8-20.  points: [b, c, n]; idx: [b, m]; out: [b, c, m]. */
+void cpfn_oracle_gather_points(int b, int c, int n, int m, const float *points,
+                               const int32_t *idx, float *out) {
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int i = 0; i < b; ++i)
+    for (int l = 0; l < c; ++l)
+      for (int j = 0; j < m; ++j)
+        out[((size_t)i * c + l) * m + j] =
+            points[((size_t)i * c + l) * n + idx[(size_t)i * m + j]];
+}
+
+/* src/sampling_gpu.cu:32-45 (atomicAdd scatter; sequential order here). */
+void cpfn_oracle_gather_points_grad(int b, int c, int n, int m,
+                                    const float *grad_out, const int32_t *idx,
+                                    float *grad_points) {
+  memset(grad_points, 0, sizeof(float) * (size_t)b * c * n);
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int i = 0; i < b; ++i)
+    for (int l = 0; l < c; ++l)
+      for (int j = 0; j < m; ++j)
+        grad_points[((size_t)i * c + l) * n + idx[(size_t)i * m + j]] +=
+            grad_out[((size_t)i * c + l) * m + j];
+}
+
+/* src/group_points_gpu.cu:8-28.  points: [b, c, n]; idx: [b, np, ns];
+ * out: [b, c, np, ns]. */
+void cpfn_oracle_group_points(int b, int c, int n, int npoints, int nsample,
+                              const float *points, const int32_t *idx,
+                              float *out) {
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int i = 0; i < b; ++i)
+    for (int l = 0; l < c; ++l)
+      for (int j = 0; j < npoints; ++j)
+        for (int k = 0; k < nsample; ++k)
+          out[(((size_t)i * c + l) * npoints + j) * nsample + k] =
+              points[((size_t)i * c + l) * n +
+                     idx[((size_t)i * npoints + j) * nsample + k]];
+}
+
+/* src/group_points_gpu.cu:43-64 (atomicAdd scatter; sequential order here). */
+void cpfn_oracle_group_points_grad(int b, int c, int n, int npoints,
+                                   int nsample, const float *grad_out,
+                                   const int32_t *idx, float *grad_points) {
+  memset(grad_points, 0, sizeof(float) * (size_t)b * c * n);
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int i = 0; i < b; ++i)
+    for (int l = 0; l < c; ++l)
+      for (int j = 0; j < npoints; ++j)
+        for (int k = 0; k < nsample; ++k)
+          grad_points[((size_t)i * c + l) * n +
+                      idx[((size_t)i * npoints + j) * nsample + k]] +=
+              grad_out[(((size_t)i * c + l) * npoints + j) * nsample + k];
+}
+
+void cpfn_oracle_set_threads(int t) {
+#ifdef _OPENMP
+  omp_set_num_threads(t > 0 ? t : 1);
+#else
+  (void)t;
+#endif
+}
+
+int cpfn_oracle_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}

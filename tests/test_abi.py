@@ -1,0 +1,75 @@
+"""The C-ABI library loads and exports every symbol include/cpfn_b200.h declares
+(no compute calls: runs without a GPU)."""
+import ctypes
+import subprocess
+
+import pytest
+import torch
+
+from cpfn_b200 import _lib, cuda_ops
+
+
+def test_header_and_signature_table_agree(built_lib):
+    assert set(_lib.header_symbols()) == set(_lib.SIGNATURES)
+    assert len(_lib.header_symbols()) >= 14
+
+
+def test_library_exports_every_header_symbol(built_lib):
+    out = subprocess.run(["nm", "-D", "--defined-only", built_lib], capture_output=True, text=True,
+                         check=True).stdout
+    exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
+    missing = set(_lib.header_symbols()) - exported
+    assert not missing, missing
+
+
+def test_library_loads_and_reports_version(built_lib):
+    L = _lib.lib()
+    assert L.cpfn_version() >= 100
+    assert L.cpfn_error_string(0) == b"ok"
+    assert b"workspace" in L.cpfn_error_string(-3)
+    assert L.cpfn_fps_workspace_bytes(4, 8192) == 0
+    assert L.cpfn_fps_workspace_bytes(2, 100000) == 2 * 100000 * 4
+
+
+def test_no_torch_types_in_abi(built_lib):
+    out = subprocess.run(["nm", "-D", "-C", built_lib], capture_output=True, text=True,
+                         check=True).stdout
+    assert "at::" not in out and "c10::" not in out and "torch::" not in out
+
+
+def test_library_is_sm100a_only(built_lib):
+    out = subprocess.run(["cuobjdump", "-lelf", built_lib], capture_output=True, text=True).stdout
+    archs = {ln.rsplit(".", 2)[-2] for ln in out.splitlines() if ln.strip().endswith(".cubin")}
+    assert archs == {"sm_100a"}, archs
+
+
+@pytest.mark.parametrize("call", [
+    lambda: cuda_ops.farthest_point_sampling(torch.zeros(1, 8, 3), 4),
+    lambda: cuda_ops.ball_query(torch.zeros(1, 2, 3), torch.zeros(1, 8, 3), 0.2, 4),
+    lambda: cuda_ops.three_nn(torch.zeros(1, 8, 3), torch.zeros(1, 4, 3)),
+    lambda: cuda_ops.gather_points(torch.zeros(1, 2, 8), torch.zeros(1, 4, dtype=torch.int32)),
+    lambda: cuda_ops.group_points(torch.zeros(1, 2, 8), torch.zeros(1, 4, 2, dtype=torch.int32)),
+    lambda: cuda_ops.three_weighted_sum(torch.zeros(1, 2, 8), torch.zeros(1, 4, 3, dtype=torch.int32),
+                                        torch.zeros(1, 4, 3)),
+])
+def test_cpu_tensors_are_rejected_like_the_reference(call):
+    # src/*.cpp: TORCH_CHECK(false, "CPU not supported")
+    with pytest.raises(RuntimeError, match="CPU not supported"):
+        call()
+
+
+def test_dtype_and_layout_checks_match_reference_messages():
+    # include/utils.h:5-25
+    with pytest.raises(RuntimeError, match="must be a float tensor"):
+        cuda_ops.farthest_point_sampling(torch.zeros(1, 8, 3, dtype=torch.float64), 4)
+    with pytest.raises(RuntimeError, match="must be an int tensor"):
+        cuda_ops.gather_points(torch.zeros(1, 2, 8), torch.zeros(1, 4, dtype=torch.int64))
+    with pytest.raises(RuntimeError, match="must be a contiguous tensor"):
+        cuda_ops.farthest_point_sampling(torch.zeros(1, 3, 8).permute(0, 2, 1), 4)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
+        _lib.lib()

@@ -1,0 +1,191 @@
+"""GPU parity of the nine pointnet2 ops: CUDA path (through the C ABI) vs the C
+oracle, vs the committed golden vectors of the reference kernels, and -- when
+oracle/_ref is present -- vs the reference kernels live on the same device.
+Integer outputs and three_nn distances must be bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from cpfn_b200 import cuda_ops, synth
+from tests.golden import cases
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "ref_cuda_ops.npz")
+
+
+def _t(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def _fps(dev):
+    return lambda xyz, m: cuda_ops.farthest_point_sampling(_t(xyz, dev), m).cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def golden():
+    if not os.path.exists(GOLDEN):
+        pytest.skip("golden vectors not generated yet")
+    return np.load(GOLDEN)
+
+
+@pytest.fixture(scope="module")
+def ref_ext():
+    from oracle import build_ref
+    mod = build_ref.load_module()
+    if mod is None:
+        pytest.skip("oracle/_ref/ref_cuda_ops.so not present")
+    return mod
+
+
+FPS_SIZES = [(1, 1), (2, 2), (7, 7), (31, 31), (32, 8), (33, 33), (63, 40), (64, 64), (100, 64),
+             (259, 128), (511, 100), (512, 128), (513, 128), (1000, 300), (1023, 64), (1024, 256),
+             (1025, 64), (2048, 128), (3000, 100), (4096, 512), (5000, 64), (8192, 512),
+             (8193, 32), (12000, 64), (16384, 32), (16385, 24), (40000, 16)]
+
+
+@pytest.mark.parametrize("n,m", FPS_SIZES)
+def test_fps_bit_exact_vs_oracle(cuda_dev, oracle_ops, n, m):
+    for kind in ("uniform", "lattice"):
+        xyz = (synth.uniform_cloud(3, n, seed=n) if kind == "uniform"
+               else synth.lattice_cloud(3, n, seed=n, pitch=8))
+        got = cuda_ops.farthest_point_sampling(_t(xyz, cuda_dev), m).cpu().numpy()
+        np.testing.assert_array_equal(got, oracle_ops.farthest_point_sampling(xyz, m), err_msg=kind)
+
+
+def test_fps_full_size_batch16(cuda_dev, oracle_ops):
+    P = synth.shape_batch(16, 8192, seed=1235)[0]
+    got = cuda_ops.farthest_point_sampling(_t(P, cuda_dev), 512).cpu().numpy()
+    np.testing.assert_array_equal(got, oracle_ops.farthest_point_sampling(P, 512))
+    # size-independent property: indices are distinct and start at 0
+    assert (got[:, 0] == 0).all()
+    assert all(len(set(r.tolist())) == 512 for r in got)
+
+
+def test_fps_skip_rule_and_degenerate(cuda_dev, oracle_ops):
+    xyz = np.full((2, 100, 3), 0.001, dtype=np.float32)  # everything skipped
+    assert (cuda_ops.farthest_point_sampling(_t(xyz, cuda_dev), 9).cpu().numpy() == 0).all()
+    xyz = synth.uniform_cloud(2, 2000, seed=5) * np.float32(0.05)  # most points inside the skip ball
+    got = cuda_ops.farthest_point_sampling(_t(xyz, cuda_dev), 200).cpu().numpy()
+    np.testing.assert_array_equal(got, oracle_ops.farthest_point_sampling(xyz, 200))
+    dup = np.tile(synth.uniform_cloud(1, 4, seed=1), (1, 16, 1))  # m > distinct points
+    got = cuda_ops.farthest_point_sampling(_t(dup, cuda_dev), 30).cpu().numpy()
+    np.testing.assert_array_equal(got, oracle_ops.farthest_point_sampling(dup, 30))
+
+
+def test_fps_empty(cuda_dev):
+    out = cuda_ops.farthest_point_sampling(torch.zeros(0, 16, 3, device=cuda_dev), 4)
+    assert out.shape == (0, 4)
+    out = cuda_ops.farthest_point_sampling(torch.zeros(2, 16, 3, device=cuda_dev), 0)
+    assert out.shape == (2, 0)
+
+
+def test_ball_query_bit_exact_vs_oracle(cuda_dev, oracle_ops):
+    for name, (q, xyz, r, k) in cases.ball_cases(oracle_ops.farthest_point_sampling).items():
+        got = cuda_ops.ball_query(_t(q, cuda_dev), _t(xyz, cuda_dev), r, k).cpu().numpy()
+        np.testing.assert_array_equal(got, oracle_ops.ball_query(q, xyz, r, k), err_msg=name)
+
+
+@pytest.mark.parametrize("n,s,k,r", [(1, 1, 1, 1.0), (5, 5, 8, 0.5), (33, 7, 3, 0.3), (700, 129, 17, 0.2),
+                                     (8192, 512, 64, 0.2), (9000, 40, 64, 0.1), (20000, 300, 128, 0.08),
+                                     (30000, 16, 64, 0.01)])
+def test_ball_query_sizes(cuda_dev, oracle_ops, n, s, k, r):
+    xyz = synth.uniform_cloud(2, n, seed=n + s)
+    q = xyz[:, ::max(1, n // s)][:, :s].copy()
+    got = cuda_ops.ball_query(_t(q, cuda_dev), _t(xyz, cuda_dev), r, k).cpu().numpy()
+    np.testing.assert_array_equal(got, oracle_ops.ball_query(q, xyz, r, k))
+
+
+def test_ball_query_full_size_property(cuda_dev, oracle_ops):
+    P = synth.shape_batch(16, 8192, seed=1235)[0]
+    Pd = _t(P, cuda_dev)
+    fidx = cuda_ops.farthest_point_sampling(Pd, 512)
+    q = torch.gather(Pd, 1, fidx.long().unsqueeze(-1).expand(-1, -1, 3)).contiguous()
+    got = cuda_ops.ball_query(q, Pd, 0.2, 64)
+    np.testing.assert_array_equal(got.cpu().numpy(), oracle_ops.ball_query(q.cpu().numpy(), P, 0.2, 64))
+    # properties: every returned point is inside the ball; rows ascend until the padding starts
+    nb = torch.gather(Pd.unsqueeze(1).expand(-1, 512, -1, -1), 2,
+                      got.long().unsqueeze(-1).expand(-1, -1, -1, 3))
+    assert (((nb - q.unsqueeze(2)) ** 2).sum(-1) < 0.2 * 0.2 + 1e-6).all()
+
+
+def test_three_nn_bit_exact_vs_oracle(cuda_dev, oracle_ops):
+    for name, (u, kn) in cases.three_nn_cases(oracle_ops.farthest_point_sampling).items():
+        d2, idx = cuda_ops.three_nn(_t(u, cuda_dev), _t(kn, cuda_dev))
+        rd, ri = oracle_ops.three_nn(u, kn)
+        np.testing.assert_array_equal(idx.cpu().numpy(), ri, err_msg=name)
+        np.testing.assert_array_equal(d2.cpu().numpy(), rd, err_msg=name)
+
+
+@pytest.mark.parametrize("n,m", [(1, 1), (10, 2), (300, 3), (8192, 512), (1000, 2049), (513, 5000)])
+def test_three_nn_sizes(cuda_dev, oracle_ops, n, m):
+    u = synth.uniform_cloud(2, n, seed=n)
+    kn = synth.lattice_cloud(2, m, seed=m, pitch=10)
+    d2, idx = cuda_ops.three_nn(_t(u, cuda_dev), _t(kn, cuda_dev))
+    rd, ri = oracle_ops.three_nn(u, kn)
+    np.testing.assert_array_equal(idx.cpu().numpy(), ri)
+    np.testing.assert_array_equal(d2.cpu().numpy(), rd)
+
+
+def test_weighted_sum_gather_group_vs_oracle(cuda_dev, oracle_ops):
+    z = cases.interp_inputs()
+    pts, idx, w, g = (_t(z[k], cuda_dev) for k in ("pts", "idx", "w", "g"))
+    np.testing.assert_array_equal(cuda_ops.three_weighted_sum(pts, idx, w).cpu().numpy(),
+                                  oracle_ops.three_weighted_sum(z["pts"], z["idx"], z["w"]))
+    # scatter-adds: float atomics, order differs -> tolerance 1e-5 relative to the row scale
+    np.testing.assert_allclose(cuda_ops.three_weighted_sum_grad(g, idx, w, z["M"]).cpu().numpy(),
+                               oracle_ops.three_weighted_sum_grad(z["g"], z["idx"], z["w"], z["M"]),
+                               rtol=1e-5, atol=1e-5)
+    gi = np.ascontiguousarray(z["idx"][:, :, 0])
+    np.testing.assert_array_equal(cuda_ops.gather_points(pts, _t(gi, cuda_dev)).cpu().numpy(),
+                                  oracle_ops.gather_points(z["pts"], gi))
+    np.testing.assert_allclose(cuda_ops.gather_points_grad(g, _t(gi, cuda_dev), z["M"]).cpu().numpy(),
+                               oracle_ops.gather_points_grad(z["g"], gi, z["M"]), rtol=1e-5, atol=1e-5)
+    gidx, gg = _t(z["gidx"], cuda_dev), _t(z["gg"], cuda_dev)
+    np.testing.assert_array_equal(cuda_ops.group_points(pts, gidx).cpu().numpy(),
+                                  oracle_ops.group_points(z["pts"], z["gidx"]))
+    np.testing.assert_allclose(cuda_ops.group_points_grad(gg, gidx, z["M"]).cpu().numpy(),
+                               oracle_ops.group_points_grad(z["gg"], z["gidx"], z["M"]),
+                               rtol=1e-5, atol=1e-5)
+
+
+def test_against_golden_reference_outputs(cuda_dev, golden):
+    for name, (xyz, m) in cases.fps_cases().items():
+        got = cuda_ops.farthest_point_sampling(_t(xyz, cuda_dev), m).cpu().numpy()
+        np.testing.assert_array_equal(got, golden["fps/" + name].astype(np.int32), err_msg=name)
+    for name, (q, xyz, r, k) in cases.ball_cases(_fps(cuda_dev)).items():
+        got = cuda_ops.ball_query(_t(q, cuda_dev), _t(xyz, cuda_dev), r, k).cpu().numpy()
+        np.testing.assert_array_equal(got, golden["ball/" + name].astype(np.int32), err_msg=name)
+    for name, (u, kn) in cases.three_nn_cases(_fps(cuda_dev)).items():
+        d2, idx = cuda_ops.three_nn(_t(u, cuda_dev), _t(kn, cuda_dev))
+        np.testing.assert_array_equal(idx.cpu().numpy(), golden["nn_idx/" + name].astype(np.int32))
+        np.testing.assert_array_equal(d2.cpu().numpy(), golden["nn_d2/" + name])
+    z = cases.interp_inputs()
+    pts, idx, w = (_t(z[k], cuda_dev) for k in ("pts", "idx", "w"))
+    np.testing.assert_array_equal(cuda_ops.three_weighted_sum(pts, idx, w).cpu().numpy(), golden["tws"])
+
+
+def test_live_against_reference_extension(cuda_dev, ref_ext):
+    """Same device, same inputs, the UNMODIFIED reference kernels vs ours."""
+    P = _t(synth.shape_batch(16, 8192, seed=1235)[0], cuda_dev)
+    a = cuda_ops.farthest_point_sampling(P, 512)
+    b = ref_ext.farthest_point_sampling(P, 512)
+    assert torch.equal(a, b)
+    q = torch.gather(P, 1, a.long().unsqueeze(-1).expand(-1, -1, 3)).contiguous()
+    assert torch.equal(cuda_ops.ball_query(q, P, 0.2, 64), ref_ext.ball_query(q, P, 0.2, 64))
+    d2a, ia = cuda_ops.three_nn(P, q)
+    d2b, ib = ref_ext.three_nn(P, q)
+    assert torch.equal(ia, ib) and torch.equal(d2a, d2b)
+    feats = torch.randn(16, 32, 512, device=cuda_dev)
+    w = torch.rand(16, 8192, 3, device=cuda_dev)
+    assert torch.equal(cuda_ops.three_weighted_sum(feats, ia, w), ref_ext.three_weighted_sum(feats, ib, w))
+    g = torch.randn(16, 32, 8192, device=cuda_dev)
+    torch.testing.assert_close(cuda_ops.three_weighted_sum_grad(g, ia, w, 512),
+                               ref_ext.three_weighted_sum_grad(g, ib, w, 512), rtol=1e-4, atol=1e-4)
+    gi = cuda_ops.ball_query(q, P, 0.2, 64)
+    f2 = torch.randn(16, 8, 8192, device=cuda_dev)
+    assert torch.equal(cuda_ops.group_points(f2, gi), ref_ext.group_points(f2, gi))
+    assert torch.equal(cuda_ops.gather_points(f2, a), ref_ext.gather_points(f2, a))
+    lat = _t(synth.lattice_cloud(4, 5000, seed=9, pitch=12), cuda_dev)
+    assert torch.equal(cuda_ops.farthest_point_sampling(lat, 700), ref_ext.farthest_point_sampling(lat, 700))
