@@ -3,7 +3,7 @@
 // Semantics (bit-exact with PointNet2/pointnet2_ops/cuda_ops/src/
 // ball_query_gpu.cu:9-44, zero-init from src/ball_query.cpp:19-21; SURVEY.md
 // appendix A.2): r2 = radius*radius in fp32; scan k ascending; a point is a hit
-// iff fma(dz,dz,fma(dy,dy,dx*dx)) < r2; output = first `nsample` hits in index
+// iff fma(dz,dz,fma(dx,dx,dy*dy)) < r2; output = first `nsample` hits in index
 // order, remaining slots padded with the first hit; no hit -> zeros.
 //
 // Design: the reference gives one THREAD a query and scans the cloud serially
@@ -119,7 +119,7 @@ extern "C" int cpfn_ball_query(const float *new_xyz, const float *xyz, int B, in
   const int qpb = kBqWarps * qpw;
   const int tile = N < kBqTile ? ((N + 31) & ~31) : kBqTile;
   const size_t smem = 3u * static_cast<size_t>(tile) * sizeof(float);
-  if (smem > 48 * 1024)
+  if (smem + 4096 > 48 * 1024)
     CPFN_CUDA_TRY(cudaFuncSetAttribute(ball_query_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        3 * kBqTile * static_cast<int>(sizeof(float))));

@@ -41,19 +41,20 @@ inline cudaStream_t as_stream(cpfn_stream_t s) {
 
 int sm_count();
 
-// Squared distance with the reference's rounding sequence:
-// FADD dx, FMUL dx*dx, FFMA dy, FFMA dz.  The _rn intrinsics pin the
-// sequence: nvcc neither contracts nor re-associates them.
+// Squared distance with the reference's rounding sequence, read off the SASS of
+// the reference kernels built for sm_100a: nvcc contracts x*x + y*y + z*z as
+// FMUL(y*y), FFMA(x,x,.), FFMA(z,z,.).  The _rn intrinsics pin the sequence:
+// nvcc neither contracts nor re-associates them.
 __device__ __forceinline__ float sqdist3(float ax, float ay, float az, float bx,
                                          float by, float bz) {
   const float dx = __fsub_rn(ax, bx);
   const float dy = __fsub_rn(ay, by);
   const float dz = __fsub_rn(az, bz);
-  return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+  return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
 }
 
 __device__ __forceinline__ float sqnorm3(float x, float y, float z) {
-  return __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)));
+  return __fmaf_rn(z, z, __fmaf_rn(x, x, __fmul_rn(y, y)));
 }
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }

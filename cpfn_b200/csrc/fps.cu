@@ -6,7 +6,7 @@
 //   * idx[0] = 0; running minimum `temp` starts at 1e10;
 //   * points with |p|^2 <= 1e-3 (double compare) are never updated and never
 //     selected;
-//   * d = fma(dz,dz,fma(dy,dy,dx*dx)), d2 = fminf(d, temp), argmax with strict
+//   * d = fma(dz,dz,fma(dx,dx,dy*dy)), d2 = fminf(d, temp), argmax with strict
 //     '>' over the reference's block of T = opt_n_threads(N) threads: among
 //     equal maxima the winner is the reference thread with the smallest
 //     bit-reversed id, then the smallest k inside that thread.
@@ -27,7 +27,6 @@
 namespace cpfn {
 namespace {
 
-constexpr int kMaxRegN = 8192;    // PPT <= 8 at 1024 threads: coords + temp in registers
 constexpr int kMaxSmemN = 16384;  // coords in shared memory (SoA), temp in registers
 
 __host__ __device__ __forceinline__ uint32_t fps_rank(uint32_t k, int log2T) {
@@ -183,7 +182,7 @@ int launch_cta(const float *xyz, int B, int N, int m, int log2T, int NT, int32_t
                cudaStream_t st) {
   const size_t smem = 3u * static_cast<size_t>((N + 31) & ~31) * sizeof(float);
   auto kern = fps_cta_kernel<PPT, REGS>;
-  if (smem > 48 * 1024)
+  if (smem + 1024 > 48 * 1024)  // static shared memory counts against the 48 KB default
     CPFN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem)));
   kern<<<B, NT, smem, st>>>(xyz, N, m, log2T, idx);

@@ -75,7 +75,7 @@ three_nn_kernel(const float *__restrict__ unknown, const float *__restrict__ kno
 constexpr int kColThreads = 256;
 constexpr int kChanTile = 16;
 
-// out[b,c,j] = fma(p3,w3, fma(p2,w2, p1*w1))   (interpolate_gpu.cu:98-99)
+// out[b,c,j] = fma(p3,w3, fma(p1,w1, p2*w2))   (interpolate_gpu.cu:98-99 as nvcc contracts it)
 __global__ void __launch_bounds__(kColThreads)
 three_weighted_sum_kernel(const float *__restrict__ points, const int32_t *__restrict__ idx,
                           const float *__restrict__ weight, int C, int M, int n,
@@ -89,8 +89,8 @@ three_weighted_sum_kernel(const float *__restrict__ points, const int32_t *__res
   const int c0 = blockIdx.y * kChanTile, c1 = min(C, c0 + kChanTile);
   for (int c = c0; c < c1; ++c) {
     const float *row = points + (static_cast<size_t>(b) * C + c) * M;
-    const float v = __fmaf_rn(__ldg(row + i3), w3, __fmaf_rn(__ldg(row + i2), w2,
-                                                           __fmul_rn(__ldg(row + i1), w1)));
+    const float v = __fmaf_rn(__ldg(row + i3), w3, __fmaf_rn(__ldg(row + i1), w1,
+                                                           __fmul_rn(__ldg(row + i2), w2)));
     out[(static_cast<size_t>(b) * C + c) * n + j] = v;
   }
 }

@@ -9,8 +9,12 @@
  * Each function cites the reference kernel it follows (paths relative to the
  * reference tree, PointNet2/pointnet2_ops/cuda_ops/).  The arithmetic that
  * decides an index is restated with the exact rounding sequence the reference
- * SASS uses on sm_100a: dx = a - b (FADD), dx*dx (FMUL), then two FFMA, i.e.
- *     d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx))
+ * SASS uses on sm_100a (cuobjdump -sass oracle/_ref/ref_cuda_ops.so): nvcc
+ * contracts  x*x + y*y + z*z  as FMUL on the MIDDLE product, then FFMA on the
+ * first, then FFMA on the last, i.e.
+ *     d2 = fmaf(dz, dz, fmaf(dx, dx, dy * dy))
+ * (SURVEY.md 2.2 states dx*dx first; the disassembly and the golden vectors
+ * say otherwise -- 14 % of three_nn distances differ by 1 ulp with that order.)
  * Compile with -ffp-contract=off so the compiler adds no contraction of its
  * own (see oracle/Makefile).
  *
@@ -43,7 +47,7 @@ int cpfn_oracle_opt_n_threads(int work_size) {
 static inline float sqdist3(float ax, float ay, float az, float bx, float by,
                             float bz) {
   const float dx = ax - bx, dy = ay - by, dz = az - bz;
-  return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+  return fmaf(dz, dz, fmaf(dx, dx, dy * dy));
 }
 
 /* src/sampling_gpu.cu:63-159 (kernel) + src/sampling.cpp:65-86 (temp = 1e10,
@@ -70,7 +74,7 @@ void cpfn_oracle_fps(int b, int n, int m, const float *xyz, int32_t *idx) {
         float best = -1.0f;
         for (int k = tid; k < n; k += T) {
           const float x2 = p[k * 3 + 0], y2 = p[k * 3 + 1], z2 = p[k * 3 + 2];
-          const float mag = fmaf(z2, z2, fmaf(y2, y2, x2 * x2));
+          const float mag = fmaf(z2, z2, fmaf(x2, x2, y2 * y2));
           if ((double)mag <= 1e-3) continue; /* :90-91, double literal */
           const float d = sqdist3(x2, y2, z2, x1, y1, z1);
           const float d2 = fminf(d, temp[k]);
@@ -162,8 +166,8 @@ void cpfn_oracle_three_nn(int b, int n, int m, const float *unknown,
   }
 }
 
-/* src/interpolate_gpu.cu:72-101: out = p1*w1 + p2*w2 + p3*w3 contracted to
- * fma(p3, w3, fma(p2, w2, p1*w1)).  points: [b, c, m]; idx, weight:
+/* src/interpolate_gpu.cu:72-101: out = p1*w1 + p2*w2 + p3*w3 contracted (same
+ * rule as above) to fma(p3, w3, fma(p1, w1, p2*w2)).  points: [b, c, m]; idx, weight:
  * [b, n, 3]; out: [b, c, n]. */
 void cpfn_oracle_three_weighted_sum(int b, int c, int m, int n,
                                     const float *points, const int32_t *idx,
@@ -178,7 +182,7 @@ void cpfn_oracle_three_weighted_sum(int b, int c, int m, int n,
       for (int j = 0; j < n; ++j) {
         const float p1 = pt[id[j * 3 + 0]], p2 = pt[id[j * 3 + 1]],
                     p3 = pt[id[j * 3 + 2]];
-        o[j] = fmaf(p3, w[j * 3 + 2], fmaf(p2, w[j * 3 + 1], p1 * w[j * 3 + 0]));
+        o[j] = fmaf(p3, w[j * 3 + 2], fmaf(p1, w[j * 3 + 0], p2 * w[j * 3 + 1]));
       }
     }
   }
