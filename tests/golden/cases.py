@@ -65,3 +65,48 @@ def interp_inputs():
     gidx = rng.integers(0, M, size=(B, 32, 8)).astype(np.int32)
     gg = rng.normal(size=(B, C, 32, 8)).astype(np.float32)
     return dict(pts=pts, idx=idx, w=w, g=g, gidx=gidx, gg=gg, M=M)
+
+
+def fitter_cases():
+    """name -> (P [B,N,3], W [B,N,K], X [B,N,3]).  `selfcheck` re-uses the seeds and
+    distributions of the reference's inline self-checks (SPFN/plane_fitter.py:30-39,
+    cylinder_fitter.py:51-63: np.random.seed(0), randn points, rand weights,
+    normalised randn normals) at a smaller batch."""
+    out = {}
+    rs = np.random.RandomState(0)
+    P = rs.randn(4, 1024, 3)
+    W = rs.rand(4, 1024, 12)
+    X = rs.randn(4, 1024, 3)
+    X = X / np.linalg.norm(X, axis=2, keepdims=True)
+    out["selfcheck"] = (P.astype(np.float32), W.astype(np.float32), X.astype(np.float32))
+    P, X, W, _ = synth.shape_batch(2, 2048, seed=31, k_slots=24)
+    out["shape_2048_k24"] = (P, W, X)
+    P, X, W, _ = synth.shape_batch(1, 8192, seed=1234, k_slots=24)   # BASELINE config 1
+    out["config1_8192_k24"] = (P, W, X)
+    P, X, W, I = synth.shape_batch(2, 4096, seed=33, k_slots=28)
+    hard = np.zeros_like(W)
+    np.put_along_axis(hard, W.argmax(2)[..., None], 1.0, axis=2)      # one-hot, slots >= 12 empty
+    out["onehot_4096_k28"] = (P, hard, X)
+    return out
+
+
+# synth.shape_cloud: instances 0-2 planes, 3-5 spheres, 6-8 cylinders, 9-11 cones.
+_TYPE_SLOTS = {"plane": (0, 3), "sphere": (3, 6), "cylinder": (6, 9), "cone": (9, 12)}
+
+
+def fit_mask(case, key, W):
+    """[B,K] mask of (cloud, slot) pairs on which parameter `key` is well-posed.
+
+    Fitting a cylinder or a cone to a plane patch (all normals equal) or a plane to a
+    sphere is rank-deficient: the reference returns an arbitrary member of a null
+    space there, so parity is asserted on the slots whose ground-truth primitive has
+    the type being fitted (every slot for the unstructured `selfcheck` case), and
+    never on slots without support."""
+    B, _, K = W.shape
+    live = W.sum(1) > 1.0
+    if case == "selfcheck":
+        return live
+    lo, hi = _TYPE_SLOTS[key.split("_")[0]]
+    m = np.zeros((B, K), dtype=bool)
+    m[:, lo:hi] = True
+    return m & live
