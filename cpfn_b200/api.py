@@ -1,0 +1,90 @@
+"""GlobalSPFN / LocalSPFN inference engine: the public entry point of the hot path.
+
+``GlobalSPFN.forward(P)`` = PointNet2 forward (FPS + ball query + SA / FP layers + heads,
+reference PointNet2/pn2_network.py:38-73) -> X normalised, W soft-maxed
+(Utils/training_utils.py:141-142) -> ``compute_parameters`` for the four primitive types
+(SPFN/losses_implementation.py:255-278).  ``run_host`` is the same call on HOST buffers
+(pinned staging, host<->device copies included) -- what bench.py reports as ``e2e``.
+"""
+import torch
+
+from . import cuda_ops
+from .pn2_network import PointNet2
+from .spfn import losses_implementation as L
+
+
+class GlobalSPFN:
+    def __init__(self, output_sizes=(3, 4, 28), device="cuda:0", classes=('plane', 'sphere', 'cylinder', 'cone')):
+        self.device = torch.device(device)
+        self.classes = list(classes)
+        self.model = PointNet2(dim_input=3, dim_pos=3, output_sizes=list(output_sizes)).to(self.device).eval()
+        for p in self.model.parameters():
+            p.requires_grad_(False)
+        self._pin = {}
+
+    def load_state_dict(self, sd, strict=True):
+        """Reference-layout state dict (training_SPFN.py:72-74 loads with strict=True)."""
+        out = self.model.load_state_dict(sd, strict=strict)
+        from . import fused
+        fused.invalidate(self.model)
+        return out
+
+    @torch.no_grad()
+    def forward(self, P, dropout=True, fit=True):
+        """P [B,N,3] float32 on the device.  Returns a dict: X [B,N,3] unit normals, T [B,N,n_types]
+        type logits, W [B,N,K] soft memberships, X_raw/T_raw/W_raw head outputs, l3_feats,
+        output_feat, sa1_fps (int32 [B,512]) and ``parameters`` (the reference's dictionary).
+        ``dropout=False`` replaces the reference's always-on dropout by the identity (parity runs)."""
+        m = self.model
+        x = P.transpose(2, 1)
+        pos = x[:, :3, :]
+        l1_pos, l1_feats = m.sa1(pos, None)
+        l2_pos, l2_feats = m.sa2(l1_pos, l1_feats)
+        _, l3_feats = m.sa3(l2_pos, l2_feats)
+        l4 = m.sfp1(l2_pos, None, l2_feats, l3_feats)
+        l5 = m.sfp2(l1_pos, l2_pos, l1_feats, l4)
+        l6 = m.sfp3(pos, l1_pos, None, l5)
+        feat = torch.relu(m.bn1(m.fc1(l6)))
+        if dropout:
+            feat = torch.nn.functional.dropout(feat, p=0.5)
+        heads = [fc(feat).transpose(1, 2) for fc in m.fc2]
+        out = {"X_raw": heads[0], "T_raw": heads[1], "W_raw": heads[2], "l3_feats": l3_feats,
+               "output_feat": feat, "l1_pos": l1_pos}
+        out["X"] = torch.nn.functional.normalize(heads[0], p=2, dim=2, eps=1e-12)
+        out["T"] = heads[1]
+        out["W"] = torch.softmax(heads[2], dim=2)
+        if fit:
+            out["parameters"] = L.compute_parameters(P, out["W"], out["X"], self.classes)
+        return out
+
+    def _pinned(self, name, shape, dtype):
+        t = self._pin.get(name)
+        if t is None or t.shape != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype, pin_memory=True)
+            self._pin[name] = t
+        return t
+
+    @torch.no_grad()
+    def run_host(self, P_host, dropout=True):
+        """P_host: CPU float32 [B,N,3] (pinned or pageable).  Copies it to the device, runs
+        forward + fitters, and returns HOST tensors: the parameter dictionary, per-point
+        instance labels (int32 [B,N], argmax of W), per-point type labels and unit normals --
+        what evaluation_globalSPFN.py:97-110 of the reference saves per shape.
+        Returns (results, h2d_bytes, d2h_bytes)."""
+        B, N, _ = P_host.shape
+        stage = self._pinned("P", P_host.shape, torch.float32)
+        stage.copy_(P_host)
+        P = stage.to(self.device, non_blocking=True)
+        out = self.forward(P, dropout=dropout)
+        res_dev = dict(out["parameters"])
+        res_dev["instance"] = torch.argmax(out["W"], dim=2).to(torch.int32)
+        res_dev["type"] = torch.argmax(out["T"], dim=2).to(torch.int32)
+        res_dev["normals"] = out["X"]
+        res, d2h = {}, 0
+        for k, v in res_dev.items():
+            h = self._pinned("out_" + k, v.shape, v.dtype)
+            h.copy_(v, non_blocking=True)
+            res[k] = h
+            d2h += v.numel() * v.element_size()
+        torch.cuda.current_stream(self.device).synchronize()
+        return res, P_host.numel() * 4, d2h

@@ -1,0 +1,530 @@
+// SPFN weighted total-least-squares primitive fitters for sm_100a: plane, sphere,
+// cylinder and cone parameters of every (cloud, instance slot) pair in ONE call.
+//
+// Semantics follow the reference fitters (paths relative to the reference tree):
+//   plane     SPFN/plane_fitter.py:9-17    -> SPFN/geometry_utils.py:74-84 (weighted_plane_fitting)
+//   sphere    SPFN/sphere_fitter.py:9-19   -> SPFN/geometry_utils.py:209-223, 121-142
+//   cylinder  SPFN/cylinder_fitter.py:10-28 (TLS on the normals, consistent frame
+//             SPFN/geometry_utils.py:8-27, 2-D circle fit)
+//   cone      SPFN/cone_fitter.py:12-36    (guarded LS apex, plane fit of the normals, half angle)
+//   TLS       SPFN/differentiable_tls.py:200-209 (last right-singular vector of sum w a a^T)
+// with their constants: division eps 1e-10, LS row weights
+// sqrt(max(w,1e-10)), condition-number cap 1e5, ridge 1e-8, acos clamp 1-1e-6, half-angle
+// clamp [1e-3, pi/2-1e-3].
+//
+// Design (not the reference's).  The reference tiles P and X K times ([B*K,N,3], 44 MB each
+// at B=16,K=28), materialises [B*K,N,3,3] outer products (132 MB, twice) and calls batched
+// SVD / solve.  Here nothing is tiled or materialised: three streaming passes over the
+// membership matrix W [B,N,K] (the only large operand) accumulate per-(b,k) weighted moments,
+// and three tiny solve kernels do the 3x3 / 2x2 eigen problems and linear solves in registers
+// (fp64 Jacobi).
+//   pass 1: sum w, sum w p, sum w |p|^2, sum w x, sum w x x^T, sum w' x x^T, sum w' x (p.x)
+//   solve1: means (rounded to fp32 like the reference's), cylinder axis, cone apex
+//   pass 2: centred moments about the per-slot means: S = sum w d d^T, S' = sum w' d d^T,
+//           sum w' d, third-order T' = sum w' d d d, Cx = sum w (x-mx)(x-mx)^T
+//   solve2: plane, sphere, cylinder (the 2-D circle fit is obtained by projecting the 3-D
+//           centred moments onto the cylinder frame -- no pass over the points is needed
+//           once the axis is known), cone axis
+//   pass 3: cone: sum w (dir.axis), sum w acos|dir.axis|;  solve3: sign fix, half angle.
+// (w' = max(w, 1e-10), d = p - mean.)  Thread t of a CTA owns slot k = t % K and point lane
+// g = t / K, so a warp reads W as one contiguous stream (coalesced, every byte used once);
+// point coordinates are staged once per CTA in shared memory as float4.  Each thread sums at
+// most 32 points in fp32, then flushes into fp64 accumulators; cross-thread and cross-CTA
+// combination is fp64 and deterministic (per-CTA partials, no atomics).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace cpfn {
+namespace {
+
+constexpr int kTlsThreads = 256;
+constexpr int kMaxCP = 1024;      // points staged per sub-chunk
+constexpr int kF1 = 23, kF2 = 31, kF3 = 2;
+constexpr int kFP = 32;           // padded feature stride of the partial arrays
+constexpr int kState = 24;        // doubles per (b,k)
+// state layout
+constexpr int ST_SW = 0, ST_DENOM = 1, ST_MU = 2, ST_M2 = 5, ST_MUX = 6, ST_CYLN = 9, ST_APEX = 12,
+              ST_S1 = 15, ST_CONEAX = 18;
+
+struct TlsGeom {
+  int G, ppt, CP, chunks, iters;
+};
+
+__host__ __device__ inline int imin(int a, int b) { return a < b ? a : b; }
+__host__ __device__ inline int imax(int a, int b) { return a > b ? a : b; }
+
+TlsGeom tls_geom(int B, int N, int K, int sms) {
+  TlsGeom g;
+  g.G = imax(1, kTlsThreads / K);
+  long long want = (static_cast<long long>(B) * N + 2LL * sms * g.G - 1) / (2LL * sms * g.G);
+  g.ppt = static_cast<int>(want < 8 ? 8 : (want > 32 ? 32 : want));
+  g.ppt = imin(g.ppt, imax(1, kMaxCP / g.G));
+  g.CP = g.G * g.ppt;
+  const int SC = (N + g.CP - 1) / g.CP;
+  const int cap = imax(1, (4 * sms + B - 1) / B);
+  g.chunks = imin(SC, cap);
+  g.iters = (SC + g.chunks - 1) / g.chunks;
+  g.chunks = (SC + g.iters - 1) / g.iters;
+  return g;
+}
+
+template <int PASS> struct NFeat { static constexpr int F = PASS == 1 ? kF1 : (PASS == 2 ? kF2 : kF3); };
+
+template <int PASS>
+__global__ void __launch_bounds__(kTlsThreads)
+tls_pass_kernel(const float *__restrict__ P, const float *__restrict__ X,
+                const float *__restrict__ W, const double *__restrict__ state,
+                double *__restrict__ part, int N, int K, int G, int CP, int iters, int chunks) {
+  constexpr int F = NFeat<PASS>::F;
+  extern __shared__ float4 s_pts[];          // [CP] positions (+ |p|^2), [CP] normals (+ p.x)
+  float4 *sp = s_pts, *sx = s_pts + CP;
+  const int b = blockIdx.y, chunk = blockIdx.x, t = threadIdx.x;
+  const bool active = t < G * K;
+  const int k = active ? t % K : 0, g = t / K;
+  const float *Pb = P + static_cast<size_t>(b) * N * 3;
+  const float *Xb = X ? X + static_cast<size_t>(b) * N * 3 : nullptr;
+  const float *Wb = W + static_cast<size_t>(b) * N * K;
+
+  float c0 = 0.f, c1 = 0.f, c2 = 0.f, e0 = 0.f, e1 = 0.f, e2 = 0.f;   // per-slot constants
+  if (PASS >= 2) {
+    const double *st = state + (static_cast<size_t>(b) * K + k) * kState;
+    if (PASS == 2) {
+      c0 = static_cast<float>(st[ST_MU]); c1 = static_cast<float>(st[ST_MU + 1]); c2 = static_cast<float>(st[ST_MU + 2]);
+      e0 = static_cast<float>(st[ST_MUX]); e1 = static_cast<float>(st[ST_MUX + 1]); e2 = static_cast<float>(st[ST_MUX + 2]);
+    } else {
+      c0 = static_cast<float>(st[ST_APEX]); c1 = static_cast<float>(st[ST_APEX + 1]); c2 = static_cast<float>(st[ST_APEX + 2]);
+      e0 = static_cast<float>(st[ST_CONEAX]); e1 = static_cast<float>(st[ST_CONEAX + 1]); e2 = static_cast<float>(st[ST_CONEAX + 2]);
+    }
+  }
+
+  float acc[F];
+  double dacc[F];
+#pragma unroll
+  for (int f = 0; f < F; ++f) { acc[f] = 0.f; dacc[f] = 0.0; }
+
+  for (int it = 0; it < iters; ++it) {
+    const int n0 = (chunk * iters + it) * CP;
+    if (n0 >= N) break;
+    const int cn = imin(CP, N - n0);
+    __syncthreads();
+    for (int i = t; i < cn; i += kTlsThreads) {
+      const float *p = Pb + static_cast<size_t>(n0 + i) * 3;
+      const float px = __ldg(p), py = __ldg(p + 1), pz = __ldg(p + 2);
+      float xx = 0.f, xy = 0.f, xz = 0.f;
+      if (Xb) {
+        const float *x = Xb + static_cast<size_t>(n0 + i) * 3;
+        xx = __ldg(x); xy = __ldg(x + 1); xz = __ldg(x + 2);
+      }
+      sp[i] = make_float4(px, py, pz, px * px + py * py + pz * pz);
+      sx[i] = make_float4(xx, xy, xz, px * xx + py * xy + pz * xz);
+    }
+    __syncthreads();
+    if (active) {
+      const float *wp = Wb + static_cast<size_t>(n0) * K + k;
+#pragma unroll 2
+      for (int j = g; j < cn; j += G) {
+        const float w = __ldg(wp + static_cast<size_t>(j) * K);
+        const float4 p = sp[j];
+        if (PASS == 1) {
+          const float4 x = sx[j];
+          const float wc = fmaxf(w, 1e-10f);
+          acc[0] += w;
+          acc[1] = fmaf(w, p.x, acc[1]); acc[2] = fmaf(w, p.y, acc[2]); acc[3] = fmaf(w, p.z, acc[3]);
+          acc[4] = fmaf(w, p.w, acc[4]);
+          const float wx = w * x.x, wy = w * x.y, wz = w * x.z;
+          acc[5] += wx; acc[6] += wy; acc[7] += wz;
+          acc[8] = fmaf(wx, x.x, acc[8]); acc[9] = fmaf(wx, x.y, acc[9]); acc[10] = fmaf(wx, x.z, acc[10]);
+          acc[11] = fmaf(wy, x.y, acc[11]); acc[12] = fmaf(wy, x.z, acc[12]); acc[13] = fmaf(wz, x.z, acc[13]);
+          const float vx = wc * x.x, vy = wc * x.y, vz = wc * x.z;
+          acc[14] = fmaf(vx, x.x, acc[14]); acc[15] = fmaf(vx, x.y, acc[15]); acc[16] = fmaf(vx, x.z, acc[16]);
+          acc[17] = fmaf(vy, x.y, acc[17]); acc[18] = fmaf(vy, x.z, acc[18]); acc[19] = fmaf(vz, x.z, acc[19]);
+          acc[20] = fmaf(vx, x.w, acc[20]); acc[21] = fmaf(vy, x.w, acc[21]); acc[22] = fmaf(vz, x.w, acc[22]);
+        } else if (PASS == 2) {
+          const float4 x = sx[j];
+          const float wc = fmaxf(w, 1e-10f);
+          const float dx = p.x - c0, dy = p.y - c1, dz = p.z - c2;
+          const float wx = w * dx, wy = w * dy, wz = w * dz;
+          acc[0] = fmaf(wx, dx, acc[0]); acc[1] = fmaf(wx, dy, acc[1]); acc[2] = fmaf(wx, dz, acc[2]);
+          acc[3] = fmaf(wy, dy, acc[3]); acc[4] = fmaf(wy, dz, acc[4]); acc[5] = fmaf(wz, dz, acc[5]);
+          const float vx = wc * dx, vy = wc * dy, vz = wc * dz;
+          acc[12] += vx; acc[13] += vy; acc[14] += vz;
+          const float uxx = vx * dx, uxy = vx * dy, uxz = vx * dz, uyy = vy * dy, uyz = vy * dz, uzz = vz * dz;
+          acc[6] += uxx; acc[7] += uxy; acc[8] += uxz; acc[9] += uyy; acc[10] += uyz; acc[11] += uzz;
+          acc[15] = fmaf(uxx, dx, acc[15]); acc[16] = fmaf(uxx, dy, acc[16]); acc[17] = fmaf(uxx, dz, acc[17]);
+          acc[18] = fmaf(uxy, dy, acc[18]); acc[19] = fmaf(uxy, dz, acc[19]); acc[20] = fmaf(uxz, dz, acc[20]);
+          acc[21] = fmaf(uyy, dy, acc[21]); acc[22] = fmaf(uyy, dz, acc[22]); acc[23] = fmaf(uyz, dz, acc[23]);
+          acc[24] = fmaf(uzz, dz, acc[24]);
+          const float ax = x.x - e0, ay = x.y - e1, az = x.z - e2;
+          const float qx = w * ax, qy = w * ay, qz = w * az;
+          acc[25] = fmaf(qx, ax, acc[25]); acc[26] = fmaf(qx, ay, acc[26]); acc[27] = fmaf(qx, az, acc[27]);
+          acc[28] = fmaf(qy, ay, acc[28]); acc[29] = fmaf(qy, az, acc[29]); acc[30] = fmaf(qz, az, acc[30]);
+        } else {
+          // cone_fitter.py:25-33: dir = normalize(p - apex, eps 1e-12); dot = axis . dir
+          const float vx = p.x - c0, vy = p.y - c1, vz = p.z - c2;
+          const float nrm = fmaxf(sqrtf(vx * vx + vy * vy + vz * vz), 1e-12f);
+          const float dot = (e0 * (vx / nrm) + e1 * (vy / nrm)) + e2 * (vz / nrm);
+          acc[0] = fmaf(w, dot, acc[0]);
+          const float cl = fminf(fmaxf(fabsf(dot), -1.0f + 1e-6f), 1.0f - 1e-6f);
+          acc[1] = fmaf(w, acosf(cl), acc[1]);
+        }
+      }
+    }
+#pragma unroll
+    for (int f = 0; f < F; ++f) { dacc[f] += static_cast<double>(acc[f]); acc[f] = 0.f; }
+  }
+
+  // Combine the G point lanes of every slot (fp64, fixed order) and write this CTA's partial.
+  double *red = reinterpret_cast<double *>(s_pts);     // [kTlsThreads][8]
+  double *out = part + (static_cast<size_t>(b) * chunks + chunk) * K * kFP;
+  constexpr int R = (F + 7) / 8;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    __syncthreads();
+    if (active) {
+#pragma unroll
+      for (int f = 0; f < 8; ++f) red[t * 8 + f] = (r * 8 + f < F) ? dacc[(r * 8 + f < F) ? r * 8 + f : 0] : 0.0;
+    }
+    __syncthreads();
+    for (int o = t; o < K * 8; o += kTlsThreads) {
+      const int kk = o >> 3, f = o & 7;
+      if (r * 8 + f < F) {
+        double s = 0.0;
+        for (int gg = 0; gg < G; ++gg) s += red[(gg * K + kk) * 8 + f];
+        out[kk * kFP + r * 8 + f] = s;
+      }
+    }
+  }
+}
+
+// ---- small dense algebra in registers (fp64) -------------------------------------------------
+
+// Cyclic Jacobi for a symmetric 3x3 (a = xx,xy,xz,yy,yz,zz).  lam[i], V[r][i] = i-th eigenpair.
+__device__ void eig_sym3(const double a[6], double lam[3], double V[3][3]) {
+  double A[3][3] = {{a[0], a[1], a[2]}, {a[1], a[3], a[4]}, {a[2], a[4], a[5]}};
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 12; ++sweep) {
+    const double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
+    const double diag = fabs(A[0][0]) + fabs(A[1][1]) + fabs(A[2][2]);
+    if (off <= 1e-18 * diag || off == 0.0) break;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        if (A[p][q] == 0.0) continue;
+        const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+        const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(tt * tt + 1.0), s = tt * c;
+        for (int r = 0; r < 3; ++r) {   // A <- A J
+          const double arp = A[r][p], arq = A[r][q];
+          A[r][p] = c * arp - s * arq; A[r][q] = s * arp + c * arq;
+        }
+        for (int r = 0; r < 3; ++r) {   // A <- J^T A
+          const double apr = A[p][r], aqr = A[q][r];
+          A[p][r] = c * apr - s * aqr; A[q][r] = s * apr + c * aqr;
+        }
+        for (int r = 0; r < 3; ++r) {
+          const double vrp = V[r][p], vrq = V[r][q];
+          V[r][p] = c * vrp - s * vrq; V[r][q] = s * vrp + c * vrq;
+        }
+      }
+  }
+  lam[0] = A[0][0]; lam[1] = A[1][1]; lam[2] = A[2][2];
+}
+
+// Right-singular vector of the smallest singular value of a symmetric matrix = eigenvector
+// of the eigenvalue smallest in magnitude (ties -> last, like the last column of V).
+__device__ void min_eigvec3(const double a[6], double n[3]) {
+  double lam[3], V[3][3];
+  eig_sym3(a, lam, V);
+  int m = 2;
+  if (fabs(lam[1]) < fabs(lam[m])) m = 1;
+  if (fabs(lam[0]) < fabs(lam[m])) m = 0;
+  double x = V[0][m], y = V[1][m], z = V[2][m];
+  const double nn = sqrt(x * x + y * y + z * z);
+  if (nn > 0.0) { x /= nn; y /= nn; z /= nn; }
+  // deterministic sign: the component of largest magnitude is positive
+  const double ax = fabs(x), ay = fabs(y), az = fabs(z);
+  const double lead = (ax >= ay && ax >= az) ? x : (ay >= az ? y : z);
+  const double sg = lead < 0.0 ? -1.0 : 1.0;
+  n[0] = sg * x; n[1] = sg * y; n[2] = sg * z;
+}
+
+// guarded_matrix_solve_ls (SPFN/geometry_utils.py:121-142) on the normal equations:
+// mask = cond(AtA) < 1e5 (singular values = |eigenvalues|), solve (AtA*mask + 1e-8 I) x = Atb*mask.
+__device__ void guarded_solve3(const double a[6], const double rhs[3], double x[3]) {
+  double lam[3], V[3][3];
+  eig_sym3(a, lam, V);
+  const double s0 = fabs(lam[0]), s1 = fabs(lam[1]), s2 = fabs(lam[2]);
+  const double smax = fmax(s0, fmax(s1, s2)), smin = fmin(s0, fmin(s1, s2));
+  const double mask = (smax / smin < 1e5) ? 1.0 : 0.0;   // NaN / inf compare false
+  double M[3][4] = {{a[0] * mask + 1e-8, a[1] * mask, a[2] * mask, rhs[0] * mask},
+                    {a[1] * mask, a[3] * mask + 1e-8, a[4] * mask, rhs[1] * mask},
+                    {a[2] * mask, a[4] * mask, a[5] * mask + 1e-8, rhs[2] * mask}};
+  for (int c = 0; c < 3; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < 3; ++r) if (fabs(M[r][c]) > fabs(M[piv][c])) piv = r;
+    if (piv != c) for (int j = 0; j < 4; ++j) { const double tmp = M[c][j]; M[c][j] = M[piv][j]; M[piv][j] = tmp; }
+    for (int r = c + 1; r < 3; ++r) {
+      const double f = M[r][c] / M[c][c];
+      for (int j = c; j < 4; ++j) M[r][j] -= f * M[c][j];
+    }
+  }
+  x[2] = M[2][3] / M[2][2];
+  x[1] = (M[1][3] - M[1][2] * x[2]) / M[1][1];
+  x[0] = (M[0][3] - M[0][1] * x[1] - M[0][2] * x[2]) / M[0][0];
+}
+
+__device__ void guarded_solve2(double axx, double axy, double ayy, const double rhs[2], double x[2]) {
+  const double h = 0.5 * (axx + ayy), dlt = sqrt(0.25 * (axx - ayy) * (axx - ayy) + axy * axy);
+  const double s0 = fabs(h + dlt), s1 = fabs(h - dlt);
+  const double mask = (fmax(s0, s1) / fmin(s0, s1) < 1e5) ? 1.0 : 0.0;
+  const double a = axx * mask + 1e-8, bb = axy * mask, d = ayy * mask + 1e-8;
+  const double r0 = rhs[0] * mask, r1 = rhs[1] * mask;
+  const double det = a * d - bb * bb;
+  x[0] = (r0 * d - bb * r1) / det;
+  x[1] = (a * r1 - bb * r0) / det;
+}
+
+__device__ __forceinline__ double sym6(const double a[6], int i, int j) {
+  const int idx[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+  return a[idx[i][j]];
+}
+
+// index of T_ijk in (xxx,xxy,xxz,xyy,xyz,xzz,yyy,yyz,yzz,zzz)
+__device__ __forceinline__ double sym10(const double t[10], int i, int j, int k) {
+  int a = i, b = j, c = k, tmp;
+  if (a > b) { tmp = a; a = b; b = tmp; }
+  if (b > c) { tmp = b; b = c; c = tmp; }
+  if (a > b) { tmp = a; a = b; b = tmp; }
+  const int map[3][3][3] = {{{0, 1, 2}, {1, 3, 4}, {2, 4, 5}},
+                            {{1, 3, 4}, {3, 6, 7}, {4, 7, 8}},
+                            {{2, 4, 5}, {4, 7, 8}, {5, 8, 9}}};
+  return t[map[a][b][c]];
+}
+
+// Sum the per-CTA partials of one (b,k): lane f owns feature f (coalesced 256-byte rows).
+__device__ __forceinline__ double sum_partials(const double *part, int b, int k, int K, int chunks,
+                                               int lane) {
+  const double *p = part + (static_cast<size_t>(b) * chunks * K + k) * kFP + lane;
+  double s = 0.0;
+  for (int c = 0; c < chunks; ++c) s += p[static_cast<size_t>(c) * K * kFP];
+  return s;
+}
+
+constexpr int kSolveWarps = 4;
+
+__global__ void __launch_bounds__(kSolveWarps * 32)
+tls_solve1_kernel(const double *__restrict__ part, double *__restrict__ state, int BK, int K,
+                  int chunks) {
+  __shared__ double sm[kSolveWarps][kFP];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bk = blockIdx.x * kSolveWarps + warp;
+  if (bk >= BK) return;
+  const int b = bk / K, k = bk - b * K;
+  sm[warp][lane] = lane < kF1 ? sum_partials(part, b, k, K, chunks, lane) : 0.0;
+  __syncwarp();
+  if (lane != 0) return;
+  const double *m = sm[warp];
+  double *st = state + static_cast<size_t>(bk) * kState;
+  const double sw = m[0];
+  const double denom = static_cast<double>(fmaxf(static_cast<float>(sw), 1e-10f));
+  st[ST_SW] = sw; st[ST_DENOM] = denom;
+  double mu[3], mux[3];
+  for (int i = 0; i < 3; ++i) {
+    mu[i] = static_cast<double>(static_cast<float>(m[1 + i] / denom));    // the reference's mean is fp32
+    mux[i] = static_cast<double>(static_cast<float>(m[5 + i] / denom));
+    st[ST_MU + i] = mu[i]; st[ST_MUX + i] = mux[i];
+    st[ST_S1 + i] = m[1 + i] - mu[i] * sw;                                  // sum w (p - mu)
+  }
+  st[ST_M2] = m[4] / denom;
+  double n[3];
+  min_eigvec3(m + 8, n);                       // cylinder axis: TLS on the normals (uncentred)
+  st[ST_CYLN] = n[0]; st[ST_CYLN + 1] = n[1]; st[ST_CYLN + 2] = n[2];
+  double apex[3];
+  guarded_solve3(m + 14, m + 20, apex);        // cone apex: rows sqrt(w') x, rhs sqrt(w') (p.x)
+  st[ST_APEX] = apex[0]; st[ST_APEX + 1] = apex[1]; st[ST_APEX + 2] = apex[2];
+}
+
+__global__ void __launch_bounds__(kSolveWarps * 32)
+tls_solve2_kernel(const double *__restrict__ part, double *__restrict__ state,
+                  float *__restrict__ out, int BK, int K, int chunks) {
+  __shared__ double sm[kSolveWarps][kFP];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bk = blockIdx.x * kSolveWarps + warp;
+  if (bk >= BK) return;
+  const int b = bk / K, k = bk - b * K;
+  sm[warp][lane] = lane < kF2 ? sum_partials(part, b, k, K, chunks, lane) : 0.0;
+  __syncwarp();
+  if (lane != 0) return;
+  const double *m = sm[warp];
+  const double *S = m, *Sp = m + 6, *s1p = m + 12, *T = m + 15, *Cx = m + 25;
+  double *st = state + static_cast<size_t>(bk) * kState;
+  const double sw = st[ST_SW], denom = st[ST_DENOM], m2 = st[ST_M2];
+  const double mu[3] = {st[ST_MU], st[ST_MU + 1], st[ST_MU + 2]};
+  const double s1[3] = {st[ST_S1], st[ST_S1 + 1], st[ST_S1 + 2]};
+  const size_t BKs = static_cast<size_t>(BK);
+  float *o_pn = out, *o_pc = out + 3 * BKs, *o_sc = out + 4 * BKs, *o_sr = out + 7 * BKs,
+        *o_ca = out + 8 * BKs, *o_cc = out + 11 * BKs, *o_cr = out + 14 * BKs,
+        *o_ap = out + 15 * BKs, *o_ax = out + 18 * BKs;
+
+  // plane: normal = TLS of the centred points, c = n . mean
+  double n[3];
+  min_eigvec3(S, n);
+  for (int i = 0; i < 3; ++i) o_pn[bk * 3 + i] = static_cast<float>(n[i]);
+  o_pc[bk] = static_cast<float>(n[0] * mu[0] + n[1] * mu[1] + n[2] * mu[2]);
+
+  // sphere: AtA = 4 S', Atb = -2 m2 s1' + 2 (|mu|^2 s1' + 2 S' mu + t'),  t'_i = sum_j T'_ijj
+  const double mu2 = mu[0] * mu[0] + mu[1] * mu[1] + mu[2] * mu[2];
+  double AtA[6], Atb[3], c[3];
+  for (int i = 0; i < 6; ++i) AtA[i] = 4.0 * Sp[i];
+  for (int i = 0; i < 3; ++i) {
+    const double Smu = sym6(Sp, i, 0) * mu[0] + sym6(Sp, i, 1) * mu[1] + sym6(Sp, i, 2) * mu[2];
+    const double t = sym10(T, i, 0, 0) + sym10(T, i, 1, 1) + sym10(T, i, 2, 2);
+    Atb[i] = -2.0 * m2 * s1p[i] + 2.0 * (mu2 * s1p[i] + 2.0 * Smu + t);
+  }
+  guarded_solve3(AtA, Atb, c);
+  {
+    const double e[3] = {mu[0] - c[0], mu[1] - c[1], mu[2] - c[2]};
+    const double r2 = (S[0] + S[3] + S[5]) + 2.0 * (e[0] * s1[0] + e[1] * s1[1] + e[2] * s1[2]) +
+                      (e[0] * e[0] + e[1] * e[1] + e[2] * e[2]) * sw;
+    for (int i = 0; i < 3; ++i) o_sc[bk * 3 + i] = static_cast<float>(c[i]);
+    o_sr[bk] = static_cast<float>(r2 / denom);
+  }
+
+  // cylinder: frame of the axis (compute_consistent_plane_frame), circle fit from projected moments
+  {
+    const double a[3] = {st[ST_CYLN], st[ST_CYLN + 1], st[ST_CYLN + 2]};
+    const double cand[3][3] = {{0.0, a[2], -a[1]}, {-a[2], 0.0, a[0]}, {a[1], -a[0], 0.0}};  // a x e_c
+    int best = 0;
+    double bn = -1.0;
+    for (int q = 0; q < 3; ++q) {
+      const double nn = cand[q][0] * cand[q][0] + cand[q][1] * cand[q][1] + cand[q][2] * cand[q][2];
+      if (nn > bn) { bn = nn; best = q; }
+    }
+    const double yn = fmax(sqrt(bn), 1e-12);
+    const double ya[3] = {cand[best][0] / yn, cand[best][1] / yn, cand[best][2] / yn};
+    const double xa[3] = {ya[1] * a[2] - ya[2] * a[1], ya[2] * a[0] - ya[0] * a[2], ya[0] * a[1] - ya[1] * a[0]};
+    const double *Fm[2] = {xa, ya};
+    double Sq[2][2], Spq[2][2], muq[2], s1q[2], s1pq[2], tq[2];
+    for (int u = 0; u < 2; ++u) {
+      muq[u] = Fm[u][0] * mu[0] + Fm[u][1] * mu[1] + Fm[u][2] * mu[2];
+      s1q[u] = Fm[u][0] * s1[0] + Fm[u][1] * s1[1] + Fm[u][2] * s1[2];
+      s1pq[u] = Fm[u][0] * s1p[0] + Fm[u][1] * s1p[1] + Fm[u][2] * s1p[2];
+      for (int v = 0; v < 2; ++v) {
+        double acc = 0.0, accp = 0.0;
+        for (int i = 0; i < 3; ++i)
+          for (int j = 0; j < 3; ++j) {
+            acc += Fm[u][i] * sym6(S, i, j) * Fm[v][j];
+            accp += Fm[u][i] * sym6(Sp, i, j) * Fm[v][j];
+          }
+        Sq[u][v] = acc; Spq[u][v] = accp;
+      }
+      double t = 0.0;
+      for (int v = 0; v < 2; ++v)
+        for (int i = 0; i < 3; ++i)
+          for (int j = 0; j < 3; ++j)
+            for (int l = 0; l < 3; ++l) t += Fm[u][i] * Fm[v][j] * Fm[v][l] * sym10(T, i, j, l);
+      tq[u] = t;
+    }
+    const double muq2 = muq[0] * muq[0] + muq[1] * muq[1];
+    const double m2q = ((Sq[0][0] + Sq[1][1]) + 2.0 * (muq[0] * s1q[0] + muq[1] * s1q[1]) + sw * muq2) / denom;
+    double rhs[2], cq[2];
+    for (int u = 0; u < 2; ++u)
+      rhs[u] = -2.0 * m2q * s1pq[u] + 2.0 * (muq2 * s1pq[u] + 2.0 * (Spq[u][0] * muq[0] + Spq[u][1] * muq[1]) + tq[u]);
+    guarded_solve2(4.0 * Spq[0][0], 4.0 * Spq[0][1], 4.0 * Spq[1][1], rhs, cq);
+    const double e[2] = {muq[0] - cq[0], muq[1] - cq[1]};
+    const double r2 = (Sq[0][0] + Sq[1][1]) + 2.0 * (e[0] * s1q[0] + e[1] * s1q[1]) + (e[0] * e[0] + e[1] * e[1]) * sw;
+    for (int i = 0; i < 3; ++i) {
+      o_ca[bk * 3 + i] = static_cast<float>(a[i]);
+      o_cc[bk * 3 + i] = static_cast<float>(cq[0] * xa[i] + cq[1] * ya[i]);
+    }
+    o_cr[bk] = static_cast<float>(r2 / denom);
+  }
+
+  // cone: apex from solve1; axis = plane-fit normal of the normals (sign fixed in solve3)
+  {
+    double ax[3];
+    min_eigvec3(Cx, ax);
+    for (int i = 0; i < 3; ++i) {
+      st[ST_CONEAX + i] = static_cast<double>(static_cast<float>(ax[i]));
+      o_ap[bk * 3 + i] = static_cast<float>(st[ST_APEX + i]);
+      o_ax[bk * 3 + i] = static_cast<float>(ax[i]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kSolveWarps * 32)
+tls_solve3_kernel(const double *__restrict__ part, const double *__restrict__ state,
+                  float *__restrict__ out, int BK, int K, int chunks) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bk = blockIdx.x * kSolveWarps + warp;
+  if (bk >= BK) return;
+  const int b = bk / K, k = bk - b * K;
+  const double v = lane < kF3 ? sum_partials(part, b, k, K, chunks, lane) : 0.0;
+  const double s = __shfl_sync(0xffffffffu, v, 0), a = __shfl_sync(0xffffffffu, v, 1);
+  if (lane != 0) return;
+  const size_t BKs = static_cast<size_t>(BK);
+  float *o_ax = out + 18 * BKs, *o_ha = out + 21 * BKs;
+  const float sf = static_cast<float>(s);
+  const float sgn = sf > 0.f ? 1.f : (sf < 0.f ? -1.f : 1.f);   // sign(), 0 -> +1 (cone_fitter.py:29-30)
+  for (int i = 0; i < 3; ++i) o_ax[bk * 3 + i] *= sgn;
+  const float wsum = static_cast<float>(state[static_cast<size_t>(bk) * kState + ST_SW]);
+  float half = static_cast<float>(a) / (wsum + 1e-10f);
+  half = fminf(fmaxf(half, 1e-3f), 1.57079632679489661923f - 1e-3f);
+  o_ha[bk] = half;
+}
+
+struct TlsWs {
+  double *state, *part;
+  size_t bytes;
+};
+
+TlsWs tls_carve(void *ws, int B, int K, const TlsGeom &g) {
+  TlsWs w;
+  const size_t n_state = static_cast<size_t>(B) * K * kState;
+  const size_t n_part = static_cast<size_t>(B) * g.chunks * K * kFP;
+  w.state = static_cast<double *>(ws);
+  w.part = w.state + n_state;
+  w.bytes = (n_state + n_part) * sizeof(double);
+  return w;
+}
+
+}  // namespace
+}  // namespace cpfn
+
+extern "C" size_t cpfn_fit_workspace_bytes(int B, int N, int K) {
+  using namespace cpfn;
+  if (B <= 0 || N <= 0 || K <= 0 || K > kTlsThreads) return 0;
+  const int sms = sm_count() > 0 ? sm_count() : 148;
+  return tls_carve(nullptr, B, K, tls_geom(B, N, K, sms)).bytes;
+}
+
+extern "C" int cpfn_fit_primitives(const float *P, const float *W, const float *X, int B, int N,
+                                   int K, float *out, void *workspace, size_t workspace_bytes,
+                                   cpfn_stream_t stream) {
+  using namespace cpfn;
+  if (B < 0 || N < 0 || K < 0) return CPFN_EINVAL;
+  if (B == 0 || K == 0) return CPFN_OK;
+  if (N == 0 || K > kTlsThreads || !P || !W || !X || !out || B > 65535) return CPFN_EINVAL;
+  const int sms = sm_count() > 0 ? sm_count() : 148;
+  const TlsGeom g = tls_geom(B, N, K, sms);
+  const TlsWs ws = tls_carve(workspace, B, K, g);
+  if (!workspace || workspace_bytes < ws.bytes) return CPFN_EWORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  const size_t smem_pts = 2u * static_cast<size_t>(g.CP) * sizeof(float4);
+  const size_t smem_red = static_cast<size_t>(kTlsThreads) * 8 * sizeof(double);
+  const size_t smem = smem_pts > smem_red ? smem_pts : smem_red;
+  const dim3 grid(g.chunks, B);
+  const int BK = B * K;
+  const int sgrid = (BK + kSolveWarps - 1) / kSolveWarps;
+  tls_pass_kernel<1><<<grid, kTlsThreads, smem, st>>>(P, X, W, ws.state, ws.part, N, K, g.G, g.CP,
+                                                      g.iters, g.chunks);
+  tls_solve1_kernel<<<sgrid, kSolveWarps * 32, 0, st>>>(ws.part, ws.state, BK, K, g.chunks);
+  tls_pass_kernel<2><<<grid, kTlsThreads, smem, st>>>(P, X, W, ws.state, ws.part, N, K, g.G, g.CP,
+                                                      g.iters, g.chunks);
+  tls_solve2_kernel<<<sgrid, kSolveWarps * 32, 0, st>>>(ws.part, ws.state, out, BK, K, g.chunks);
+  tls_pass_kernel<3><<<grid, kTlsThreads, smem, st>>>(P, X, W, ws.state, ws.part, N, K, g.G, g.CP,
+                                                      g.iters, g.chunks);
+  tls_solve3_kernel<<<sgrid, kSolveWarps * 32, 0, st>>>(ws.part, ws.state, out, BK, K, g.chunks);
+  return check_launch();
+}

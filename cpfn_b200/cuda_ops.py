@@ -13,6 +13,15 @@ import torch
 from . import _lib
 
 
+# Number of kernels this package enqueued (bench.py reports it as gpu_launches).
+LAUNCHES = 0
+
+
+def count_launches(n=1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
 def _check_contiguous(x, name):
     if not x.is_contiguous():
         raise RuntimeError("%s must be a contiguous tensor" % name)
@@ -46,6 +55,11 @@ def _p(x):
     return x.data_ptr()
 
 
+def _check(code, what, launches=1):
+    _lib.check(code, what)
+    count_launches(launches)
+
+
 def farthest_point_sampling(points, nsamples):
     """points f32 [B,N,3] -> i32 [B,nsamples] (sampling.cpp:65-86)."""
     _check_contiguous(points, "points")
@@ -57,7 +71,7 @@ def farthest_point_sampling(points, nsamples):
     ws_bytes = L.cpfn_fps_workspace_bytes(B, N)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=points.device) if ws_bytes else None
     with torch.cuda.device(points.device):
-        _lib.check(L.cpfn_furthest_point_sampling(_p(points), B, N, int(nsamples), _p(out),
+        _check(L.cpfn_furthest_point_sampling(_p(points), B, N, int(nsamples), _p(out),
                                                   _p(ws) if ws is not None else None, ws_bytes,
                                                   _stream(points)), "farthest_point_sampling")
     return out
@@ -76,7 +90,7 @@ def ball_query(new_xyz, xyz, radius, nsample):
     N = xyz.size(1)
     out = torch.empty((B, S, nsample), dtype=torch.int32, device=new_xyz.device)
     with torch.cuda.device(new_xyz.device):
-        _lib.check(_lib.lib().cpfn_ball_query(_p(new_xyz), _p(xyz), xyz.size(0), N, S, float(radius),
+        _check(_lib.lib().cpfn_ball_query(_p(new_xyz), _p(xyz), xyz.size(0), N, S, float(radius),
                                               int(nsample), _p(out), _stream(new_xyz)), "ball_query")
     return out
 
@@ -94,7 +108,7 @@ def gather_points(points, idx):
     M = idx.size(1)
     out = torch.empty((B, C, M), dtype=torch.float32, device=points.device)
     with torch.cuda.device(points.device):
-        _lib.check(_lib.lib().cpfn_gather_points(_p(points), _p(idx), B, C, N, M, _p(out),
+        _check(_lib.lib().cpfn_gather_points(_p(points), _p(idx), B, C, N, M, _p(out),
                                                  _stream(points)), "gather_points")
     return out
 
@@ -111,7 +125,7 @@ def gather_points_grad(grad_out, idx, n):
     B, C, M = grad_out.shape
     out = torch.empty((B, C, n), dtype=torch.float32, device=grad_out.device)
     with torch.cuda.device(grad_out.device):
-        _lib.check(_lib.lib().cpfn_gather_points_grad(_p(grad_out), _p(idx), B, C, int(n), M,
+        _check(_lib.lib().cpfn_gather_points_grad(_p(grad_out), _p(idx), B, C, int(n), M,
                                                       _p(out), _stream(grad_out)),
                    "gather_points_grad")
     return out
@@ -130,7 +144,7 @@ def group_points(points, idx):
     S, K = idx.size(1), idx.size(2)
     out = torch.empty((B, C, S, K), dtype=torch.float32, device=points.device)
     with torch.cuda.device(points.device):
-        _lib.check(_lib.lib().cpfn_group_points(_p(points), _p(idx), B, C, N, S, K, _p(out),
+        _check(_lib.lib().cpfn_group_points(_p(points), _p(idx), B, C, N, S, K, _p(out),
                                                 _stream(points)), "group_points")
     return out
 
@@ -148,7 +162,7 @@ def group_points_grad(grad_out, idx, n):
     S, K = idx.size(1), idx.size(2)
     out = torch.empty((B, C, n), dtype=torch.float32, device=grad_out.device)
     with torch.cuda.device(grad_out.device):
-        _lib.check(_lib.lib().cpfn_group_points_grad(_p(grad_out), _p(idx), B, C, int(n), S, K,
+        _check(_lib.lib().cpfn_group_points_grad(_p(grad_out), _p(idx), B, C, int(n), S, K,
                                                      _p(out), _stream(grad_out)),
                    "group_points_grad")
     return out
@@ -169,7 +183,7 @@ def three_nn(unknowns, knows):
     idx = torch.empty((B, n, 3), dtype=torch.int32, device=unknowns.device)
     dist2 = torch.empty((B, n, 3), dtype=torch.float32, device=unknowns.device)
     with torch.cuda.device(unknowns.device):
-        _lib.check(_lib.lib().cpfn_three_nn(_p(unknowns), _p(knows), B, n, m, _p(dist2), _p(idx),
+        _check(_lib.lib().cpfn_three_nn(_p(unknowns), _p(knows), B, n, m, _p(dist2), _p(idx),
                                             _stream(unknowns)), "three_nn")
     return [dist2, idx]
 
@@ -191,7 +205,7 @@ def three_weighted_sum(points, idx, weight):
     n = idx.size(1)
     out = torch.empty((B, C, n), dtype=torch.float32, device=points.device)
     with torch.cuda.device(points.device):
-        _lib.check(_lib.lib().cpfn_three_weighted_sum(_p(points), _p(idx), _p(weight), B, C, M, n,
+        _check(_lib.lib().cpfn_three_weighted_sum(_p(points), _p(idx), _p(weight), B, C, M, n,
                                                       _p(out), _stream(points)),
                    "three_weighted_sum")
     return out
@@ -213,7 +227,7 @@ def three_weighted_sum_grad(grad_out, idx, weight, m):
     B, C, n = grad_out.shape
     out = torch.empty((B, C, m), dtype=torch.float32, device=grad_out.device)
     with torch.cuda.device(grad_out.device):
-        _lib.check(_lib.lib().cpfn_three_weighted_sum_grad(_p(grad_out), _p(idx), _p(weight), B, C,
+        _check(_lib.lib().cpfn_three_weighted_sum_grad(_p(grad_out), _p(idx), _p(weight), B, C,
                                                            n, int(m), _p(out), _stream(grad_out)),
                    "three_weighted_sum_grad")
     return out

@@ -1,0 +1,55 @@
+"""One C-ABI call (cpfn_fit_primitives, include/cpfn_b200.h) fits all four primitive types
+for every (cloud, instance slot): the fused replacement of
+``SPFN/losses_implementation.py:255-278`` and the four ``compute_parameters`` it calls.
+No CPU or torch fallback: CPU tensors raise."""
+import torch
+
+from .. import _lib, cuda_ops
+
+KEYS = (("plane_normal", 0, 3), ("plane_center", 3, 1), ("sphere_center", 4, 3),
+        ("sphere_radius_squared", 7, 1), ("cylinder_axis", 8, 3), ("cylinder_center", 11, 3),
+        ("cylinder_radius_squared", 14, 1), ("cone_apex", 15, 3), ("cone_axis", 18, 3),
+        ("cone_half_angle", 21, 1))
+
+_ws_cache = {}
+
+
+def _workspace(nbytes, device):
+    key = (device.type, device.index)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def fit_primitives(P, W, X):
+    """P [B,N,3], W [B,N,K], X [B,N,3] float32 CUDA -> dict of the ten reference keys
+    (each a contiguous view of one [22*B*K] buffer)."""
+    if not P.is_cuda:
+        raise RuntimeError("CPU not supported")
+    if torch.is_grad_enabled() and (W.requires_grad or X.requires_grad):
+        raise NotImplementedError(
+            "cpfn_b200.spfn: the fitter backward pass is not implemented yet; call under "
+            "torch.no_grad() (evaluation / GlobalSPFN forward)")
+    B, N, _ = P.shape
+    K = W.shape[2]
+    P = P.detach().float().contiguous()
+    W = W.detach().float().contiguous()
+    X = X.detach().float().contiguous()
+    out = torch.empty(22 * B * K, dtype=torch.float32, device=P.device)
+    L = _lib.lib()
+    with torch.cuda.device(P.device):
+        nbytes = L.cpfn_fit_workspace_bytes(B, N, K)
+        ws = _workspace(nbytes, P.device)
+        _lib.check(L.cpfn_fit_primitives(P.data_ptr(), W.data_ptr(), X.data_ptr(), B, N, K,
+                                         out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                         torch.cuda.current_stream(P.device).cuda_stream),
+                   "fit_primitives")
+    cuda_ops.count_launches(6)
+    BK = B * K
+    res = {}
+    for name, off, width in KEYS:
+        seg = out.narrow(0, off * BK, width * BK)
+        res[name] = seg.view(B, K, 3) if width == 3 else seg.view(B, K)
+    return res

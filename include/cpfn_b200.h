@@ -108,6 +108,30 @@ CPFN_API int cpfn_three_weighted_sum_grad(const float *grad_out, const int32_t *
                                  int M, float *grad_points,
                                  cpfn_stream_t stream);
 
+/* ---------------------------------------------------------------------------
+ * SPFN weighted total-least-squares primitive fitters.
+ * ------------------------------------------------------------------------- */
+
+/* Plane, sphere, cylinder and cone parameters of every (cloud, instance slot).
+ * Replaces SPFN/losses_implementation.py:255-278 (compute_parameters) and the four
+ * fitters it dispatches to: plane_fitter.py:9-17, sphere_fitter.py:9-19,
+ * cylinder_fitter.py:10-28, cone_fitter.py:12-36 (and through them
+ * SPFN/geometry_utils.py:8-27,74-84,121-142,209-223 and differentiable_tls.py:200-209).
+ * P [B,N,3] points, W [B,N,K] soft or one-hot memberships, X [B,N,3] unit normals.
+ * `out` is a struct-of-arrays block of 22*B*K floats (BK = B*K):
+ *   [ 0BK) plane_normal [B,K,3]        [ 3BK) plane_center [B,K]
+ *   [ 4BK) sphere_center [B,K,3]       [ 7BK) sphere_radius_squared [B,K]
+ *   [ 8BK) cylinder_axis [B,K,3]       [11BK) cylinder_center [B,K,3]
+ *   [14BK) cylinder_radius_squared     [15BK) cone_apex [B,K,3]
+ *   [18BK) cone_axis [B,K,3]           [21BK) cone_half_angle [B,K]
+ * plane_normal and cylinder_axis are defined up to sign (as the reference's SVD);
+ * here the component of largest magnitude is made positive.  K <= 256.
+ * Six kernels are enqueued on `stream`; no host synchronisation. */
+CPFN_API size_t cpfn_fit_workspace_bytes(int B, int N, int K);
+CPFN_API int cpfn_fit_primitives(const float *P, const float *W, const float *X, int B,
+                                 int N, int K, float *out, void *workspace,
+                                 size_t workspace_bytes, cpfn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
