@@ -35,6 +35,17 @@ class GlobalSPFN:
         type logits, W [B,N,K] soft memberships, X_raw/T_raw/W_raw head outputs, l3_feats,
         output_feat, sa1_fps (int32 [B,512]) and ``parameters`` (the reference's dictionary).
         ``dropout=False`` replaces the reference's always-on dropout by the identity (parity runs)."""
+        from . import fused
+        if fused.available():
+            heads, l3_feats, feat, l1_xyz, l2_xyz = fused.pointnet2_forward(self.model, P, dropout=dropout)
+            out = {"X_raw": heads[0], "T_raw": heads[1], "W_raw": heads[2], "l3_feats": l3_feats,
+                   "output_feat": feat, "l1_pos": l1_xyz.permute(0, 2, 1), "l2_pos": l2_xyz.permute(0, 2, 1)}
+            out["X"] = torch.nn.functional.normalize(heads[0], p=2, dim=2, eps=1e-12)
+            out["T"] = heads[1]
+            out["W"] = torch.softmax(heads[2], dim=2)
+            if fit:
+                out["parameters"] = L.compute_parameters(P, out["W"], out["X"], self.classes)
+            return out
         m = self.model
         x = P.transpose(2, 1)
         pos = x[:, :3, :]
@@ -49,7 +60,7 @@ class GlobalSPFN:
             feat = torch.nn.functional.dropout(feat, p=0.5)
         heads = [fc(feat).transpose(1, 2) for fc in m.fc2]
         out = {"X_raw": heads[0], "T_raw": heads[1], "W_raw": heads[2], "l3_feats": l3_feats,
-               "output_feat": feat, "l1_pos": l1_pos}
+               "output_feat": feat, "l1_pos": l1_pos, "l2_pos": l2_pos}
         out["X"] = torch.nn.functional.normalize(heads[0], p=2, dim=2, eps=1e-12)
         out["T"] = heads[1]
         out["W"] = torch.softmax(heads[2], dim=2)

@@ -29,7 +29,7 @@
 // (w' = max(w, 1e-10), d = p - mean.)  Thread t of a CTA owns slot k = t % K and point lane
 // g = t / K, so a warp reads W as one contiguous stream (coalesced, every byte used once);
 // point coordinates are staged once per CTA in shared memory as float4.  Each thread sums at
-// most 32 points in fp32, then flushes into fp64 accumulators; cross-thread and cross-CTA
+// most 32 points in fp32 (weights preloaded: 32 independent loads in flight); cross-thread and cross-CTA
 // combination is fp64 and deterministic (per-CTA partials, no atomics).
 #include <math.h>
 
@@ -40,6 +40,7 @@ namespace {
 
 constexpr int kTlsThreads = 256;
 constexpr int kMaxCP = 1024;      // points staged per sub-chunk
+constexpr int kPPT = 32;          // points per thread and sub-chunk (weights preloaded in registers)
 constexpr int kF1 = 23, kF2 = 31, kF3 = 2;
 constexpr int kFP = 32;           // padded feature stride of the partial arrays
 constexpr int kState = 24;        // doubles per (b,k)
@@ -58,7 +59,7 @@ TlsGeom tls_geom(int B, int N, int K, int sms) {
   TlsGeom g;
   g.G = imax(1, kTlsThreads / K);
   long long want = (static_cast<long long>(B) * N + 2LL * sms * g.G - 1) / (2LL * sms * g.G);
-  g.ppt = static_cast<int>(want < 8 ? 8 : (want > 32 ? 32 : want));
+  g.ppt = static_cast<int>(want < 8 ? 8 : (want > kPPT ? kPPT : want));
   g.ppt = imin(g.ppt, imax(1, kMaxCP / g.G));
   g.CP = g.G * g.ppt;
   const int SC = (N + g.CP - 1) / g.CP;
@@ -72,19 +73,22 @@ TlsGeom tls_geom(int B, int N, int K, int sms) {
 template <int PASS> struct NFeat { static constexpr int F = PASS == 1 ? kF1 : (PASS == 2 ? kF2 : kF3); };
 
 template <int PASS>
-__global__ void __launch_bounds__(kTlsThreads)
+__global__ void __launch_bounds__(kTlsThreads, 2)
 tls_pass_kernel(const float *__restrict__ P, const float *__restrict__ X,
                 const float *__restrict__ W, const double *__restrict__ state,
                 double *__restrict__ part, int N, int K, int G, int CP, int iters, int chunks) {
   constexpr int F = NFeat<PASS>::F;
   extern __shared__ float4 s_pts[];          // [CP] positions (+ |p|^2), [CP] normals (+ p.x)
   float4 *sp = s_pts, *sx = s_pts + CP;
+  double *red = reinterpret_cast<double *>(s_pts + 2 * CP);   // [kTlsThreads][8]
+  double *tot = red + kTlsThreads * 8;                        // [K][kFP] running fp64 totals
   const int b = blockIdx.y, chunk = blockIdx.x, t = threadIdx.x;
   const bool active = t < G * K;
   const int k = active ? t % K : 0, g = t / K;
   const float *Pb = P + static_cast<size_t>(b) * N * 3;
   const float *Xb = X ? X + static_cast<size_t>(b) * N * 3 : nullptr;
   const float *Wb = W + static_cast<size_t>(b) * N * K;
+  const int ppt = CP / G;
 
   float c0 = 0.f, c1 = 0.f, c2 = 0.f, e0 = 0.f, e1 = 0.f, e2 = 0.f;   // per-slot constants
   if (PASS >= 2) {
@@ -97,16 +101,22 @@ tls_pass_kernel(const float *__restrict__ P, const float *__restrict__ X,
       e0 = static_cast<float>(st[ST_CONEAX]); e1 = static_cast<float>(st[ST_CONEAX + 1]); e2 = static_cast<float>(st[ST_CONEAX + 2]);
     }
   }
-
-  float acc[F];
-  double dacc[F];
-#pragma unroll
-  for (int f = 0; f < F; ++f) { acc[f] = 0.f; dacc[f] = 0.0; }
+  for (int o = t; o < K * kFP; o += kTlsThreads) tot[o] = 0.0;
 
   for (int it = 0; it < iters; ++it) {
     const int n0 = (chunk * iters + it) * CP;
     if (n0 >= N) break;
     const int cn = imin(CP, N - n0);
+    // All of this thread's membership weights first: up to 32 independent loads in flight.
+    float wv[kPPT];
+    {
+      const float *wp = Wb + static_cast<size_t>(n0) * K + k;
+#pragma unroll
+      for (int i = 0; i < kPPT; ++i) {
+        const int j = g + i * G;
+        wv[i] = (active && i < ppt && j < cn) ? __ldg(wp + static_cast<size_t>(j) * K) : 0.f;
+      }
+    }
     __syncthreads();
     for (int i = t; i < cn; i += kTlsThreads) {
       const float *p = Pb + static_cast<size_t>(n0 + i) * 3;
@@ -120,81 +130,83 @@ tls_pass_kernel(const float *__restrict__ P, const float *__restrict__ X,
       sx[i] = make_float4(xx, xy, xz, px * xx + py * xy + pz * xz);
     }
     __syncthreads();
-    if (active) {
-      const float *wp = Wb + static_cast<size_t>(n0) * K + k;
-#pragma unroll 2
-      for (int j = g; j < cn; j += G) {
-        const float w = __ldg(wp + static_cast<size_t>(j) * K);
-        const float4 p = sp[j];
-        if (PASS == 1) {
-          const float4 x = sx[j];
-          const float wc = fmaxf(w, 1e-10f);
-          acc[0] += w;
-          acc[1] = fmaf(w, p.x, acc[1]); acc[2] = fmaf(w, p.y, acc[2]); acc[3] = fmaf(w, p.z, acc[3]);
-          acc[4] = fmaf(w, p.w, acc[4]);
-          const float wx = w * x.x, wy = w * x.y, wz = w * x.z;
-          acc[5] += wx; acc[6] += wy; acc[7] += wz;
-          acc[8] = fmaf(wx, x.x, acc[8]); acc[9] = fmaf(wx, x.y, acc[9]); acc[10] = fmaf(wx, x.z, acc[10]);
-          acc[11] = fmaf(wy, x.y, acc[11]); acc[12] = fmaf(wy, x.z, acc[12]); acc[13] = fmaf(wz, x.z, acc[13]);
-          const float vx = wc * x.x, vy = wc * x.y, vz = wc * x.z;
-          acc[14] = fmaf(vx, x.x, acc[14]); acc[15] = fmaf(vx, x.y, acc[15]); acc[16] = fmaf(vx, x.z, acc[16]);
-          acc[17] = fmaf(vy, x.y, acc[17]); acc[18] = fmaf(vy, x.z, acc[18]); acc[19] = fmaf(vz, x.z, acc[19]);
-          acc[20] = fmaf(vx, x.w, acc[20]); acc[21] = fmaf(vy, x.w, acc[21]); acc[22] = fmaf(vz, x.w, acc[22]);
-        } else if (PASS == 2) {
-          const float4 x = sx[j];
-          const float wc = fmaxf(w, 1e-10f);
-          const float dx = p.x - c0, dy = p.y - c1, dz = p.z - c2;
-          const float wx = w * dx, wy = w * dy, wz = w * dz;
-          acc[0] = fmaf(wx, dx, acc[0]); acc[1] = fmaf(wx, dy, acc[1]); acc[2] = fmaf(wx, dz, acc[2]);
-          acc[3] = fmaf(wy, dy, acc[3]); acc[4] = fmaf(wy, dz, acc[4]); acc[5] = fmaf(wz, dz, acc[5]);
-          const float vx = wc * dx, vy = wc * dy, vz = wc * dz;
-          acc[12] += vx; acc[13] += vy; acc[14] += vz;
-          const float uxx = vx * dx, uxy = vx * dy, uxz = vx * dz, uyy = vy * dy, uyz = vy * dz, uzz = vz * dz;
-          acc[6] += uxx; acc[7] += uxy; acc[8] += uxz; acc[9] += uyy; acc[10] += uyz; acc[11] += uzz;
-          acc[15] = fmaf(uxx, dx, acc[15]); acc[16] = fmaf(uxx, dy, acc[16]); acc[17] = fmaf(uxx, dz, acc[17]);
-          acc[18] = fmaf(uxy, dy, acc[18]); acc[19] = fmaf(uxy, dz, acc[19]); acc[20] = fmaf(uxz, dz, acc[20]);
-          acc[21] = fmaf(uyy, dy, acc[21]); acc[22] = fmaf(uyy, dz, acc[22]); acc[23] = fmaf(uyz, dz, acc[23]);
-          acc[24] = fmaf(uzz, dz, acc[24]);
-          const float ax = x.x - e0, ay = x.y - e1, az = x.z - e2;
-          const float qx = w * ax, qy = w * ay, qz = w * az;
-          acc[25] = fmaf(qx, ax, acc[25]); acc[26] = fmaf(qx, ay, acc[26]); acc[27] = fmaf(qx, az, acc[27]);
-          acc[28] = fmaf(qy, ay, acc[28]); acc[29] = fmaf(qy, az, acc[29]); acc[30] = fmaf(qz, az, acc[30]);
-        } else {
-          // cone_fitter.py:25-33: dir = normalize(p - apex, eps 1e-12); dot = axis . dir
-          const float vx = p.x - c0, vy = p.y - c1, vz = p.z - c2;
-          const float nrm = fmaxf(sqrtf(vx * vx + vy * vy + vz * vz), 1e-12f);
-          const float dot = (e0 * (vx / nrm) + e1 * (vy / nrm)) + e2 * (vz / nrm);
-          acc[0] = fmaf(w, dot, acc[0]);
-          const float cl = fminf(fmaxf(fabsf(dot), -1.0f + 1e-6f), 1.0f - 1e-6f);
-          acc[1] = fmaf(w, acosf(cl), acc[1]);
+    float acc[F];
+#pragma unroll
+    for (int f = 0; f < F; ++f) acc[f] = 0.f;
+#pragma unroll
+    for (int i = 0; i < kPPT; ++i) {
+      const int j = g + i * G;
+      if (i >= ppt || j >= cn) continue;
+      const float w = wv[i];
+      const float4 p = sp[j];
+      if (PASS == 1) {
+        const float4 x = sx[j];
+        const float wc = fmaxf(w, 1e-10f);
+        acc[0] += w;
+        acc[1] = fmaf(w, p.x, acc[1]); acc[2] = fmaf(w, p.y, acc[2]); acc[3] = fmaf(w, p.z, acc[3]);
+        acc[4] = fmaf(w, p.w, acc[4]);
+        const float wx = w * x.x, wy = w * x.y, wz = w * x.z;
+        acc[5] += wx; acc[6] += wy; acc[7] += wz;
+        acc[8] = fmaf(wx, x.x, acc[8]); acc[9] = fmaf(wx, x.y, acc[9]); acc[10] = fmaf(wx, x.z, acc[10]);
+        acc[11] = fmaf(wy, x.y, acc[11]); acc[12] = fmaf(wy, x.z, acc[12]); acc[13] = fmaf(wz, x.z, acc[13]);
+        const float vx = wc * x.x, vy = wc * x.y, vz = wc * x.z;
+        acc[14] = fmaf(vx, x.x, acc[14]); acc[15] = fmaf(vx, x.y, acc[15]); acc[16] = fmaf(vx, x.z, acc[16]);
+        acc[17] = fmaf(vy, x.y, acc[17]); acc[18] = fmaf(vy, x.z, acc[18]); acc[19] = fmaf(vz, x.z, acc[19]);
+        acc[20] = fmaf(vx, x.w, acc[20]); acc[21] = fmaf(vy, x.w, acc[21]); acc[22] = fmaf(vz, x.w, acc[22]);
+      } else if (PASS == 2) {
+        const float4 x = sx[j];
+        const float wc = fmaxf(w, 1e-10f);
+        const float dx = p.x - c0, dy = p.y - c1, dz = p.z - c2;
+        const float wx = w * dx, wy = w * dy, wz = w * dz;
+        acc[0] = fmaf(wx, dx, acc[0]); acc[1] = fmaf(wx, dy, acc[1]); acc[2] = fmaf(wx, dz, acc[2]);
+        acc[3] = fmaf(wy, dy, acc[3]); acc[4] = fmaf(wy, dz, acc[4]); acc[5] = fmaf(wz, dz, acc[5]);
+        const float vx = wc * dx, vy = wc * dy, vz = wc * dz;
+        acc[12] += vx; acc[13] += vy; acc[14] += vz;
+        const float uxx = vx * dx, uxy = vx * dy, uxz = vx * dz, uyy = vy * dy, uyz = vy * dz, uzz = vz * dz;
+        acc[6] += uxx; acc[7] += uxy; acc[8] += uxz; acc[9] += uyy; acc[10] += uyz; acc[11] += uzz;
+        acc[15] = fmaf(uxx, dx, acc[15]); acc[16] = fmaf(uxx, dy, acc[16]); acc[17] = fmaf(uxx, dz, acc[17]);
+        acc[18] = fmaf(uxy, dy, acc[18]); acc[19] = fmaf(uxy, dz, acc[19]); acc[20] = fmaf(uxz, dz, acc[20]);
+        acc[21] = fmaf(uyy, dy, acc[21]); acc[22] = fmaf(uyy, dz, acc[22]); acc[23] = fmaf(uyz, dz, acc[23]);
+        acc[24] = fmaf(uzz, dz, acc[24]);
+        const float ax = x.x - e0, ay = x.y - e1, az = x.z - e2;
+        const float qx = w * ax, qy = w * ay, qz = w * az;
+        acc[25] = fmaf(qx, ax, acc[25]); acc[26] = fmaf(qx, ay, acc[26]); acc[27] = fmaf(qx, az, acc[27]);
+        acc[28] = fmaf(qy, ay, acc[28]); acc[29] = fmaf(qy, az, acc[29]); acc[30] = fmaf(qz, az, acc[30]);
+      } else {
+        // cone_fitter.py:25-33: dir = normalize(p - apex, eps 1e-12); dot = axis . dir
+        const float vx = p.x - c0, vy = p.y - c1, vz = p.z - c2;
+        const float nrm = fmaxf(sqrtf(vx * vx + vy * vy + vz * vz), 1e-12f);
+        const float dot = (e0 * (vx / nrm) + e1 * (vy / nrm)) + e2 * (vz / nrm);
+        acc[0] = fmaf(w, dot, acc[0]);
+        const float cl = fminf(fmaxf(fabsf(dot), -1.0f + 1e-6f), 1.0f - 1e-6f);
+        acc[1] = fmaf(w, acosf(cl), acc[1]);
+      }
+    }
+    // Combine the G point lanes of every slot in fp64 (fixed order) into the CTA totals.
+    constexpr int R = (F + 7) / 8;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (r > 0) __syncthreads();
+      if (active) {
+#pragma unroll
+        for (int f = 0; f < 8; ++f)
+          red[t * 8 + f] = (r * 8 + f < F) ? static_cast<double>(acc[(r * 8 + f < F) ? r * 8 + f : 0]) : 0.0;
+      }
+      __syncthreads();
+      for (int o = t; o < K * 8; o += kTlsThreads) {
+        const int kk = o >> 3, f = o & 7;
+        if (r * 8 + f < F) {
+          double s = 0.0;
+          for (int gg = 0; gg < G; ++gg) s += red[(gg * K + kk) * 8 + f];
+          tot[kk * kFP + r * 8 + f] += s;
         }
       }
     }
-#pragma unroll
-    for (int f = 0; f < F; ++f) { dacc[f] += static_cast<double>(acc[f]); acc[f] = 0.f; }
   }
-
-  // Combine the G point lanes of every slot (fp64, fixed order) and write this CTA's partial.
-  double *red = reinterpret_cast<double *>(s_pts);     // [kTlsThreads][8]
+  __syncthreads();
   double *out = part + (static_cast<size_t>(b) * chunks + chunk) * K * kFP;
-  constexpr int R = (F + 7) / 8;
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    __syncthreads();
-    if (active) {
-#pragma unroll
-      for (int f = 0; f < 8; ++f) red[t * 8 + f] = (r * 8 + f < F) ? dacc[(r * 8 + f < F) ? r * 8 + f : 0] : 0.0;
-    }
-    __syncthreads();
-    for (int o = t; o < K * 8; o += kTlsThreads) {
-      const int kk = o >> 3, f = o & 7;
-      if (r * 8 + f < F) {
-        double s = 0.0;
-        for (int gg = 0; gg < G; ++gg) s += red[(gg * K + kk) * 8 + f];
-        out[kk * kFP + r * 8 + f] = s;
-      }
-    }
-  }
+  for (int o = t; o < K * kFP; o += kTlsThreads)
+    if ((o & (kFP - 1)) < F) out[o] = tot[o];
 }
 
 // ---- small dense algebra in registers (fp64) -------------------------------------------------
@@ -323,26 +335,28 @@ tls_solve1_kernel(const double *__restrict__ part, double *__restrict__ state, i
   const int b = bk / K, k = bk - b * K;
   sm[warp][lane] = lane < kF1 ? sum_partials(part, b, k, K, chunks, lane) : 0.0;
   __syncwarp();
-  if (lane != 0) return;
   const double *m = sm[warp];
   double *st = state + static_cast<size_t>(bk) * kState;
-  const double sw = m[0];
-  const double denom = static_cast<double>(fmaxf(static_cast<float>(sw), 1e-10f));
-  st[ST_SW] = sw; st[ST_DENOM] = denom;
-  double mu[3], mux[3];
-  for (int i = 0; i < 3; ++i) {
-    mu[i] = static_cast<double>(static_cast<float>(m[1 + i] / denom));    // the reference's mean is fp32
-    mux[i] = static_cast<double>(static_cast<float>(m[5 + i] / denom));
-    st[ST_MU + i] = mu[i]; st[ST_MUX + i] = mux[i];
-    st[ST_S1 + i] = m[1 + i] - mu[i] * sw;                                  // sum w (p - mu)
+  if (lane == 0) {
+    const double sw = m[0];
+    const double denom = static_cast<double>(fmaxf(static_cast<float>(sw), 1e-10f));
+    st[ST_SW] = sw; st[ST_DENOM] = denom;
+    for (int i = 0; i < 3; ++i) {
+      const double mu = static_cast<double>(static_cast<float>(m[1 + i] / denom));   // the reference's mean is fp32
+      st[ST_MU + i] = mu;
+      st[ST_MUX + i] = static_cast<double>(static_cast<float>(m[5 + i] / denom));
+      st[ST_S1 + i] = m[1 + i] - mu * sw;                                             // sum w (p - mu)
+    }
+    st[ST_M2] = m[4] / denom;
+  } else if (lane == 1) {
+    double n[3];
+    min_eigvec3(m + 8, n);                       // cylinder axis: TLS on the normals (uncentred)
+    st[ST_CYLN] = n[0]; st[ST_CYLN + 1] = n[1]; st[ST_CYLN + 2] = n[2];
+  } else if (lane == 2) {
+    double apex[3];
+    guarded_solve3(m + 14, m + 20, apex);        // cone apex: rows sqrt(w') x, rhs sqrt(w') (p.x)
+    st[ST_APEX] = apex[0]; st[ST_APEX + 1] = apex[1]; st[ST_APEX + 2] = apex[2];
   }
-  st[ST_M2] = m[4] / denom;
-  double n[3];
-  min_eigvec3(m + 8, n);                       // cylinder axis: TLS on the normals (uncentred)
-  st[ST_CYLN] = n[0]; st[ST_CYLN + 1] = n[1]; st[ST_CYLN + 2] = n[2];
-  double apex[3];
-  guarded_solve3(m + 14, m + 20, apex);        // cone apex: rows sqrt(w') x, rhs sqrt(w') (p.x)
-  st[ST_APEX] = apex[0]; st[ST_APEX + 1] = apex[1]; st[ST_APEX + 2] = apex[2];
 }
 
 __global__ void __launch_bounds__(kSolveWarps * 32)
@@ -355,7 +369,7 @@ tls_solve2_kernel(const double *__restrict__ part, double *__restrict__ state,
   const int b = bk / K, k = bk - b * K;
   sm[warp][lane] = lane < kF2 ? sum_partials(part, b, k, K, chunks, lane) : 0.0;
   __syncwarp();
-  if (lane != 0) return;
+  if (lane > 3) return;
   const double *m = sm[warp];
   const double *S = m, *Sp = m + 6, *s1p = m + 12, *T = m + 15, *Cx = m + 25;
   double *st = state + static_cast<size_t>(bk) * kState;
@@ -367,12 +381,27 @@ tls_solve2_kernel(const double *__restrict__ part, double *__restrict__ state,
         *o_ca = out + 8 * BKs, *o_cc = out + 11 * BKs, *o_cr = out + 14 * BKs,
         *o_ap = out + 15 * BKs, *o_ax = out + 18 * BKs;
 
-  // plane: normal = TLS of the centred points, c = n . mean
-  double n[3];
-  min_eigvec3(S, n);
-  for (int i = 0; i < 3; ++i) o_pn[bk * 3 + i] = static_cast<float>(n[i]);
-  o_pc[bk] = static_cast<float>(n[0] * mu[0] + n[1] * mu[1] + n[2] * mu[2]);
-
+  // The four sub-problems of a slot are independent: lanes 0..3 take one each.
+  if (lane == 0) {
+    // plane: normal = TLS of the centred points, c = n . mean
+    double n[3];
+    min_eigvec3(S, n);
+    for (int i = 0; i < 3; ++i) o_pn[bk * 3 + i] = static_cast<float>(n[i]);
+    o_pc[bk] = static_cast<float>(n[0] * mu[0] + n[1] * mu[1] + n[2] * mu[2]);
+    return;
+  }
+  if (lane == 3) {
+    // cone: apex from solve1; axis = plane-fit normal of the normals (sign fixed in solve3)
+    double ax[3];
+    min_eigvec3(Cx, ax);
+    for (int i = 0; i < 3; ++i) {
+      st[ST_CONEAX + i] = static_cast<double>(static_cast<float>(ax[i]));
+      o_ap[bk * 3 + i] = static_cast<float>(st[ST_APEX + i]);
+      o_ax[bk * 3 + i] = static_cast<float>(ax[i]);
+    }
+    return;
+  }
+  if (lane == 1) {
   // sphere: AtA = 4 S', Atb = -2 m2 s1' + 2 (|mu|^2 s1' + 2 S' mu + t'),  t'_i = sum_j T'_ijj
   const double mu2 = mu[0] * mu[0] + mu[1] * mu[1] + mu[2] * mu[2];
   double AtA[6], Atb[3], c[3];
@@ -389,6 +418,8 @@ tls_solve2_kernel(const double *__restrict__ part, double *__restrict__ state,
                       (e[0] * e[0] + e[1] * e[1] + e[2] * e[2]) * sw;
     for (int i = 0; i < 3; ++i) o_sc[bk * 3 + i] = static_cast<float>(c[i]);
     o_sr[bk] = static_cast<float>(r2 / denom);
+  }
+  return;
   }
 
   // cylinder: frame of the axis (compute_consistent_plane_frame), circle fit from projected moments
@@ -439,17 +470,6 @@ tls_solve2_kernel(const double *__restrict__ part, double *__restrict__ state,
       o_cc[bk * 3 + i] = static_cast<float>(cq[0] * xa[i] + cq[1] * ya[i]);
     }
     o_cr[bk] = static_cast<float>(r2 / denom);
-  }
-
-  // cone: apex from solve1; axis = plane-fit normal of the normals (sign fixed in solve3)
-  {
-    double ax[3];
-    min_eigvec3(Cx, ax);
-    for (int i = 0; i < 3; ++i) {
-      st[ST_CONEAX + i] = static_cast<double>(static_cast<float>(ax[i]));
-      o_ap[bk * 3 + i] = static_cast<float>(st[ST_APEX + i]);
-      o_ax[bk * 3 + i] = static_cast<float>(ax[i]);
-    }
   }
 }
 
@@ -511,9 +531,14 @@ extern "C" int cpfn_fit_primitives(const float *P, const float *W, const float *
   const TlsWs ws = tls_carve(workspace, B, K, g);
   if (!workspace || workspace_bytes < ws.bytes) return CPFN_EWORKSPACE;
   cudaStream_t st = as_stream(stream);
-  const size_t smem_pts = 2u * static_cast<size_t>(g.CP) * sizeof(float4);
-  const size_t smem_red = static_cast<size_t>(kTlsThreads) * 8 * sizeof(double);
-  const size_t smem = smem_pts > smem_red ? smem_pts : smem_red;
+  const size_t smem = 2u * static_cast<size_t>(g.CP) * sizeof(float4) +
+                      static_cast<size_t>(kTlsThreads) * 8 * sizeof(double) +
+                      static_cast<size_t>(K) * kFP * sizeof(double);
+  if (smem > 48 * 1024) {
+    CPFN_CUDA_TRY(cudaFuncSetAttribute(tls_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    CPFN_CUDA_TRY(cudaFuncSetAttribute(tls_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    CPFN_CUDA_TRY(cudaFuncSetAttribute(tls_pass_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  }
   const dim3 grid(g.chunks, B);
   const int BK = B * K;
   const int sgrid = (BK + kSolveWarps - 1) / kSolveWarps;

@@ -1,22 +1,309 @@
-"""Fused inference kernels behind PointsetAbstraction / PointsetFeaturePropagation.
+"""Host side of the fused tcgen05 MLP-chain kernel (csrc/mlp_chain.cu, C ABI
+``cpfn_mlp_chain``): BatchNorm folding and weight packing at load time, and the
+inference forward of PointsetAbstraction / PointsetFeaturePropagation / the whole
+PointNet2 on top of it.
 
-Placeholder until the tcgen05 kernels land: ``available()`` is False and the modules
-use the per-op kernels.
+Layout: between the fused kernels features are POINT-major ([B, N, C], a point's
+channels contiguous) so that a neighbourhood gather reads whole 512-byte rows; the
+reference's channel-major [B, C, N] tensors are produced only where the reference API
+returns them (``l3_feats``, ``output_feat``, the module-level SA / FP forwards).
 """
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib, cuda_ops
+
+MAX_LAYERS = 6
+IN_DENSE, IN_GROUP, IN_INTERP = 0, 1, 2
+OUT_ROWS, OUT_POOL = 0, 1
+TIMED_OPS = ("mlp_chain",)
+
+
+class _Layer(ctypes.Structure):
+    _fields_ = [("cin", ctypes.c_int32), ("cout", ctypes.c_int32), ("relu", ctypes.c_int32),
+                ("bias_per_cloud", ctypes.c_int32), ("bias", ctypes.c_void_p), ("mask", ctypes.c_void_p),
+                ("out_cm", ctypes.c_void_p)]
+
+
+class _Chain(ctypes.Structure):
+    _fields_ = [("n_layers", ctypes.c_int32), ("layers", _Layer * MAX_LAYERS),
+                ("weights", ctypes.c_void_p), ("weight_bytes", ctypes.c_size_t),
+                ("tile_cols", ctypes.c_int32), ("in_mode", ctypes.c_int32),
+                ("B", ctypes.c_int32), ("cols_per_cloud", ctypes.c_int32),
+                ("a_src", ctypes.c_void_p), ("a_ch", ctypes.c_int32), ("a_rows", ctypes.c_int32),
+                ("idx", ctypes.c_void_p), ("xyz", ctypes.c_void_p), ("centers", ctypes.c_void_p),
+                ("group_k", ctypes.c_int32),
+                ("b_src", ctypes.c_void_p), ("b_ch", ctypes.c_int32), ("b_rows", ctypes.c_int32),
+                ("nn_w", ctypes.c_void_p),
+                ("out_mode", ctypes.c_int32), ("out", ctypes.c_void_p), ("ldo", ctypes.c_int32),
+                ("pool_g", ctypes.c_int32)]
 
 
 def available():
-    return False
+    """The fused path needs the library and a CUDA device; there is no fallback inside it."""
+    return torch.cuda.is_available() and hasattr(_lib.lib(), "cpfn_mlp_chain")
 
 
-def set_abstraction_forward(module, pos, feats):
-    raise RuntimeError("fused set abstraction is not built")
+# ---- weight preparation (load time) -------------------------------------------------------------
+
+def fold_bn(conv_w, conv_b, bn):
+    """conv (1x1) followed by eval-mode BatchNorm == one affine map: W' = s W, b' = s (b - mean) + beta,
+    s = gamma / sqrt(var + eps)."""
+    w = conv_w.detach().double().reshape(conv_w.shape[0], conv_w.shape[1]).cpu()
+    b = conv_b.detach().double().cpu()
+    if bn is None:
+        return w.float().numpy(), b.float().numpy()
+    s = bn.weight.detach().double().cpu() / torch.sqrt(bn.running_var.detach().double().cpu() + bn.eps)
+    return ((w * s[:, None]).float().numpy(),
+            ((b - bn.running_mean.detach().double().cpu()) * s + bn.bias.detach().double().cpu()).float().numpy())
 
 
-def feature_propagation_forward(module, pos1, pos2, feats1, feats2):
-    raise RuntimeError("fused feature propagation is not built")
+def pack_weights(w):
+    """[cout, cin] float32 numpy -> uint8 numpy blob in the kernel's shared-memory image."""
+    L = _lib.lib()
+    w = np.ascontiguousarray(w, dtype=np.float32)
+    cout, cin = w.shape
+    nbytes = L.cpfn_mlp_packed_bytes(cout, cin)
+    blob = np.zeros(nbytes, dtype=np.uint8)
+    _lib.check(L.cpfn_mlp_pack_weights_host(w.ctypes.data, cout, cin, blob.ctypes.data), "mlp_pack_weights")
+    return blob
+
+
+def pad_bias(b):
+    cout = b.shape[-1]
+    pad = (cout + 127) // 128 * 128
+    out = np.zeros(b.shape[:-1] + (pad,), dtype=np.float32)
+    out[..., :cout] = b
+    return out
+
+
+class PackedChain:
+    """Device-resident weights / biases of one chain: list of (W [cout,cin], b [cout], relu)."""
+
+    def __init__(self, layers, device):
+        self.dims = [(w.shape[1], w.shape[0], bool(r)) for w, _, r in layers]
+        blob = np.concatenate([pack_weights(w) for w, _, _ in layers])
+        self.weights = torch.from_numpy(blob).to(device)
+        self.biases = [torch.from_numpy(pad_bias(b)).to(device) for _, b, _ in layers]
+
+
+def run_chain(pc, B, cols_per_cloud, out, ldo, tile_cols=128, in_mode=IN_DENSE, a_src=None, a_ch=0, a_rows=0,
+              idx=None, xyz=None, centers=None, group_k=0, b_src=None, b_ch=0, b_rows=0, nn_w=None,
+              out_mode=OUT_ROWS, pool_g=0, biases=None, bias_per_cloud=(), masks=None, out_cm=None):
+    """Enqueue one fused chain on torch's current stream."""
+    c = _Chain()
+    c.n_layers = len(pc.dims)
+    keep = []
+    for l, (cin, cout, relu) in enumerate(pc.dims):
+        bias = biases[l] if (biases is not None and biases[l] is not None) else pc.biases[l]
+        keep.append(bias)
+        c.layers[l].cin, c.layers[l].cout, c.layers[l].relu = cin, cout, int(relu)
+        c.layers[l].bias_per_cloud = int(l in bias_per_cloud)
+        c.layers[l].bias = bias.data_ptr()
+        c.layers[l].mask = masks[l].data_ptr() if (masks and masks.get(l) is not None) else None
+        c.layers[l].out_cm = out_cm[l].data_ptr() if (out_cm and out_cm.get(l) is not None) else None
+    c.weights, c.weight_bytes = pc.weights.data_ptr(), pc.weights.numel()
+    c.tile_cols, c.in_mode, c.B, c.cols_per_cloud = tile_cols, in_mode, B, cols_per_cloud
+    p = lambda t: t.data_ptr() if t is not None else None
+    c.a_src, c.a_ch, c.a_rows = p(a_src), a_ch, a_rows
+    c.idx, c.xyz, c.centers, c.group_k = p(idx), p(xyz), p(centers), group_k
+    c.b_src, c.b_ch, c.b_rows, c.nn_w = p(b_src), b_ch, b_rows, p(nn_w)
+    c.out_mode, c.out, c.ldo, c.pool_g = out_mode, out.data_ptr(), ldo, pool_g
+    with torch.cuda.device(out.device):
+        _lib.check(_lib.lib().cpfn_mlp_chain(ctypes.byref(c), torch.cuda.current_stream(out.device).cuda_stream),
+                   "mlp_chain")
+    cuda_ops.count_launches(1)
+    return out
+
+
+def pick_tile(dims, cols_per_cloud, need_cloud_aligned=False, prefer=128):
+    """Largest tile (128 / 64 / 32 columns) whose two activation buffers plus a 3-stage weight
+    ring fit the 227 KB of shared memory (mirrors launch_chain in csrc/mlp_chain.cu)."""
+    for tile in (128, 64, 32):
+        if tile > prefer:
+            continue
+        if need_cloud_aligned and cols_per_cloud % tile:
+            continue
+        need = [0, 0]
+        for l, (cin, _, _) in enumerate(dims):
+            need[l & 1] = max(need[l & 1], (cin + 31) // 32 * tile * 128)
+        if sum(need) + 1280 + 3 * 16384 <= 227 * 1024:
+            return tile
+    raise RuntimeError("cpfn_b200.fused: chain does not fit shared memory: %r" % (dims,))
+
+
+def mlp_chain(*args, **kwargs):
+    """Timed alias used by bench.py's per-op profile."""
+    return run_chain(*args, **kwargs)
+
+
+# ---- PointNet2 on the fused chains --------------------------------------------------------------
+
+_CACHE_ATTR = "_cpfn_fused_cache"
 
 
 def invalidate(model):
-    """Drop cached folded weights after a state-dict load."""
-    return None
+    """Drop the folded / packed weights cached on the modules (call after load_state_dict)."""
+    for m in model.modules():
+        for k in [k for k in vars(m) if k.startswith(_CACHE_ATTR)]:
+            delattr(m, k)
+
+
+def _sa_chain(module, device):
+    pc = getattr(module, _CACHE_ATTR, None)
+    if pc is None or pc.weights.device != device:
+        layers = []
+        for j, (conv, bn) in enumerate(zip(module.conv_blocks[0], module.bn_blocks[0])):
+            w, b = fold_bn(conv.weight, conv.bias, bn)
+            if j == 0 and module.group_all and w.shape[1] > 3:
+                # reference group_all order is [xyz, feats] (pointset_abstraction.py:54-56); the
+                # kernel builds rows as [feats, xyz]: permute the input channels of the first layer
+                w = np.concatenate([w[:, 3:], w[:, :3]], axis=1)
+            layers.append((w, b, True))
+        pc = PackedChain(layers, device)
+        setattr(module, _CACHE_ATTR, pc)
+    return pc
+
+
+def sa_forward_pm(module, xyz, feats_pm):
+    """Point-major set abstraction.  xyz [B,N,3], feats_pm [B,N,D] | None ->
+    (new_xyz [B,S,3] | None, new_feats_pm [B,S,D'])."""
+    assert len(module.radius_list) == 1, "multi-scale grouping: use the per-op path"
+    B, N, _ = xyz.shape
+    dev = xyz.device
+    pc = _sa_chain(module, dev)
+    cout = pc.dims[-1][1]
+    D = 0 if feats_pm is None else feats_pm.shape[2]
+    if module.group_all:
+        idx = torch.arange(N, dtype=torch.int32, device=dev).repeat(B)
+        centers = torch.zeros(B, 3, dtype=torch.float32, device=dev)
+        out = torch.empty(B, 1, cout, dtype=torch.float32, device=dev)
+        tile = pick_tile(pc.dims, N, need_cloud_aligned=True, prefer=32 if cout > 512 else 128)
+        run_chain(pc, B, N, out, cout, tile_cols=tile, in_mode=IN_GROUP, a_src=feats_pm, a_ch=D, a_rows=N,
+                  idx=idx, xyz=xyz, centers=centers, group_k=N, out_mode=OUT_POOL, pool_g=N)
+        return None, out
+    S, K = module.num_points, module.num_samples_list[0]
+    fps_idx = cuda_ops.farthest_point_sampling(xyz, S)
+    new_xyz = torch.gather(xyz, 1, fps_idx.long().unsqueeze(-1).expand(-1, -1, 3))
+    group_idx = cuda_ops.ball_query(new_xyz, xyz, module.radius_list[0], K)
+    out = torch.empty(B, S, cout, dtype=torch.float32, device=dev)
+    run_chain(pc, B, S * K, out, cout, tile_cols=pick_tile(pc.dims, S * K), in_mode=IN_GROUP, a_src=feats_pm, a_ch=D, a_rows=N,
+              idx=group_idx, xyz=xyz, centers=new_xyz, group_k=K, out_mode=OUT_POOL, pool_g=K)
+    return new_xyz, out
+
+
+def _fp_chain(module, device, split=None):
+    """split = number of leading input channels of layer 0 that are a per-cloud constant
+    (FP1: the broadcast global feature) -> returns (chain without them, const-part weight)."""
+    key = _CACHE_ATTR + ("_s%d_%d" % split if split else "")
+    pc = getattr(module, key, None)
+    if pc is None or pc[0].weights.device != device:
+        layers, wconst = [], None
+        for j, (conv, bn) in enumerate(zip(module.mlp_convs, module.mlp_bns)):
+            w, b = fold_bn(conv.weight, conv.bias, bn)
+            if j == 0 and split:
+                # the constant part becomes its own one-layer chain (with the layer's bias)
+                wconst = PackedChain([(np.ascontiguousarray(w[:, split[0]:split[1]]), b, False)], device)
+                w = np.concatenate([w[:, :split[0]], w[:, split[1]:]], axis=1)
+            layers.append((w, b, True))
+        pc = (PackedChain(layers, device), wconst)
+        setattr(module, key, pc)
+    return pc
+
+
+def fp_forward_pm(module, xyz1, xyz2, feats1_pm, feats2_pm):
+    """Point-major feature propagation.  xyz1 [B,N,3], xyz2 [B,S,3] | None, feats1_pm [B,N,D1] | None,
+    feats2_pm [B,S,D2] -> [B,N,D']."""
+    B, N, _ = xyz1.shape
+    dev = xyz1.device
+    D1 = 0 if feats1_pm is None else feats1_pm.shape[2]
+    if xyz2 is None:
+        # pos2 is None: feats2 is one row per cloud, repeated over the N points (reference :33-34).
+        # Its contribution to layer 0 is a per-cloud constant: fold it into a per-cloud bias.
+        D2 = feats2_pm.shape[2]
+        pc, wconst = _fp_chain(module, dev, split=(D1, D1 + D2))
+        g = feats2_pm.reshape(B, D2).contiguous()
+        bias0 = torch.zeros(B, pc.biases[0].numel(), dtype=torch.float32, device=dev)
+        run_chain(wconst, B, 1, bias0, bias0.shape[1], tile_cols=32, in_mode=IN_DENSE, a_src=g, a_ch=D2, a_rows=1)
+        out = torch.empty(B, N, pc.dims[-1][1], dtype=torch.float32, device=dev)
+        tile = pick_tile(pc.dims, N, need_cloud_aligned=True)
+        run_chain(pc, B, N, out, out.shape[2], tile_cols=tile, in_mode=IN_DENSE, a_src=feats1_pm, a_ch=D1, a_rows=N,
+                  biases=[bias0] + [None] * (len(pc.dims) - 1), bias_per_cloud=(0,))
+        return out
+    pc, _ = _fp_chain(module, dev)
+    dist2, idx = cuda_ops.three_nn(xyz1, xyz2)
+    recip = 1.0 / (torch.sqrt(dist2) + 1e-8)
+    w = (recip / torch.sum(recip, dim=2, keepdim=True)).contiguous()
+    out = torch.empty(B, N, pc.dims[-1][1], dtype=torch.float32, device=dev)
+    run_chain(pc, B, N, out, out.shape[2], tile_cols=pick_tile(pc.dims, N), in_mode=IN_INTERP, a_src=feats1_pm, a_ch=D1, a_rows=N,
+              idx=idx, b_src=feats2_pm, b_ch=feats2_pm.shape[2], b_rows=feats2_pm.shape[1], nn_w=w)
+    return out
+
+
+def _pm(t):
+    return None if t is None else t.permute(0, 2, 1).contiguous()
+
+
+def set_abstraction_forward(module, pos, feats):
+    """Reference-layout wrapper: pos [B,3,N], feats [B,D,N] | None -> (new_pos [B,3,S] | None, [B,D',S])."""
+    new_xyz, out = sa_forward_pm(module, _pm(pos.float()), _pm(feats))
+    return (None if new_xyz is None else new_xyz.permute(0, 2, 1)), out.permute(0, 2, 1)
+
+
+def feature_propagation_forward(module, pos1, pos2, feats1, feats2):
+    out = fp_forward_pm(module, _pm(pos1.float()), _pm(pos2), _pm(feats1), _pm(feats2))
+    return out.permute(0, 2, 1)
+
+
+def _head_chain(model, device):
+    pc = getattr(model, _CACHE_ATTR, None)
+    if pc is None or pc[0].weights.device != device:
+        layers = []
+        for conv, bn in zip(model.sfp3.mlp_convs, model.sfp3.mlp_bns):
+            w, b = fold_bn(conv.weight, conv.bias, bn)
+            layers.append((w, b, True))
+        w, b = fold_bn(model.fc1.weight, model.fc1.bias, model.bn1)
+        layers.append((w, b, True))
+        hw = np.concatenate([fold_bn(fc.weight, fc.bias, None)[0] for fc in model.fc2], axis=0)
+        hb = np.concatenate([fold_bn(fc.weight, fc.bias, None)[1] for fc in model.fc2], axis=0)
+        layers.append((hw, hb, False))
+        pc = (PackedChain(layers, device), [fc.out_channels for fc in model.fc2])
+        setattr(model, _CACHE_ATTR, pc)
+    return pc
+
+
+@torch.no_grad()
+def pointnet2_forward(model, P, dropout=True):
+    """Whole PointNet2 forward (reference pn2_network.py:38-73) on the fused kernels.
+    P [B,N,3] float32 CUDA.  FP3, fc1 + bn1 + ReLU, dropout and the heads are ONE chain.
+    Returns (heads [list of [B,N,o_i]], l3_feats [B,1024,1], output_feat [B,128,N], l1_xyz, l2_xyz)."""
+    assert not (model.use_glob_features or model.use_loc_features or model.features_extractor)
+    P = P.float().contiguous()
+    B, N, _ = P.shape
+    dev = P.device
+    l1_xyz, l1 = sa_forward_pm(model.sa1, P, None)
+    l2_xyz, l2 = sa_forward_pm(model.sa2, l1_xyz, l1)
+    _, l3 = sa_forward_pm(model.sa3, l2_xyz, l2)
+    l4 = fp_forward_pm(model.sfp1, l2_xyz, None, l2, l3)
+    l5 = fp_forward_pm(model.sfp2, l1_xyz, l2_xyz, l1, l4)
+    pc, head_sizes = _head_chain(model, dev)
+    n_out = sum(head_sizes)
+    dist2, idx = cuda_ops.three_nn(P, l1_xyz)
+    recip = 1.0 / (torch.sqrt(dist2) + 1e-8)
+    w = (recip / torch.sum(recip, dim=2, keepdim=True)).contiguous()
+    heads = torch.empty(B, N, n_out, dtype=torch.float32, device=dev)
+    output_feat = torch.empty(B, 128, N, dtype=torch.float32, device=dev)
+    fc1_layer = len(pc.dims) - 2
+    masks = None
+    if dropout:
+        # the reference's always-on dropout (pn2_network.py:63): same generator, same shape, same mask
+        masks = {fc1_layer: torch.nn.functional.dropout(torch.ones(B, 128, N, device=dev), p=0.5)}
+    run_chain(pc, B, N, heads, n_out, tile_cols=pick_tile(pc.dims, N, need_cloud_aligned=True), in_mode=IN_INTERP, a_src=None, a_ch=0, a_rows=N, idx=idx,
+              b_src=l5, b_ch=l5.shape[2], b_rows=l5.shape[1], nn_w=w, masks=masks, out_cm={fc1_layer: output_feat})
+    outs, o = [], 0
+    for n in head_sizes:
+        outs.append(heads[:, :, o:o + n])
+        o += n
+    return outs, l3.reshape(B, -1, 1), output_feat, l1_xyz, l2_xyz

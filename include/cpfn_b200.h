@@ -132,6 +132,51 @@ CPFN_API int cpfn_fit_primitives(const float *P, const float *W, const float *X,
                                  int N, int K, float *out, void *workspace,
                                  size_t workspace_bytes, cpfn_stream_t stream);
 
+/* ---------------------------------------------------------------------------
+ * Fused shared-MLP chains (set abstraction, feature propagation, heads) on the
+ * tcgen05 tensor cores.  Inference only: BatchNorm is folded into the weights.
+ * ------------------------------------------------------------------------- */
+#define CPFN_MLP_MAX_LAYERS 6
+#define CPFN_MLP_IN_DENSE 0   /* rows of a_src [cols, a_ch] */
+#define CPFN_MLP_IN_GROUP 1   /* [a_src[b, idx] (a_ch) | xyz[b, idx] - centers[b, col / group_k] (3)] */
+#define CPFN_MLP_IN_INTERP 2  /* [a_src[col] (a_ch, skip) | sum_q nn_w[col,q] * b_src[b, idx[col,q]] (b_ch)] */
+#define CPFN_MLP_OUT_ROWS 0   /* out [cols, ldo]: every column's last-layer output */
+#define CPFN_MLP_OUT_POOL 1   /* out [cols / pool_g, ldo]: max over each group of pool_g columns */
+
+typedef struct {
+  int32_t cin, cout;          /* real channel counts; layer l+1 cin == layer l cout */
+  int32_t relu;               /* ReLU after the bias */
+  int32_t bias_per_cloud;     /* bias is [B, 128*ceil(cout/128)] instead of [128*ceil(cout/128)] */
+  const float *bias;          /* BN-folded bias, zero padded to a multiple of 128 */
+  const float *mask;          /* optional multiplicative mask [B, cout, cols_per_cloud] after ReLU (dropout) */
+  float *out_cm;              /* optional channel-major copy [B, cout, cols_per_cloud] of this layer's output */
+} cpfn_mlp_layer_t;
+
+typedef struct {
+  int32_t n_layers;
+  cpfn_mlp_layer_t layers[CPFN_MLP_MAX_LAYERS];
+  const void *weights;        /* device: the layers' cpfn_mlp_pack_weights_host images, concatenated */
+  size_t weight_bytes;
+  int32_t tile_cols;          /* 128, 64 or 32 columns per CTA tile */
+  int32_t in_mode;            /* CPFN_MLP_IN_* */
+  int32_t B, cols_per_cloud;  /* columns = B * cols_per_cloud (S*K grouped samples, or N points) */
+  const float *a_src; int32_t a_ch; int32_t a_rows;   /* point-major [B, a_rows, a_ch] (DENSE / INTERP: rows = columns) */
+  const int32_t *idx;         /* GROUP: [B,S,K] ball-query result; INTERP: [B,N,3] three_nn indices */
+  const float *xyz;           /* GROUP: [B, a_rows, 3] */
+  const float *centers;       /* GROUP: [B, S, 3] */
+  int32_t group_k;            /* GROUP: K (columns per centre) */
+  const float *b_src; int32_t b_ch; int32_t b_rows;   /* INTERP: [B, b_rows, b_ch] */
+  const float *nn_w;          /* INTERP: [B,N,3] interpolation weights */
+  int32_t out_mode;           /* CPFN_MLP_OUT_* */
+  float *out; int32_t ldo; int32_t pool_g;
+} cpfn_mlp_chain_t;
+
+/* Replaces the conv+BN+ReLU(+max) chains of pointset_abstraction.py:61-74,
+ * pointset_feature_propagation.py:36-51 and pn2_network.py:60-68 (see csrc/mlp_chain.cu). */
+CPFN_API size_t cpfn_mlp_packed_bytes(int cout, int cin);
+CPFN_API int cpfn_mlp_pack_weights_host(const float *W_host, int cout, int cin, void *packed_host);
+CPFN_API int cpfn_mlp_chain(const cpfn_mlp_chain_t *chain, cpfn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
