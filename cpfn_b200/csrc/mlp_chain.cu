@@ -10,13 +10,13 @@
 //
 // One CTA owns a tile of NT columns (grouped samples, or points) and carries it through
 // EVERY layer of the chain without leaving the SM:
-//   worker warps  build the input tile [NT x Cin] in shared memory (gather by ball-query index
-//                 and recentre / 3-point weighted interpolation + skip concat / dense rows),
-//                 rounded to TF32, in the canonical K-major 128-byte-swizzled UMMA layout;
-//   MMA thread    for each layer issues tcgen05.mma.kind::tf32 (M = 128 output channels, N = NT
-//                 columns, K = 8 per instruction): D[ch, col] += W[ch, k] * A[col, k], with the
+//   8 worker warps build the input tile [NT x Cin] in shared memory (gather by ball-query index
+//                 and recentre / 3-point weighted interpolation + skip concat / dense rows) in the
+//                 canonical K-major 128-byte-swizzled UMMA layout;
+//   MMA thread    for each layer issues tcgen05.mma.kind::f16 (M = 128 output channels, N = NT
+//                 columns, K = 16 per instruction): D[ch, col] += W[ch, k] * A[col, k], with the
 //                 fp32 accumulators in TMEM;
-//   producer      streams the BN-folded, pre-swizzled weight blocks (16 KB = 128 ch x 32 k)
+//   producer      streams the BN-folded, pre-swizzled weight blocks (16 KB = 128 ch x 64 k bf16)
 //                 through an mbarrier ring with cp.async.bulk (TMA bulk copy), running ahead
 //                 across layer boundaries;
 //   worker warps  read the accumulators back (tcgen05.ld, thread = channel), add the folded
@@ -24,23 +24,33 @@
 //                 layer's operand tile straight into shared memory -- or, after the last layer,
 //                 max-pool over each group of columns in registers / store the rows.
 // The grouped tensor, the interpolated tensor and all intermediate activations never exist in
-// HBM.  Arithmetic: TF32 operands (round-to-nearest), fp32 accumulate (north_star tolerance
-// for the MLP path: 1e-3 relative).
+// HBM.
+//
+// Arithmetic: split-bf16 ("bf16x3").  Every fp32 operand x is held as hi = bf16(x) and
+// lo = bf16(x - hi) (together 16 mantissa bits) and each product is accumulated in fp32 as
+// a_hi*w_hi + a_lo*w_hi + a_hi*w_lo: three bf16 MMAs at twice the TF32 rate, i.e. 3/4 of the
+// tensor time of one TF32 pass and the same shared-memory footprint as fp32 operands, with a
+// per-product error of ~2^-16 instead of TF32's 2^-11.  Measured end-to-end error of the
+// 14-layer GlobalSPFN forward against the fp32 oracle: ~1e-5 of the tensor scale (plain TF32:
+// 2e-3 .. 5e-3, which misses the 1e-3 tolerance of the north star).
 #include <string.h>
+
+#include <cuda_bf16.h>
 
 #include "common.cuh"
 
 namespace cpfn {
 namespace {
 
-constexpr int kChainThreads = 192;   // warp 0 producer, warp 1 MMA (+ TMEM alloc), warps 2-5 workers
-constexpr int kWorkers = 128;
-constexpr int kStageBytes = 16384;   // one weight block: 128 rows x 128 B
+constexpr int kChainThreads = 320;   // warp 0 producer, warp 1 MMA (+ TMEM alloc), warps 2-9 workers
+constexpr int kWorkers = 256;
+constexpr int kStageBytes = 16384;   // one weight block: 128 rows x 128 B (64 bf16)
 constexpr int kMaxLayers = CPFN_MLP_MAX_LAYERS;
 constexpr int kMaxStages = 8;
+constexpr int kMiscBytes = 4096;     // barriers, TMEM slot, per-row loader scratch
 
 struct LayerP {
-  int cin_atoms, ksteps, cout_chunks, cout, relu, bias_per_cloud, next_atoms;
+  int cin_atoms, ksteps, cout_chunks, cout, relu, bias_per_cloud, next_k16;
   const float *bias;
   const float *mask;
   float *out_cm;
@@ -94,6 +104,7 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t *slot, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -104,35 +115,42 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ float to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+__device__ __forceinline__ void st_shared_b32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
-__device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) {
-  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+__device__ __forceinline__ void st_shared_v2(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
 }
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, float4 v) {
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+__device__ __forceinline__ void st_shared_u16(uint32_t addr, uint16_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
+
+// bf16x2 pack: low half = bf16(a), high half = bf16(b)  (one cvt.rn.bf16x2.f32)
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t *>(&h);
+}
+// (hi, lo) split of two floats: H = {bf16(a), bf16(b)}, L = {bf16(a - hi_a), bf16(b - hi_b)}
+__device__ __forceinline__ void split2(float a, float b, uint32_t &H, uint32_t &L) {
+  H = pack_bf16(a, b);
+  const float ha = __uint_as_float(H << 16), hb = __uint_as_float(H & 0xFFFF0000u);
+  L = pack_bf16(a - ha, b - hb);
 }
 
 // Shared-memory matrix descriptor, K-major, SWIZZLE_128B: start address, LBO (ignored for
@@ -147,105 +165,123 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   return d;
 }
 
-// Byte offset of element (row, channel) in an activation tile: K-atoms of 32 channels,
-// each [NT rows x 128 B] with the 16-byte chunks XOR-swizzled by (row & 7).
+// Activation tile of one K-atom (64 channels): a "hi" and a "lo" part, each [NT rows x 128 B]
+// with the 16-byte chunks XOR-swizzled by (row & 7).  Byte offset of channel e (0..63) of `row`
+// inside a part, and of part (atom, lo?) inside the buffer:
+__device__ __forceinline__ uint32_t part_off(int row, int e) {
+  return static_cast<uint32_t>((row >> 3) * 1024 + (row & 7) * 128 + ((((e >> 3) ^ (row & 7)) << 4) | ((e & 7) << 1)));
+}
 template <int NT>
-__device__ __forceinline__ uint32_t act_off(int row, int ch) {
-  const int atom = ch >> 5, e = ch & 31;
-  return static_cast<uint32_t>(atom * (NT * 128) + (row >> 3) * 1024 + (row & 7) * 128 +
-                               ((((e >> 2) ^ (row & 7)) << 4) | ((e & 3) << 2)));
+__device__ __forceinline__ uint32_t part_base(int atom, int lo) { return static_cast<uint32_t>((2 * atom + lo) * (NT * 128)); }
+
+template <int NT>
+__device__ __forceinline__ void store_scalar(uint32_t buf, int row, int ch, float v) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+  const uint32_t o = part_base<NT>(ch >> 6, 0) + part_off(row, ch & 63);
+  st_shared_u16(buf + o, *reinterpret_cast<const uint16_t *>(&h));
+  st_shared_u16(buf + o + NT * 128, *reinterpret_cast<const uint16_t *>(&l));
 }
 
-// ---- input tile builders (128 worker threads) -------------------------------------------------
 template <int NT>
-__device__ void load_tile(const ChainP &p, uint32_t buf, long long col0, int wq, int lane) {
-  constexpr int RB = 8;                      // rows in flight per warp
-  const int cin_pad = p.L[0].cin_atoms * 32;
-  const int nA4 = p.a_ch >> 2;
-  for (int r0 = wq * RB; r0 < NT; r0 += 4 * RB) {
-    long long col[RB];
-    long long arow[RB];
-    bool valid[RB];
-#pragma unroll
-    for (int u = 0; u < RB; ++u) {
-      col[u] = col0 + r0 + u;
-      valid[u] = col[u] < p.cols;
-      const long long c = valid[u] ? col[u] : 0;
-      if (p.in_mode == CPFN_MLP_IN_GROUP) {
-        const long long cloud = c / p.cols_per_cloud;
-        arow[u] = cloud * p.a_rows + __ldg(p.idx + c);
-      } else {
-        arow[u] = c;
-      }
-    }
-    // segment A: a_ch channels copied from a_src rows
-    for (int c4 = lane; c4 < nA4; c4 += 32) {
-      float4 v[RB];
-#pragma unroll
-      for (int u = 0; u < RB; ++u)
-        v[u] = valid[u] ? __ldg(reinterpret_cast<const float4 *>(p.a_src + arow[u] * p.a_ch) + c4)
-                        : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int u = 0; u < RB; ++u) {
-        const int row = r0 + u;
-        const float4 t = make_float4(to_tf32(v[u].x), to_tf32(v[u].y), to_tf32(v[u].z), to_tf32(v[u].w));
-        st_shared_v4(buf + act_off<NT>(row, c4 * 4), t);
-      }
-    }
-    int done = p.a_ch;
+__device__ __forceinline__ void store_quad(uint32_t buf, int row, int c4, float4 v) {
+  uint32_t H01, L01, H23, L23;
+  split2(v.x, v.y, H01, L01);
+  split2(v.z, v.w, H23, L23);
+  const uint32_t o = part_base<NT>(c4 >> 4, 0) + part_off(row, (c4 & 15) * 4);
+  st_shared_v2(buf + o, H01, H23);
+  st_shared_v2(buf + o + NT * 128, L01, L23);
+}
+
+// ---- input tile builder (256 worker threads) --------------------------------------------------
+// Phase A: one thread per row resolves the row's source indices (one dependent-load chain for
+// the whole tile) and writes the 3 recentred coordinates / the zero padding.  Phase B: one warp
+// per row copies (or interpolates) the feature rows, 8 rows in flight.
+template <int NT>
+__device__ void load_tile(const ChainP &p, uint32_t buf, long long col0, int w8, int lane, int *s_arow,
+                          int *s_brow, float *s_w) {
+  const int t = w8 * 32 + lane;
+  const int cin = p.a_ch + (p.in_mode == CPFN_MLP_IN_GROUP ? 3 : (p.in_mode == CPFN_MLP_IN_INTERP ? p.b_ch : 0));
+  const int k16 = p.L[0].ksteps * 16;
+  if (t < NT) {
+    const long long col = col0 + t;
+    const bool valid = col < p.cols;
+    const long long c = valid ? col : 0;
+    const long long cloud = c / p.cols_per_cloud;
+    int arow = static_cast<int>(c);
+    int pad_from = cin;
     if (p.in_mode == CPFN_MLP_IN_GROUP) {
-      // segment B: recentred position (pointset_abstraction.py:62-63): xyz[idx] - centre
-      if (lane < 3) {
+      arow = static_cast<int>(cloud * p.a_rows + __ldg(p.idx + c));
+      // recentred position (pointset_abstraction.py:62-63): xyz[idx] - centre
+      const float *a = p.xyz + static_cast<long long>(arow) * 3;
+      const float *ce = p.centers + (c / p.group_k) * 3;
 #pragma unroll
-        for (int u = 0; u < RB; ++u) {
-          float d = 0.f;
-          if (valid[u]) {
-            const float a = __ldg(p.xyz + arow[u] * 3 + lane);
-            const float c = __ldg(p.centers + (col[u] / p.group_k) * 3 + lane);
-            d = __fsub_rn(a, c);
-          }
-          st_shared_f32(buf + act_off<NT>(r0 + u, p.a_ch + lane), to_tf32(d));
-        }
+      for (int q = 0; q < 3; ++q) {
+        const float d = valid ? __fsub_rn(__ldg(a + q), __ldg(ce + q)) : 0.f;
+        store_scalar<NT>(buf, t, p.a_ch + q, d);
       }
-      done += 3;
     } else if (p.in_mode == CPFN_MLP_IN_INTERP) {
-      // segment B: three_weighted_sum (interpolate_gpu.cu:98-99): fma(p3,w3, fma(p1,w1, p2*w2))
-      const int nB4 = p.b_ch >> 2;
-      long long brow[RB][3];
-      float w[RB][3];
 #pragma unroll
-      for (int u = 0; u < RB; ++u) {
-        const long long c = valid[u] ? col[u] : 0;
-        const long long cloud = c / p.cols_per_cloud;
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-          brow[u][q] = cloud * p.b_rows + __ldg(p.idx + c * 3 + q);
-          w[u][q] = __ldg(p.nn_w + c * 3 + q);
-        }
+      for (int q = 0; q < 3; ++q) {
+        s_brow[t * 3 + q] = static_cast<int>(cloud * p.b_rows + __ldg(p.idx + c * 3 + q));
+        s_w[t * 3 + q] = __ldg(p.nn_w + c * 3 + q);
       }
-      for (int c4 = lane; c4 < nB4; c4 += 32) {
-#pragma unroll
-        for (int u = 0; u < RB; ++u) {
-          float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (valid[u]) {
-            const float4 f1 = __ldg(reinterpret_cast<const float4 *>(p.b_src + brow[u][0] * p.b_ch) + c4);
-            const float4 f2 = __ldg(reinterpret_cast<const float4 *>(p.b_src + brow[u][1] * p.b_ch) + c4);
-            const float4 f3 = __ldg(reinterpret_cast<const float4 *>(p.b_src + brow[u][2] * p.b_ch) + c4);
-            o.x = __fmaf_rn(f3.x, w[u][2], __fmaf_rn(f1.x, w[u][0], __fmul_rn(f2.x, w[u][1])));
-            o.y = __fmaf_rn(f3.y, w[u][2], __fmaf_rn(f1.y, w[u][0], __fmul_rn(f2.y, w[u][1])));
-            o.z = __fmaf_rn(f3.z, w[u][2], __fmaf_rn(f1.z, w[u][0], __fmul_rn(f2.z, w[u][1])));
-            o.w = __fmaf_rn(f3.w, w[u][2], __fmaf_rn(f1.w, w[u][0], __fmul_rn(f2.w, w[u][1])));
-          }
-          const float4 t = make_float4(to_tf32(o.x), to_tf32(o.y), to_tf32(o.z), to_tf32(o.w));
-          st_shared_v4(buf + act_off<NT>(r0 + u, p.a_ch + c4 * 4), t);
-        }
-      }
-      done += p.b_ch;
     }
-    // zero the K padding (a zero weight times stale shared memory could still be NaN)
-    for (int ch = done + lane; ch < cin_pad; ch += 32) {
+    s_arow[t] = valid ? arow : -1;
+    for (int ch = pad_from; ch < k16; ++ch) store_scalar<NT>(buf, t, ch, 0.f);   // K padding must be finite zeros
+  }
+  worker_bar();
+  constexpr int RB = 8;
+  const int nA4 = p.a_ch >> 2;
+  if (nA4 > 0) {
+    for (int r0 = w8; r0 < NT; r0 += 8 * RB) {
+      int arow[RB];
 #pragma unroll
-      for (int u = 0; u < RB; ++u) st_shared_f32(buf + act_off<NT>(r0 + u, ch), 0.f);
+      for (int u = 0; u < RB; ++u) arow[u] = (r0 + 8 * u < NT) ? s_arow[r0 + 8 * u] : -1;
+      for (int c4 = lane; c4 < nA4; c4 += 32) {
+        float4 v[RB];
+#pragma unroll
+        for (int u = 0; u < RB; ++u)
+          v[u] = arow[u] >= 0 ? __ldg(reinterpret_cast<const float4 *>(p.a_src + static_cast<long long>(arow[u]) * p.a_ch) + c4)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < RB; ++u)
+          if (r0 + 8 * u < NT) store_quad<NT>(buf, r0 + 8 * u, c4, v[u]);
+      }
+    }
+  }
+  if (p.in_mode == CPFN_MLP_IN_INTERP) {
+    // three_weighted_sum (interpolate_gpu.cu:98-99 as compiled): fma(p3,w3, fma(p1,w1, p2*w2))
+    constexpr int RI = 4;
+    const int nB4 = p.b_ch >> 2, a4 = p.a_ch >> 2;
+    for (int r0 = w8; r0 < NT; r0 += 8 * RI) {
+      for (int c4 = lane; c4 < nB4; c4 += 32) {
+        float4 f[RI][3];
+        float w[RI][3];
+        bool ok[RI];
+#pragma unroll
+        for (int u = 0; u < RI; ++u) {
+          const int r = r0 + 8 * u;
+          ok[u] = r < NT && s_arow[r < NT ? r : 0] >= 0;
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            w[u][q] = ok[u] ? s_w[r * 3 + q] : 0.f;
+            f[u][q] = ok[u] ? __ldg(reinterpret_cast<const float4 *>(p.b_src + static_cast<long long>(s_brow[r * 3 + q]) * p.b_ch) + c4)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < RI; ++u) {
+          const int r = r0 + 8 * u;
+          if (r >= NT) continue;
+          float4 o;
+          o.x = __fmaf_rn(f[u][2].x, w[u][2], __fmaf_rn(f[u][0].x, w[u][0], __fmul_rn(f[u][1].x, w[u][1])));
+          o.y = __fmaf_rn(f[u][2].y, w[u][2], __fmaf_rn(f[u][0].y, w[u][0], __fmul_rn(f[u][1].y, w[u][1])));
+          o.z = __fmaf_rn(f[u][2].z, w[u][2], __fmaf_rn(f[u][0].z, w[u][0], __fmul_rn(f[u][1].z, w[u][1])));
+          o.w = __fmaf_rn(f[u][2].w, w[u][2], __fmaf_rn(f[u][0].w, w[u][0], __fmul_rn(f[u][1].w, w[u][1])));
+          store_quad<NT>(buf, r, a4 + c4, o);
+        }
+      }
     }
   }
 }
@@ -262,6 +298,9 @@ mlp_chain_kernel(const __grid_constant__ ChainP p) {
   uint64_t *full = bars, *empty = bars + kMaxStages, *act_ready = bars + 2 * kMaxStages,
            *acc_full = bars + 2 * kMaxStages + 1;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kMaxStages + 2);
+  int *s_arow = reinterpret_cast<int *>(bars + 32);          // [128]
+  int *s_brow = s_arow + 128;                                // [128][3]
+  float *s_w = reinterpret_cast<float *>(s_brow + 384);      // [128][3]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -293,9 +332,9 @@ mlp_chain_kernel(const __grid_constant__ ChainP p) {
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one thread) =====
+    // ===== MMA issuer (one thread): per K-atom  D += Whi*Ahi + Whi*Alo  then  D += Wlo*Ahi =====
     if (lane == 0) {
-      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(NT >> 3) << 17) |
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(NT >> 3) << 17) |
                                  (static_cast<uint32_t>(128 >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0, act_phase = 0;
@@ -309,34 +348,52 @@ mlp_chain_kernel(const __grid_constant__ ChainP p) {
             act_phase ^= 1;
             tc_fence_after();
             for (int m = 0; m < mc; ++m) {
+              const uint32_t d_tmem = tmem_base + m * NT;
               for (int j = 0; j < L.cin_atoms; ++j) {
-                mbar_wait(full + stage, phase);
-                tc_fence_after();
-                const uint32_t a_base = smem_u32(ring + stage * kStageBytes);
-                const uint32_t b_base = in_buf + j * (NT * 128);
                 const int ks = min(4, L.ksteps - 4 * j);
+                const uint32_t a_hi = in_buf + part_base<NT>(j, 0), a_lo = a_hi + NT * 128;
+                mbar_wait(full + stage, phase);            // W_hi block
+                tc_fence_after();
+                uint32_t w_base = smem_u32(ring + stage * kStageBytes);
+                for (int kk = 0; kk < ks; ++kk) {
+                  umma_bf16(d_tmem, make_desc(w_base + kk * 32), make_desc(a_hi + kk * 32), idesc, (j | kk) != 0 ? 1u : 0u);
+                  umma_bf16(d_tmem, make_desc(w_base + kk * 32), make_desc(a_lo + kk * 32), idesc, 1u);
+                }
+                umma_commit(empty + stage);                // frees the stage when these MMAs retire
+                if (++stage == p.nstage) { stage = 0; phase ^= 1; }
+                mbar_wait(full + stage, phase);            // W_lo block
+                tc_fence_after();
+                w_base = smem_u32(ring + stage * kStageBytes);
                 for (int kk = 0; kk < ks; ++kk)
-                  umma_tf32(tmem_base + m * NT, make_desc(a_base + kk * 32), make_desc(b_base + kk * 32), idesc,
-                            (j | kk) != 0 ? 1u : 0u);
-                umma_commit(empty + stage);          // frees the weight stage when these MMAs retire
+                  umma_bf16(d_tmem, make_desc(w_base + kk * 32), make_desc(a_hi + kk * 32), idesc, 1u);
+                umma_commit(empty + stage);
                 if (++stage == p.nstage) { stage = 0; phase ^= 1; }
               }
             }
-            umma_commit(acc_full);                   // accumulators of this wave complete
+            umma_commit(acc_full);                         // accumulators of this wave complete
           }
         }
       }
     }
   } else {
     // ===== workers: build the input tile, then the epilogue of every layer =====
+    const int w8 = warp - 2;                          // 0..7
     const int wq = warp & 3;                          // TMEM lane quarter this warp may access
+    const int half = (w8 >> 2);                       // which half of the tile's columns
+    const int par = lane & 1;
     const int row_in_chunk = wq * 32 + lane;
+    const int e_pair = ((wq & 1) * 32 + lane) & ~1;   // channel (within the 64-wide atom) of the pair's even lane
+    uint32_t swz[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) swz[k] = part_off(2 * k + par, e_pair);
+    const uint32_t sel_send = par ? 0x5410u : 0x7632u, sel_keep = par ? 0x7632u : 0x5410u;
+    constexpr int HC = NT / 2;                        // columns per worker warp
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const long long col0 = static_cast<long long>(tile) * NT;
       const long long cloud = col0 / p.cols_per_cloud;
       const long long n_in_cloud = col0 - cloud * p.cols_per_cloud;
-      load_tile<NT>(p, smem_u32(act0), col0, wq, lane);
+      load_tile<NT>(p, smem_u32(act0), col0, w8, lane, s_arow, s_brow, s_w);
       fence_proxy_async();
       mbar_arrive(act_ready);
       for (int l = 0; l < p.n_layers; ++l) {
@@ -344,6 +401,7 @@ mlp_chain_kernel(const __grid_constant__ ChainP p) {
         const bool last = (l == p.n_layers - 1);
         const uint32_t out_buf = smem_u32((l & 1) ? act0 : act1);
         const int cout_pad = L.cout_chunks * 128;
+        const bool slow = (L.mask != nullptr) || (L.out_cm != nullptr);
         for (int m0 = 0; m0 < L.cout_chunks; m0 += wave_max) {
           const int mc = min(wave_max, L.cout_chunks - m0);
           mbar_wait(acc_full, acc_phase);
@@ -353,36 +411,69 @@ mlp_chain_kernel(const __grid_constant__ ChainP p) {
             const int ch = (m0 + m) * 128 + row_in_chunk;
             const bool ch_real = ch < L.cout;
             const float bias = __ldg(L.bias + (L.bias_per_cloud ? cloud * cout_pad : 0) + ch);
-            const bool to_smem = !last && ch < L.next_atoms * 32;
+            const bool to_smem = !last && (ch & ~1) < L.next_k16;
+            const uint32_t o_hi = out_buf + part_base<NT>(ch >> 6, 0);
             const size_t cm_base = (static_cast<size_t>(cloud) * L.cout + ch) * p.cols_per_cloud + n_in_cloud;
-            float pool = 0.f;                         // post-ReLU values are >= 0
-            for (int c0 = 0; c0 < NT; c0 += 32) {
-              uint32_t r[32];
-              tmem_ld32(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + m * NT + c0, r);
+            float pool = 0.f;                          // post-ReLU values are >= 0
+#pragma unroll 1
+            for (int cb = 0; cb < HC; cb += 16) {
+              const int c = half * HC + cb;            // first column of this batch inside the tile
+              uint32_t r[16];
+              tmem_ld16(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + m * NT + c, r);
+              float v[16];
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                float v = __uint_as_float(r[i]) + bias;
-                if (L.relu) v = fmaxf(v, 0.f);
-                const bool col_ok = col0 + c0 + i < p.cols;
-                if (L.mask != nullptr && ch_real && col_ok) v *= __ldg(L.mask + cm_base + c0 + i);
-                if (L.out_cm != nullptr && ch_real && col_ok) L.out_cm[cm_base + c0 + i] = v;
-                if (to_smem) st_shared_f32(out_buf + act_off<NT>(c0 + i, ch), to_tf32(v));
-                if (last) {
-                  if (p.out_mode == CPFN_MLP_OUT_ROWS) {
-                    if (ch_real && col_ok) p.out[(col0 + c0 + i) * p.ldo + ch] = v;
-                  } else {
-                    pool = fmaxf(pool, col_ok ? v : 0.f);
-                    if (p.pool_g <= NT && ((c0 + i + 1) % p.pool_g) == 0) {
-                      const long long grp = (col0 + c0 + i) / p.pool_g;
-                      if (ch_real && col0 + c0 + i + 1 - p.pool_g < p.cols) p.out[grp * p.ldo + ch] = pool;
-                      pool = 0.f;
+              for (int i = 0; i < 16; ++i) {
+                v[i] = __uint_as_float(r[i]) + bias;
+                if (L.relu) v[i] = fmaxf(v[i], 0.f);
+              }
+              if (slow && ch_real) {                   // dropout mask / channel-major copy (fc1 layer)
+#pragma unroll
+                for (int i4 = 0; i4 < 4; ++i4) {
+                  if (col0 + c + i4 * 4 < p.cols) {    // tiles are cloud-aligned here: whole quads are valid
+                    if (L.mask != nullptr) {
+                      const float4 mk = __ldg(reinterpret_cast<const float4 *>(L.mask + cm_base + c) + i4);
+                      v[i4 * 4] *= mk.x; v[i4 * 4 + 1] *= mk.y; v[i4 * 4 + 2] *= mk.z; v[i4 * 4 + 3] *= mk.w;
                     }
+                    if (L.out_cm != nullptr)
+                      reinterpret_cast<float4 *>(L.out_cm + cm_base + c)[i4] =
+                          make_float4(v[i4 * 4], v[i4 * 4 + 1], v[i4 * 4 + 2], v[i4 * 4 + 3]);
                   }
                 }
               }
+              if (!last) {
+                // next layer's operand: (hi, lo) bf16 split, channel pairs packed into 32-bit words
+                const uint32_t rowgrp = o_hi + static_cast<uint32_t>(c >> 3) * 1024;
+#pragma unroll
+                for (int i = 0; i < 16; i += 2) {
+                  uint32_t H, Lw;
+                  split2(v[i], v[i + 1], H, Lw);
+                  const uint32_t send = __byte_perm(H, Lw, sel_send);
+                  const uint32_t keep = __byte_perm(H, Lw, sel_keep);
+                  const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
+                  const uint32_t a = par ? recv : keep, b = par ? keep : recv;
+                  if (to_smem) {
+                    const uint32_t addr = rowgrp + swz[(i >> 1) & 3] + (i >> 3) * 1024;
+                    st_shared_b32(addr, __byte_perm(a, b, 0x5410));
+                    st_shared_b32(addr + NT * 128, __byte_perm(a, b, 0x7632));
+                  }
+                }
+              } else if (p.out_mode == CPFN_MLP_OUT_ROWS) {
+                if (ch_real) {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i)
+                    if (col0 + c + i < p.cols) p.out[(col0 + c + i) * p.ldo + ch] = v[i];
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) pool = fmaxf(pool, (col0 + c + i < p.cols) ? v[i] : 0.f);
+                if (p.pool_g <= HC && ((c + 16) % p.pool_g) == 0) {
+                  if (ch_real && col0 + c + 16 - p.pool_g < p.cols) p.out[((col0 + c) / p.pool_g) * p.ldo + ch] = pool;
+                  pool = 0.f;
+                }
+              }
             }
-            if (last && p.out_mode == CPFN_MLP_OUT_POOL && p.pool_g > NT && ch_real)
-              atomicMax(reinterpret_cast<int *>(p.out + (col0 / p.pool_g) * p.ldo + ch), __float_as_int(pool));
+            if (last && p.out_mode == CPFN_MLP_OUT_POOL && p.pool_g > HC && ch_real && col0 + half * HC < p.cols)
+              atomicMax(reinterpret_cast<int *>(p.out + ((col0 + half * HC) / p.pool_g) * p.ldo + ch), __float_as_int(pool));
           }
           tc_fence_before();
           const bool final_wave = last && (m0 + wave_max >= L.cout_chunks);
@@ -415,21 +506,21 @@ int launch_chain(const cpfn_mlp_chain_t *c, cudaStream_t st) {
     const cpfn_mlp_layer_t &s = c->layers[l];
     LayerP &L = p.L[l];
     if (s.cin <= 0 || s.cout <= 0 || !s.bias) return CPFN_EINVAL;
-    L.cin_atoms = (s.cin + 31) / 32;
-    L.ksteps = (s.cin + 7) / 8;
+    L.cin_atoms = (s.cin + 63) / 64;
+    L.ksteps = (s.cin + 15) / 16;
     L.cout_chunks = (s.cout + 127) / 128;
     L.cout = s.cout;
     L.relu = s.relu;
     L.bias_per_cloud = s.bias_per_cloud;
     L.bias = s.bias; L.mask = s.mask; L.out_cm = s.out_cm;
-    L.next_atoms = 0;
+    L.next_k16 = 0;
     if (l > 0) {
       if (s.cin != c->layers[l - 1].cout) return CPFN_EINVAL;
-      p.L[l - 1].next_atoms = L.cin_atoms;
+      p.L[l - 1].next_k16 = L.ksteps * 16;
     }
-    total_blocks += L.cout_chunks * L.cin_atoms;
+    total_blocks += L.cout_chunks * L.cin_atoms * 2;
     if (L.cout_chunks > max_chunks) max_chunks = L.cout_chunks;
-    const size_t in_bytes = static_cast<size_t>(L.cin_atoms) * NT * 128;
+    const size_t in_bytes = static_cast<size_t>(L.cin_atoms) * 2 * NT * 128;
     if (in_bytes > act_need[l & 1]) act_need[l & 1] = in_bytes;
     if ((s.bias_per_cloud || s.mask || s.out_cm) && (c->cols_per_cloud % NT) != 0) return CPFN_EINVAL;
   }
@@ -443,7 +534,7 @@ int launch_chain(const cpfn_mlp_chain_t *c, cudaStream_t st) {
   p.idx = c->idx; p.xyz = c->xyz; p.centers = c->centers; p.group_k = c->group_k;
   p.b_src = c->b_src; p.b_ch = c->b_ch; p.b_rows = c->b_rows; p.nn_w = c->nn_w;
   p.out_mode = c->out_mode; p.out = c->out; p.ldo = c->ldo; p.pool_g = c->pool_g;
-  // input row width must match layer 0
+  // input row width must match layer 0; source row ids are kept as int32
   int width = c->a_ch;
   if (c->in_mode == CPFN_MLP_IN_GROUP) width += 3;
   else if (c->in_mode == CPFN_MLP_IN_INTERP) width += c->b_ch;
@@ -451,15 +542,22 @@ int launch_chain(const cpfn_mlp_chain_t *c, cudaStream_t st) {
   if (c->a_ch > 0 && !c->a_src) return CPFN_EINVAL;
   if (c->in_mode == CPFN_MLP_IN_GROUP && (!c->idx || !c->xyz || !c->centers || c->group_k <= 0)) return CPFN_EINVAL;
   if (c->in_mode == CPFN_MLP_IN_INTERP && (!c->idx || !c->b_src || !c->nn_w)) return CPFN_EINVAL;
+  if (p.cols >= 2147483647LL || static_cast<long long>(c->B) * c->a_rows >= 2147483647LL ||
+      static_cast<long long>(c->B) * c->b_rows >= 2147483647LL) return CPFN_EINVAL;
+  bool atomic_pool = false;
   if (c->out_mode == CPFN_MLP_OUT_POOL) {
-    if (c->pool_g <= 0 || (c->pool_g % 32) != 0 || !c->layers[c->n_layers - 1].relu) return CPFN_EINVAL;
-    if (c->pool_g <= NT ? (NT % c->pool_g) != 0 : ((c->pool_g % NT) != 0 || (c->cols_per_cloud % c->pool_g) != 0))
-      return CPFN_EINVAL;
+    if (c->pool_g <= 0 || (c->pool_g % 16) != 0 || !c->layers[c->n_layers - 1].relu) return CPFN_EINVAL;
+    if (c->pool_g <= NT / 2) {
+      if ((NT / 2) % c->pool_g != 0) return CPFN_EINVAL;
+    } else {
+      if ((c->pool_g % (NT / 2)) != 0 || (c->cols_per_cloud % c->pool_g) != 0) return CPFN_EINVAL;
+      atomic_pool = true;
+    }
   }
   p.tmem_cols = pow2_at_least(NT * (max_chunks < 512 / NT ? max_chunks : 512 / NT));
   p.act_bytes0 = static_cast<int>(act_need[0]);
   p.act_bytes1 = static_cast<int>(act_need[1]);
-  const size_t fixed = act_need[0] + act_need[1] + 1024 /*align*/ + 256 /*barriers*/;
+  const size_t fixed = act_need[0] + act_need[1] + 1024 /*align*/ + kMiscBytes;
   const size_t max_smem = 227 * 1024;
   if (fixed + 2 * kStageBytes > max_smem) return CPFN_EINVAL;
   // Two CTAs per SM (one's epilogue overlaps the other's MMAs) when shared memory and TMEM allow.
@@ -478,7 +576,7 @@ int launch_chain(const cpfn_mlp_chain_t *c, cudaStream_t st) {
   const int sms = sm_count() > 0 ? sm_count() : 148;
   const int grid = p.n_tiles < per_sm * sms ? p.n_tiles : per_sm * sms;
   if (grid <= 0) return CPFN_OK;
-  if (c->out_mode == CPFN_MLP_OUT_POOL && c->pool_g > NT)
+  if (atomic_pool)
     CPFN_CUDA_TRY(cudaMemsetAsync(c->out, 0, sizeof(float) * static_cast<size_t>(p.cols / c->pool_g) * c->ldo, st));
   kern<<<grid, kChainThreads, smem, st>>>(p);
   return check_launch();
@@ -488,34 +586,47 @@ int launch_chain(const cpfn_mlp_chain_t *c, cudaStream_t st) {
 }  // namespace cpfn
 
 // Host-side layout transform: W [cout, cin] row-major fp32 (BatchNorm already folded) ->
-// blocks of 128 output channels x 32 input channels in the kernel's shared-memory image
-// (TF32 round-to-nearest-away, zero padded, 16-byte chunks XOR-swizzled by row & 7),
-// ordered chunk-major then K-atom -- exactly the order the MMA thread consumes them.
+// blocks of 128 output channels x 64 input channels of bf16 in the kernel's shared-memory image
+// (zero padded, 16-byte chunks XOR-swizzled by row & 7).  Every (chunk, K-atom) contributes a
+// "hi" block (bf16(w)) followed by a "lo" block (bf16(w - hi)); blocks are ordered chunk-major
+// then K-atom -- exactly the order the MMA thread consumes them.
+static uint16_t cpfn_bf16_rn(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return static_cast<uint16_t>(u >> 16);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return static_cast<uint16_t>(u >> 16);
+}
+
 extern "C" size_t cpfn_mlp_packed_bytes(int cout, int cin) {
   if (cout <= 0 || cin <= 0) return 0;
-  return static_cast<size_t>((cout + 127) / 128) * ((cin + 31) / 32) * cpfn::kStageBytes;
+  return static_cast<size_t>((cout + 127) / 128) * ((cin + 63) / 64) * 2 * cpfn::kStageBytes;
 }
 
 extern "C" int cpfn_mlp_pack_weights_host(const float *W, int cout, int cin, void *packed) {
   if (!W || !packed || cout <= 0 || cin <= 0) return CPFN_EINVAL;
-  const int chunks = (cout + 127) / 128, atoms = (cin + 31) / 32;
-  uint32_t *dst = static_cast<uint32_t *>(packed);
+  const int chunks = (cout + 127) / 128, atoms = (cin + 63) / 64;
+  uint16_t *dst = static_cast<uint16_t *>(packed);
+  const size_t blk_elems = cpfn::kStageBytes / 2;
   for (int m = 0; m < chunks; ++m)
     for (int j = 0; j < atoms; ++j) {
-      uint32_t *blk = dst + (static_cast<size_t>(m) * atoms + j) * (cpfn::kStageBytes / 4);
+      uint16_t *hi = dst + (static_cast<size_t>(m) * atoms + j) * 2 * blk_elems;
+      uint16_t *lo = hi + blk_elems;
       for (int r = 0; r < 128; ++r)
-        for (int e = 0; e < 32; ++e) {
-          const int co = m * 128 + r, ci = j * 32 + e;
-          uint32_t bits = 0;
+        for (int e = 0; e < 64; ++e) {
+          const int co = m * 128 + r, ci = j * 64 + e;
+          uint16_t h = 0, l = 0;
           if (co < cout && ci < cin) {
-            float f = W[static_cast<size_t>(co) * cin + ci];
-            uint32_t u;
-            memcpy(&u, &f, 4);
-            if ((u & 0x7F800000u) != 0x7F800000u) u += 0x1000u;   // cvt.rna.tf32: nearest, ties away
-            bits = u & 0xFFFFE000u;
+            const float f = W[static_cast<size_t>(co) * cin + ci];
+            h = cpfn_bf16_rn(f);
+            uint32_t hb = static_cast<uint32_t>(h) << 16;
+            float hf;
+            memcpy(&hf, &hb, 4);
+            l = cpfn_bf16_rn(f - hf);
           }
-          const int off = (r >> 3) * 1024 + (r & 7) * 128 + ((((e >> 2) ^ (r & 7)) << 4) | ((e & 3) << 2));
-          blk[off >> 2] = bits;
+          const int off = (r >> 3) * 1024 + (r & 7) * 128 + ((((e >> 3) ^ (r & 7)) << 4) | ((e & 7) << 1));
+          hi[off >> 1] = h;
+          lo[off >> 1] = l;
         }
     }
   return CPFN_OK;

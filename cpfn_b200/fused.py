@@ -128,8 +128,8 @@ def pick_tile(dims, cols_per_cloud, need_cloud_aligned=False, prefer=128):
             continue
         need = [0, 0]
         for l, (cin, _, _) in enumerate(dims):
-            need[l & 1] = max(need[l & 1], (cin + 31) // 32 * tile * 128)
-        if sum(need) + 1280 + 3 * 16384 <= 227 * 1024:
+            need[l & 1] = max(need[l & 1], (cin + 63) // 64 * 2 * tile * 128)
+        if sum(need) + 1024 + 4096 + 3 * 16384 <= 227 * 1024:
             return tile
     raise RuntimeError("cpfn_b200.fused: chain does not fit shared memory: %r" % (dims,))
 

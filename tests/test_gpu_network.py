@@ -4,7 +4,8 @@ tests/golden/ref_network.npz) and against that golden directly.
 
 Indices (FPS, ball query, 3-NN) must be bit-exact.  Features: the per-op path uses torch
 fp32 convolutions (TF32 disabled here) -> 1e-4 relative to the tensor scale; the fused
-tcgen05 path computes the MLPs in TF32 with fp32 accumulation -> 1e-3 (north_star)."""
+tcgen05 path computes the MLPs in split-bf16 (hi+lo, three MMAs) with fp32 accumulation ->
+2e-4 (north_star allows 1e-3)."""
 import os
 
 import numpy as np
@@ -38,7 +39,7 @@ def test_forward_matches_oracle_and_golden(engine, cuda_dev):
     eng, sd = engine
     P = cases.network_input()
     g = np.load(GOLDEN)
-    tol = 1e-3 if fused.available() else 1e-4
+    tol = 2e-4 if fused.available() else 1e-4
     out = eng.forward(torch.from_numpy(P).to(cuda_dev), dropout=False, fit=False)
     ref = onet.pointnet2_forward(sd, P, 3)
     assert _rel(out["l3_feats"].cpu().numpy(), ref["l3_feats"]) < tol
