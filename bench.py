@@ -266,7 +266,8 @@ def run_ours(args):
                 "algorithmic_bytes": fps_bytes, "kernel_us": round(fps_t * 1e6, 2),
                 "note": "effective bytes B*(m-1)*N*16 (SURVEY 8d); data is register/SMEM resident, compulsory HBM is 1.6 MB"}
 
-    cb = cpu_baseline(steps=2, warmup=1, batch=2)
+    cb = (cpu_baseline(steps=2, warmup=1, batch=2) if not os.environ.get('CPFN_BENCH_NO_CPU')
+          else {'value': None, 'unit': UNIT, 'cores': 0, 'kind': 'port', 'sample': 'skipped'})
     total_points = world * B_PER_GPU * N_POINTS
     ms_per_step = dev_ms / args.steps
     line = {

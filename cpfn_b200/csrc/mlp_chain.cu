@@ -341,7 +341,7 @@ mlp_chain_kernel(const __grid_constant__ ChainP p) {
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         for (int l = 0; l < p.n_layers; ++l) {
           const LayerP &L = p.L[l];
-          const uint32_t in_buf = smem_u32((l & 1) ? act1 : act0);
+          const uint32_t in_buf = smem_u32(act0);   // in-place: a layer's output overwrites its (fully consumed) input
           for (int m0 = 0; m0 < L.cout_chunks; m0 += wave_max) {
             const int mc = min(wave_max, L.cout_chunks - m0);
             mbar_wait(act_ready, act_phase);
@@ -399,7 +399,7 @@ mlp_chain_kernel(const __grid_constant__ ChainP p) {
       for (int l = 0; l < p.n_layers; ++l) {
         const LayerP &L = p.L[l];
         const bool last = (l == p.n_layers - 1);
-        const uint32_t out_buf = smem_u32((l & 1) ? act0 : act1);
+        const uint32_t out_buf = smem_u32(act0);
         const int cout_pad = L.cout_chunks * 128;
         const bool slow = (L.mask != nullptr) || (L.out_cm != nullptr);
         for (int m0 = 0; m0 < L.cout_chunks; m0 += wave_max) {
@@ -490,6 +490,222 @@ mlp_chain_kernel(const __grid_constant__ ChainP p) {
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
+// =================================================================================================
+// Points-as-M variant (tiles of 128 columns): D[point, channel] = A[point, k] * W[channel, k]^T.
+// The activation tile is the A operand (M = 128 rows = TMEM lanes), a weight block is the B operand
+// (N = up to 128 output channels = TMEM columns).  An epilogue thread owns one POINT and reads 16
+// consecutive channels per tcgen05.ld, so the (hi, lo) split packs 8 channels into one 16-byte
+// shared-memory store with no cross-lane traffic (about half the instructions per element of the
+// channels-as-M kernel above, no padding of 64-wide layers to 128), the channel-major copy and the
+// dropout mask are coalesced across the warp, and the max-pool is one REDUX per channel.
+// =================================================================================================
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(kChainThreads, 2)
+mlp_chain_pm_kernel(const __grid_constant__ ChainP p) {
+  constexpr int NT = 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t *ring = smem;
+  uint8_t *act0 = ring + p.nstage * kStageBytes;
+  uint8_t *act1 = act0 + p.act_bytes0;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(act1 + p.act_bytes1);
+  uint64_t *full = bars, *empty = bars + kMaxStages, *act_ready = bars + 2 * kMaxStages,
+           *acc_full = bars + 2 * kMaxStages + 1;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kMaxStages + 2);
+  int *s_arow = reinterpret_cast<int *>(bars + 32);
+  int *s_brow = s_arow + 128;
+  float *s_w = reinterpret_cast<float *>(s_brow + 384);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.nstage; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    mbar_init(act_ready, kWorkers);
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int wave_max = p.tmem_cols / 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int blk = 0; blk < p.total_blocks; ++blk) {
+          mbar_wait(empty + stage, phase ^ 1);
+          mbar_arrive_expect_tx(full + stage, kStageBytes);
+          bulk_g2s(ring + stage * kStageBytes, p.weights + static_cast<size_t>(blk) * kStageBytes, kStageBytes,
+                   full + stage);
+          if (++stage == p.nstage) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(128 >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0, act_phase = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int l = 0; l < p.n_layers; ++l) {
+          const LayerP &L = p.L[l];
+          const uint32_t in_buf = smem_u32(act0);   // in-place: a layer's output overwrites its (fully consumed) input
+          const int cout16 = (L.cout + 15) & ~15;
+          for (int m0 = 0; m0 < L.cout_chunks; m0 += wave_max) {
+            const int mc = min(wave_max, L.cout_chunks - m0);
+            mbar_wait(act_ready, act_phase);
+            act_phase ^= 1;
+            tc_fence_after();
+            for (int m = 0; m < mc; ++m) {
+              const uint32_t d_tmem = tmem_base + m * 128;
+              const int nch = min(128, cout16 - (m0 + m) * 128);
+              const uint32_t idesc = idesc0 | (static_cast<uint32_t>(nch >> 3) << 17);
+              for (int j = 0; j < L.cin_atoms; ++j) {
+                const int ks = min(4, L.ksteps - 4 * j);
+                const uint32_t a_hi = in_buf + part_base<NT>(j, 0), a_lo = a_hi + NT * 128;
+                mbar_wait(full + stage, phase);            // W_hi block
+                tc_fence_after();
+                uint32_t w_base = smem_u32(ring + stage * kStageBytes);
+                for (int kk = 0; kk < ks; ++kk) {
+                  umma_bf16(d_tmem, make_desc(a_hi + kk * 32), make_desc(w_base + kk * 32), idesc, (j | kk) != 0 ? 1u : 0u);
+                  umma_bf16(d_tmem, make_desc(a_lo + kk * 32), make_desc(w_base + kk * 32), idesc, 1u);
+                }
+                umma_commit(empty + stage);
+                if (++stage == p.nstage) { stage = 0; phase ^= 1; }
+                mbar_wait(full + stage, phase);            // W_lo block
+                tc_fence_after();
+                w_base = smem_u32(ring + stage * kStageBytes);
+                for (int kk = 0; kk < ks; ++kk)
+                  umma_bf16(d_tmem, make_desc(a_hi + kk * 32), make_desc(w_base + kk * 32), idesc, 1u);
+                umma_commit(empty + stage);
+                if (++stage == p.nstage) { stage = 0; phase ^= 1; }
+              }
+            }
+            umma_commit(acc_full);
+          }
+        }
+      }
+    }
+  } else {
+    const int w8 = warp - 2;
+    const int wq = warp & 3;                          // TMEM lane quarter = rows wq*32 .. wq*32+31 of the tile
+    const int half = (w8 >> 2);                       // which 64-channel half of every 128-channel chunk
+    const int row = wq * 32 + lane;
+    const uint32_t row_base = static_cast<uint32_t>((row >> 3) * 1024 + (row & 7) * 128);
+    const int r7 = row & 7;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      const long long col0 = static_cast<long long>(tile) * NT;
+      const long long col = col0 + row;
+      const bool row_ok = col < p.cols;
+      const long long cloud = col0 / p.cols_per_cloud;
+      const long long n_in_cloud = col0 - cloud * p.cols_per_cloud;
+      load_tile<NT>(p, smem_u32(act0), col0, w8, lane, s_arow, s_brow, s_w);
+      fence_proxy_async();
+      mbar_arrive(act_ready);
+      for (int l = 0; l < p.n_layers; ++l) {
+        const LayerP &L = p.L[l];
+        const bool last = (l == p.n_layers - 1);
+        const uint32_t out_buf = smem_u32(act0);
+        const int cout_pad = L.cout_chunks * 128, cout16 = (L.cout + 15) & ~15;
+        const bool slow = (L.mask != nullptr) || (L.out_cm != nullptr);
+        const float *bias_base = L.bias + (L.bias_per_cloud ? cloud * cout_pad : 0);
+        for (int m0 = 0; m0 < L.cout_chunks; m0 += wave_max) {
+          const int mc = min(wave_max, L.cout_chunks - m0);
+          mbar_wait(acc_full, acc_phase);
+          acc_phase ^= 1;
+          tc_fence_after();
+          for (int m = 0; m < mc; ++m) {
+            const int chunk0 = (m0 + m) * 128;
+            const int nch = min(128, cout16 - chunk0);
+#pragma unroll 1
+            for (int cb = half * 64; cb < min(nch, half * 64 + 64); cb += 16) {
+              const int ch0 = chunk0 + cb;
+              uint32_t r[16];
+              tmem_ld16(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + m * 128 + cb, r);
+              float v[16];
+#pragma unroll
+              for (int i4 = 0; i4 < 4; ++i4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bias_base + ch0) + i4);
+                v[i4 * 4] = __uint_as_float(r[i4 * 4]) + b4.x;
+                v[i4 * 4 + 1] = __uint_as_float(r[i4 * 4 + 1]) + b4.y;
+                v[i4 * 4 + 2] = __uint_as_float(r[i4 * 4 + 2]) + b4.z;
+                v[i4 * 4 + 3] = __uint_as_float(r[i4 * 4 + 3]) + b4.w;
+              }
+              if (L.relu) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+              }
+              if (slow && row_ok) {                    // dropout mask / channel-major copy: coalesced over the warp
+                const size_t o0 = (static_cast<size_t>(cloud) * L.cout + ch0) * p.cols_per_cloud + n_in_cloud + row;
+                const size_t cs = static_cast<size_t>(p.cols_per_cloud);
+                if (L.mask != nullptr) {
+                  float mk[16];
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) mk[i] = (ch0 + i < L.cout) ? __ldg(L.mask + o0 + i * cs) : 1.f;
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) v[i] *= mk[i];
+                }
+                if (L.out_cm != nullptr) {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i)
+                    if (ch0 + i < L.cout) L.out_cm[o0 + i * cs] = v[i];
+                }
+              }
+              if (!last) {
+                if (ch0 < L.next_k16) {
+                  uint32_t H[8], Lo[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) split2(v[2 * i], v[2 * i + 1], H[i], Lo[i]);
+                  const uint32_t base = out_buf + part_base<NT>(ch0 >> 6, 0) + row_base;
+                  const int c8 = (ch0 & 63) >> 3;
+                  const uint32_t a0 = base + (((c8) ^ r7) << 4), a1 = base + (((c8 + 1) ^ r7) << 4);
+                  st_shared_v4(a0, H[0], H[1], H[2], H[3]);
+                  st_shared_v4(a1, H[4], H[5], H[6], H[7]);
+                  st_shared_v4(a0 + NT * 128, Lo[0], Lo[1], Lo[2], Lo[3]);
+                  st_shared_v4(a1 + NT * 128, Lo[4], Lo[5], Lo[6], Lo[7]);
+                }
+              } else if (p.out_mode == CPFN_MLP_OUT_ROWS) {
+                if (row_ok) {
+                  float *o = p.out + col * p.ldo + ch0;
+#pragma unroll
+                  for (int i = 0; i < 16; ++i)
+                    if (ch0 + i < L.cout) o[i] = v[i];
+                }
+              } else {
+                // max over the warp's 32 rows: one REDUX per channel (post-ReLU floats order like uint32)
+                uint32_t mine = 0u;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const uint32_t u = __reduce_max_sync(0xffffffffu, row_ok ? __float_as_uint(v[i]) : 0u);
+                  if (lane == i) mine = u;
+                }
+                if (lane < 16 && ch0 + lane < L.cout && col0 + wq * 32 < p.cols)
+                  atomicMax(reinterpret_cast<unsigned int *>(p.out) + ((col0 + wq * 32) / p.pool_g) * p.ldo + ch0 + lane, mine);
+              }
+            }
+          }
+          tc_fence_before();
+          const bool final_wave = last && (m0 + wave_max >= L.cout_chunks);
+          if (!final_wave) {
+            fence_proxy_async();
+            mbar_arrive(act_ready);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
 int pow2_at_least(int x) {
   int p = 32;
   while (p < x) p <<= 1;
@@ -521,7 +737,7 @@ int launch_chain(const cpfn_mlp_chain_t *c, cudaStream_t st) {
     total_blocks += L.cout_chunks * L.cin_atoms * 2;
     if (L.cout_chunks > max_chunks) max_chunks = L.cout_chunks;
     const size_t in_bytes = static_cast<size_t>(L.cin_atoms) * 2 * NT * 128;
-    if (in_bytes > act_need[l & 1]) act_need[l & 1] = in_bytes;
+    if (in_bytes > act_need[0]) act_need[0] = in_bytes;
     if ((s.bias_per_cloud || s.mask || s.out_cm) && (c->cols_per_cloud % NT) != 0) return CPFN_EINVAL;
   }
   if (static_cast<size_t>(total_blocks) * kStageBytes != c->weight_bytes) return CPFN_EINVAL;
@@ -545,7 +761,12 @@ int launch_chain(const cpfn_mlp_chain_t *c, cudaStream_t st) {
   if (p.cols >= 2147483647LL || static_cast<long long>(c->B) * c->a_rows >= 2147483647LL ||
       static_cast<long long>(c->B) * c->b_rows >= 2147483647LL) return CPFN_EINVAL;
   bool atomic_pool = false;
-  if (c->out_mode == CPFN_MLP_OUT_POOL) {
+  if (c->out_mode == CPFN_MLP_OUT_POOL && NT == 128) {
+    // points-as-M kernel: every warp (32 rows) max-reduces and merges with atomicMax
+    if (c->pool_g <= 0 || (c->pool_g % 32) != 0 || !c->layers[c->n_layers - 1].relu ||
+        (c->cols_per_cloud % c->pool_g) != 0) return CPFN_EINVAL;
+    atomic_pool = true;
+  } else if (c->out_mode == CPFN_MLP_OUT_POOL) {
     if (c->pool_g <= 0 || (c->pool_g % 16) != 0 || !c->layers[c->n_layers - 1].relu) return CPFN_EINVAL;
     if (c->pool_g <= NT / 2) {
       if ((NT / 2) % c->pool_g != 0) return CPFN_EINVAL;
@@ -554,9 +775,13 @@ int launch_chain(const cpfn_mlp_chain_t *c, cudaStream_t st) {
       atomic_pool = true;
     }
   }
-  p.tmem_cols = pow2_at_least(NT * (max_chunks < 512 / NT ? max_chunks : 512 / NT));
+  p.tmem_cols = NT == 128 ? pow2_at_least(128 * (max_chunks < 4 ? max_chunks : 4))
+                          : pow2_at_least(NT * (max_chunks < 512 / NT ? max_chunks : 512 / NT));
   p.act_bytes0 = static_cast<int>(act_need[0]);
-  p.act_bytes1 = static_cast<int>(act_need[1]);
+  p.act_bytes1 = 0;
+  // the epilogue writes a layer's output over its input, so every non-final layer must fit one TMEM wave
+  for (int l = 0; l + 1 < c->n_layers; ++l)
+    if (p.L[l].cout_chunks * (NT == 128 ? 128 : NT) > p.tmem_cols) return CPFN_EINVAL;
   const size_t fixed = act_need[0] + act_need[1] + 1024 /*align*/ + kMiscBytes;
   const size_t max_smem = 227 * 1024;
   if (fixed + 2 * kStageBytes > max_smem) return CPFN_EINVAL;
@@ -571,7 +796,8 @@ int launch_chain(const cpfn_mlp_chain_t *c, cudaStream_t st) {
   if (nstage > total_blocks) nstage = total_blocks < 2 ? 2 : total_blocks;
   p.nstage = nstage;
   const size_t smem = fixed + static_cast<size_t>(nstage) * kStageBytes;
-  auto kern = mlp_chain_kernel<NT>;
+  void (*kern)(ChainP) = mlp_chain_kernel<NT>;
+  if (NT == 128) kern = mlp_chain_pm_kernel;
   CPFN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const int sms = sm_count() > 0 ? sm_count() : 148;
   const int grid = p.n_tiles < per_sm * sms ? p.n_tiles : per_sm * sms;

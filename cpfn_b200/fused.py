@@ -118,7 +118,15 @@ def run_chain(pc, B, cols_per_cloud, out, ldo, tile_cols=128, in_mode=IN_DENSE, 
     return out
 
 
-def pick_tile(dims, cols_per_cloud, need_cloud_aligned=False, prefer=128):
+def pick_tile(dims, cols_per_cloud, need_cloud_aligned=False, prefer=128, name=None):
+    """Tile choice; CPFN_TILE_<SA1|SA2|HEAD>=128|64|32 overrides it (tuning experiments)."""
+    import os
+    if name and os.environ.get("CPFN_TILE_" + name):
+        return int(os.environ["CPFN_TILE_" + name])
+    return _pick_tile(dims, cols_per_cloud, need_cloud_aligned, prefer)
+
+
+def _pick_tile(dims, cols_per_cloud, need_cloud_aligned=False, prefer=128):
     """Largest tile (128 / 64 / 32 columns) whose two activation buffers plus a 3-stage weight
     ring fit the 227 KB of shared memory (mirrors launch_chain in csrc/mlp_chain.cu)."""
     for tile in (128, 64, 32):
@@ -126,10 +134,11 @@ def pick_tile(dims, cols_per_cloud, need_cloud_aligned=False, prefer=128):
             continue
         if need_cloud_aligned and cols_per_cloud % tile:
             continue
-        need = [0, 0]
-        for l, (cin, _, _) in enumerate(dims):
-            need[l & 1] = max(need[l & 1], (cin + 63) // 64 * 2 * tile * 128)
-        if sum(need) + 1024 + 4096 + 3 * 16384 <= 227 * 1024:
+        need = max((cin + 63) // 64 * 2 * tile * 128 for cin, _, _ in dims)   # one in-place activation buffer
+        wave = 4 if tile == 128 else 512 // tile
+        if any((cout + 127) // 128 > wave for _, cout, _ in dims[:-1]):
+            continue
+        if need + 1024 + 4096 + 3 * 16384 <= 227 * 1024:
             return tile
     raise RuntimeError("cpfn_b200.fused: chain does not fit shared memory: %r" % (dims,))
 
@@ -189,7 +198,7 @@ def sa_forward_pm(module, xyz, feats_pm):
     new_xyz = torch.gather(xyz, 1, fps_idx.long().unsqueeze(-1).expand(-1, -1, 3))
     group_idx = cuda_ops.ball_query(new_xyz, xyz, module.radius_list[0], K)
     out = torch.empty(B, S, cout, dtype=torch.float32, device=dev)
-    run_chain(pc, B, S * K, out, cout, tile_cols=pick_tile(pc.dims, S * K), in_mode=IN_GROUP, a_src=feats_pm, a_ch=D, a_rows=N,
+    run_chain(pc, B, S * K, out, cout, tile_cols=pick_tile(pc.dims, S * K, name=('SA1' if D == 0 else 'SA2'), prefer=(128 if D == 0 else 64)), in_mode=IN_GROUP, a_src=feats_pm, a_ch=D, a_rows=N,
               idx=group_idx, xyz=xyz, centers=new_xyz, group_k=K, out_mode=OUT_POOL, pool_g=K)
     return new_xyz, out
 
@@ -300,7 +309,7 @@ def pointnet2_forward(model, P, dropout=True):
     if dropout:
         # the reference's always-on dropout (pn2_network.py:63): same generator, same shape, same mask
         masks = {fc1_layer: torch.nn.functional.dropout(torch.ones(B, 128, N, device=dev), p=0.5)}
-    run_chain(pc, B, N, heads, n_out, tile_cols=pick_tile(pc.dims, N, need_cloud_aligned=True), in_mode=IN_INTERP, a_src=None, a_ch=0, a_rows=N, idx=idx,
+    run_chain(pc, B, N, heads, n_out, tile_cols=pick_tile(pc.dims, N, need_cloud_aligned=True, name='HEAD'), in_mode=IN_INTERP, a_src=None, a_ch=0, a_rows=N, idx=idx,
               b_src=l5, b_ch=l5.shape[2], b_rows=l5.shape[1], nn_w=w, masks=masks, out_cm={fc1_layer: output_feat})
     outs, o = [], 0
     for n in head_sizes:
