@@ -21,6 +21,7 @@
 // The argmax key is 64 bits: hi = bits(d2) (non-negative floats order like
 // uint32), lo = ~rank where rank encodes the reference tie-break order.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -132,6 +133,183 @@ fps_cta_kernel(const float *__restrict__ xyz, int N, int m, int log2T,
   }
 }
 
+// ---- thread-block-cluster variant ---------------------------------------------------------------
+// At GlobalSPFN's B = 16 clouds the one-CTA kernel above uses 16 of 148 SMs and every round costs
+// the whole cloud's 8192 distance updates on ONE SM.  Here a cluster of C CTAs (C = 8, 4 or 2,
+// chosen so that B*C <= #SMs) owns a cloud: CTA r keeps points [r*Nc, (r+1)*Nc) and their running
+// minima in registers, reduces them to one 64-bit (distance, ~rank) key, and pushes that key into the
+// shared memory of all C CTAs with st.async (DSMEM), whose completion is counted by an mbarrier in
+// the RECEIVING CTA -- no cluster-wide barrier (~380 cycles) in the round loop.  Every CTA then
+// takes the maximum of the C keys, which is the same winner (and the same tie-break) as the
+// reference's single block.  Keys and barriers are double-buffered by round parity: a CTA can only
+// be one round ahead of its slowest peer, because round j+1 needs every peer's round-j key.
+__device__ __forceinline__ uint32_t fps_smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_u64(uint32_t remote_addr, unsigned long long v, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+               ::"r"(remote_addr), "l"(v), "r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void fps_mbar_init(unsigned long long *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fps_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fps_mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fps_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fps_mbar_wait_cluster(unsigned long long *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "FPS_WAIT:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra FPS_DONE;\n\t"
+      "bra FPS_WAIT;\n\t"
+      "FPS_DONE:\n\t"
+      "}\n" ::"r"(fps_smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// Block-wide argmax returning the whole 64-bit key (hi = distance bits, lo = ~rank; 0 = no candidate).
+__device__ __forceinline__ unsigned long long block_argmax_key(uint32_t hi, uint32_t lo,
+                                                               unsigned long long (*slot)[32], int buf,
+                                                               int nwarps) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t M = __reduce_max_sync(0xffffffffu, hi);
+  uint32_t L = __reduce_max_sync(0xffffffffu, hi == M ? lo : 0u);
+  if (lane == 0) slot[buf][warp] = (static_cast<unsigned long long>(M) << 32) | L;
+  __syncthreads();
+  const unsigned long long v = lane < nwarps ? slot[buf][lane] : 0ull;
+  const uint32_t h2 = static_cast<uint32_t>(v >> 32), l2 = static_cast<uint32_t>(v);
+  M = __reduce_max_sync(0xffffffffu, h2);
+  L = __reduce_max_sync(0xffffffffu, h2 == M ? l2 : 0u);
+  return (static_cast<unsigned long long>(M) << 32) | L;
+}
+
+constexpr int kFpsClusterThreads = 512;   // == the reference's block size T for N >= 512, see fps_rank
+
+template <int PPT>
+__global__ void __launch_bounds__(kFpsClusterThreads, 1)
+fps_cluster_kernel(const float *__restrict__ xyz, int N, int m, int log2T, int Nc,
+                   int32_t *__restrict__ idx) {
+  extern __shared__ float s_xyz[];
+  __shared__ unsigned long long slot[2][32];
+  __shared__ __align__(8) unsigned long long xslot[2][8];
+  __shared__ __align__(8) unsigned long long xbar[2];
+  const uint32_t C = cluster_nctarank(), r = cluster_ctarank();
+  const int cloud = blockIdx.x / C;
+  const int t = threadIdx.x;
+  constexpr int NT = kFpsClusterThreads, nwarps = NT / 32;
+  const int Np = (N + 31) & ~31;
+  const float *p = xyz + static_cast<size_t>(cloud) * N * 3;
+  int32_t *out = idx + static_cast<size_t>(cloud) * m;
+  float *sx = s_xyz, *sy = s_xyz + Np, *sz = s_xyz + 2 * Np;
+
+  stage_soa(p, N, Np, s_xyz);            // every CTA keeps the whole cloud for the centroid look-up
+  if (t == 0) {
+    fps_mbar_init(&xbar[0], 1);
+    fps_mbar_init(&xbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  cluster_sync_all();                    // all barriers exist before any peer can complete_tx on them
+
+  // thread t owns k = r*Nc + t + i*512: k mod 512 is the same for all i, so scanning i upward visits
+  // the thread's points in increasing reference rank and strict '>' keeps the right one on ties
+  float px[PPT], py[PPT], pz[PPT], tmp[PPT];
+  const int k0 = static_cast<int>(r) * Nc + t;
+#pragma unroll
+  for (int i = 0; i < PPT; ++i) {
+    const int k = k0 + i * NT;
+    float x = 0.f, y = 0.f, z = 0.f;
+    bool live = false;
+    if (k < N && i * NT + t < Nc) {
+      x = sx[k]; y = sy[k]; z = sz[k];
+      live = !(static_cast<double>(sqnorm3(x, y, z)) <= 1e-3);
+    }
+    px[i] = x; py[i] = y; pz[i] = z;
+    tmp[i] = live ? 1e10f : -1.0f;
+  }
+  // where this thread (t < C) delivers: CTA t's xslot[parity][r] and xbar[parity]
+  uint32_t my_slot0 = 0, my_slot1 = 0, my_bar0 = 0, my_bar1 = 0;
+  if (t < static_cast<int>(C)) {
+    my_slot0 = mapa_u32(fps_smem_u32(&xslot[0][r]), t);
+    my_slot1 = mapa_u32(fps_smem_u32(&xslot[1][r]), t);
+    my_bar0 = mapa_u32(fps_smem_u32(&xbar[0]), t);
+    my_bar1 = mapa_u32(fps_smem_u32(&xbar[1]), t);
+  }
+
+  if (r == 0 && t == 0) out[0] = 0;
+  float cx = sx[0], cy = sy[0], cz = sz[0];
+  for (int j = 1; j < m; ++j) {
+    float best = -1.0f;
+    int bi = 0;
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+      const float d2 = fminf(sqdist3(px[i], py[i], pz[i], cx, cy, cz), tmp[i]);
+      tmp[i] = d2;
+      if (d2 > best) { best = d2; bi = i; }
+    }
+    uint32_t hi = 0u, lo = 0u;
+    if (best >= 0.0f) {
+      hi = __float_as_uint(best);
+      lo = ~fps_rank(static_cast<uint32_t>(k0 + bi * NT), log2T);
+    }
+    const unsigned long long key = block_argmax_key(hi, lo, slot, j & 1, nwarps);
+    const int par = j & 1;
+    if (t == 0) fps_mbar_expect_tx(&xbar[par], 8u * C);
+    if (t < static_cast<int>(C)) st_async_u64(par ? my_slot1 : my_slot0, key, par ? my_bar1 : my_bar0);
+    fps_mbar_wait_cluster(&xbar[par], ((j - 1) >> 1) & 1);   // (j-1)/2-th use of this barrier
+    const int lane = t & 31;
+    const unsigned long long v = lane < static_cast<int>(C) ? xslot[par][lane] : 0ull;
+    const uint32_t h2 = static_cast<uint32_t>(v >> 32), l2 = static_cast<uint32_t>(v);
+    const uint32_t M = __reduce_max_sync(0xffffffffu, h2);
+    const uint32_t L = __reduce_max_sync(0xffffffffu, h2 == M ? l2 : 0u);
+    const int old = L ? static_cast<int>(fps_unrank(~L, log2T)) : 0;
+    if (r == 0 && t == 0) out[j] = old;
+    cx = sx[old]; cy = sy[old]; cz = sz[old];
+  }
+  cluster_sync_all();                    // nobody leaves while a peer may still write into its shared memory
+}
+
+template <int PPT>
+int launch_cluster(const float *xyz, int B, int N, int m, int log2T, int C, int Nc, int32_t *idx,
+                   cudaStream_t st) {
+  const size_t smem = 3u * static_cast<size_t>((N + 31) & ~31) * sizeof(float);
+  auto kern = fps_cluster_kernel<PPT>;
+  CPFN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(B) * C);
+  cfg.blockDim = dim3(kFpsClusterThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CPFN_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, xyz, N, m, log2T, Nc, idx));
+  return check_launch();
+}
+
 // Any N: running minimum in a global workspace [B,N], coordinates re-read
 // through L1/L2 every round.  Only used beyond kMaxSmemN points per cloud.
 __global__ void __launch_bounds__(1024, 1)
@@ -214,6 +392,20 @@ extern "C" int cpfn_furthest_point_sampling(const float *xyz, int B, int N, int 
     fps_stream_kernel<<<B, 1024, 0, st>>>(xyz, N, nsamples, log2T,
                                           static_cast<float *>(workspace), idx);
     return check_launch();
+  }
+  // Few clouds, many points: a cluster of C CTAs per cloud (B*C <= #SMs), 512 threads each.
+  if (N >= 2048 && T == 512 && getenv("CPFN_FPS_NO_CLUSTER") == nullptr) {
+    const int sms = sm_count() > 0 ? sm_count() : 148;
+    int C = 8;
+    while (C > 1 && static_cast<long long>(B) * C > sms) C >>= 1;
+    if (C > 1) {
+      const int Nc = ((N + C - 1) / C + 511) / 512 * 512;
+      const int ppt = Nc / 512;
+      if (ppt <= 1) return launch_cluster<1>(xyz, B, N, nsamples, log2T, C, Nc, idx, st);
+      if (ppt <= 2) return launch_cluster<2>(xyz, B, N, nsamples, log2T, C, Nc, idx, st);
+      if (ppt <= 4) return launch_cluster<4>(xyz, B, N, nsamples, log2T, C, Nc, idx, st);
+      if (ppt <= 8) return launch_cluster<8>(xyz, B, N, nsamples, log2T, C, Nc, idx, st);
+    }
   }
   // Block size: a multiple of T (>= one warp); N >= 1024 always uses 1024.
   const int NT = N >= 1024 ? 1024 : (T < 32 ? 32 : T);
