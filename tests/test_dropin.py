@@ -1,0 +1,40 @@
+"""The drop-in registration maps the reference's module names onto this package (CPU, no compute)."""
+import sys
+
+import pytest
+
+
+def test_full_install_maps_reference_names(built_lib):
+    from cpfn_b200 import dropin
+    saved = {k: v for k, v in sys.modules.items() if k == "PointNet2" or k.startswith("PointNet2.") or k == "SPFN" or k.startswith("SPFN.")}
+    try:
+        dropin.install("full")
+        from PointNet2.pn2_network import PointNet2
+        from PointNet2.pointnet2_ops import cuda_ops
+        from PointNet2.pointnet2_ops.modules.pointset_abstraction import PointsetAbstraction
+        from PointNet2.pointnet2_ops.modules.geometry_utils import farthest_point_sample, ball_query, three_nn  # noqa: F401
+        from SPFN import cone_fitter, fitter_factory, losses_implementation
+        import cpfn_b200
+        assert PointNet2.__module__.startswith("cpfn_b200")
+        assert PointsetAbstraction.__module__.startswith("cpfn_b200")
+        assert cuda_ops is cpfn_b200.cuda_ops
+        for name in ("farthest_point_sampling", "ball_query", "gather_points", "gather_points_grad", "group_points",
+                     "group_points_grad", "three_nn", "three_weighted_sum", "three_weighted_sum_grad"):
+            assert callable(getattr(cuda_ops, name))          # bindings.cpp:7-18 of the reference
+        fitter_factory.register_primitives(["sphere", "plane", "cylinder", "cone"])
+        assert fitter_factory.primitive_name_to_id("plane") == 1 and fitter_factory.get_n_registered_primitives() == 4
+        assert callable(cone_fitter.compute_parameters) and callable(losses_implementation.compute_parameters)
+    finally:
+        dropin.uninstall()
+        sys.modules.update(saved)
+
+
+def test_cpu_tensors_are_rejected_like_the_reference(built_lib):
+    import torch
+    from cpfn_b200 import cuda_ops
+    with pytest.raises(RuntimeError, match="CPU not supported"):
+        cuda_ops.farthest_point_sampling(torch.zeros(1, 8, 3), 2)
+    with pytest.raises(RuntimeError, match="float"):
+        cuda_ops.farthest_point_sampling(torch.zeros(1, 8, 3, dtype=torch.float64), 2)
+    with pytest.raises(RuntimeError, match="contiguous"):
+        cuda_ops.ball_query(torch.zeros(1, 3, 4).transpose(1, 2), torch.zeros(1, 8, 3), 0.1, 4)
