@@ -45,6 +45,9 @@ SIGNATURES = {
                                         c_void_p, c_void_p]),
     "cpfn_three_weighted_sum_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                              c_int, c_void_p, c_void_p]),
+    "cpfn_three_nn_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "cpfn_gather_xyz": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "cpfn_spfn_post": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "cpfn_mlp_packed_bytes": (c_size_t, [c_int, c_int]),
     "cpfn_mlp_pack_weights_host": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "cpfn_mlp_chain": (c_int, [c_void_p, c_void_p]),

@@ -37,12 +37,16 @@ class GlobalSPFN:
         ``dropout=False`` replaces the reference's always-on dropout by the identity (parity runs)."""
         from . import fused
         if fused.available():
-            heads, l3_feats, feat, l1_xyz, l2_xyz = fused.pointnet2_forward(self.model, P, dropout=dropout)
+            heads, l3_feats, feat, l1_xyz, l2_xyz, packed = fused.pointnet2_forward(self.model, P, dropout=dropout)
             out = {"X_raw": heads[0], "T_raw": heads[1], "W_raw": heads[2], "l3_feats": l3_feats,
                    "output_feat": feat, "l1_pos": l1_xyz.permute(0, 2, 1), "l2_pos": l2_xyz.permute(0, 2, 1)}
-            out["X"] = torch.nn.functional.normalize(heads[0], p=2, dim=2, eps=1e-12)
+            if len(heads) == 3 and heads[0].shape[2] == 3 and heads[2].shape[2] <= 64:
+                # SPFN post-processing (Utils/training_utils.py:141-142) in one kernel
+                out["X"], out["W"] = fused.spfn_post(packed, 0, 3 + heads[1].shape[2], heads[2].shape[2])
+            else:
+                out["X"] = torch.nn.functional.normalize(heads[0], p=2, dim=2, eps=1e-12)
+                out["W"] = torch.softmax(heads[2], dim=2)
             out["T"] = heads[1]
-            out["W"] = torch.softmax(heads[2], dim=2)
             if fit:
                 out["parameters"] = L.compute_parameters(P, out["W"], out["X"], self.classes)
             return out

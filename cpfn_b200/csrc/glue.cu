@@ -1,0 +1,143 @@
+// Small fused helpers of the inference forward (each replaces a chain of tiny element-wise
+// torch kernels of the reference's Python modules):
+//   cpfn_three_nn_weights  three_nn + sqrt + inverse-distance weights
+//                          (modules/geometry_utils.py:184, pointset_feature_propagation.py:38-42)
+//   cpfn_gather_xyz        centroid gather new_xyz = xyz[fps_idx] (pointset_abstraction.py:50)
+//   cpfn_spfn_post         X = normalize(head0), W = softmax(head2) (Utils/training_utils.py:141-142)
+#include <math.h>
+
+#include "common.cuh"
+
+namespace cpfn {
+namespace {
+
+constexpr int kGlueThreads = 256;
+constexpr int kNnTile = 2048;
+
+// Same scan as three_nn_kernel (interp_group.cu; bit-exact indices and squared distances), then
+// d = sqrt(d2); r = 1 / (d + 1e-8); w = r / ((r0 + r1) + r2)   -- every step correctly rounded fp32,
+// the order torch's element-wise kernels apply them in the reference.
+__global__ void __launch_bounds__(kGlueThreads)
+three_nn_weights_kernel(const float *__restrict__ unknown, const float *__restrict__ known, int n, int m,
+                        float *__restrict__ weight, int32_t *__restrict__ idx) {
+  __shared__ float4 s_known[kNnTile];
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * kGlueThreads + threadIdx.x;
+  const float *kn = known + static_cast<size_t>(b) * m * 3;
+  float ux = 0.f, uy = 0.f, uz = 0.f;
+  if (j < n) {
+    const float *u = unknown + (static_cast<size_t>(b) * n + j) * 3;
+    ux = __ldg(u); uy = __ldg(u + 1); uz = __ldg(u + 2);
+  }
+  float b1 = INFINITY, b2 = INFINITY, b3 = INFINITY;
+  int i1 = 0, i2 = 0, i3 = 0;
+  for (int t0 = 0; t0 < m; t0 += kNnTile) {
+    const int tn = min(kNnTile, m - t0);
+    __syncthreads();
+    for (int k = threadIdx.x; k < tn; k += kGlueThreads) {
+      const float *s = kn + static_cast<size_t>(t0 + k) * 3;
+      s_known[k] = make_float4(__ldg(s), __ldg(s + 1), __ldg(s + 2), 0.f);
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int k = 0; k < tn; ++k) {
+      const float4 c = s_known[k];
+      const float d = sqdist3(ux, uy, uz, c.x, c.y, c.z);
+      if (d < b3) {
+        const int kk = t0 + k;
+        if (d < b1) { b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = kk; }
+        else if (d < b2) { b3 = b2; i3 = i2; b2 = d; i2 = kk; }
+        else { b3 = d; i3 = kk; }
+      }
+    }
+  }
+  if (j < n) {
+    const float r1 = __frcp_rn(__fadd_rn(__fsqrt_rn(b1), 1e-8f));
+    const float r2 = __frcp_rn(__fadd_rn(__fsqrt_rn(b2), 1e-8f));
+    const float r3 = __frcp_rn(__fadd_rn(__fsqrt_rn(b3), 1e-8f));
+    const float s = __fadd_rn(__fadd_rn(r1, r2), r3);
+    const size_t o = (static_cast<size_t>(b) * n + j) * 3;
+    weight[o] = __fdiv_rn(r1, s); weight[o + 1] = __fdiv_rn(r2, s); weight[o + 2] = __fdiv_rn(r3, s);
+    idx[o] = i1; idx[o + 1] = i2; idx[o + 2] = i3;
+  }
+}
+
+__global__ void __launch_bounds__(kGlueThreads)
+gather_xyz_kernel(const float *__restrict__ xyz, const int32_t *__restrict__ idx, int N, int S, long long total,
+                  float *__restrict__ out) {
+  const long long e = static_cast<long long>(blockIdx.x) * kGlueThreads + threadIdx.x;   // over B*S*3
+  if (e >= total) return;
+  const long long row = e / 3;
+  const int c = static_cast<int>(e - row * 3);
+  const long long b = row / S;
+  out[e] = __ldg(xyz + (b * N + __ldg(idx + row)) * 3 + c);
+}
+
+// One thread per point.  heads [rows, ld]: columns [x_off, x_off+3) = normals, [w_off, w_off+K) = logits.
+// X = x / max(||x||, 1e-12) (F.normalize, p=2); W = softmax(logits).
+template <int KMAX>
+__global__ void __launch_bounds__(kGlueThreads)
+spfn_post_kernel(const float *__restrict__ heads, long long rows, int ld, int x_off, int w_off, int K,
+                 float *__restrict__ X, float *__restrict__ W) {
+  const long long r = static_cast<long long>(blockIdx.x) * kGlueThreads + threadIdx.x;
+  if (r >= rows) return;
+  const float *h = heads + r * ld;
+  const float x = __ldg(h + x_off), y = __ldg(h + x_off + 1), z = __ldg(h + x_off + 2);
+  const float nrm = fmaxf(sqrtf(x * x + y * y + z * z), 1e-12f);
+  X[r * 3] = x / nrm; X[r * 3 + 1] = y / nrm; X[r * 3 + 2] = z / nrm;
+  float v[KMAX];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    v[k] = k < K ? __ldg(h + w_off + k) : -INFINITY;
+    mx = fmaxf(mx, v[k]);
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    v[k] = k < K ? expf(v[k] - mx) : 0.f;
+    sum += v[k];
+  }
+  float *w = W + r * K;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k)
+    if (k < K) w[k] = v[k] / sum;
+}
+
+}  // namespace
+}  // namespace cpfn
+
+extern "C" int cpfn_three_nn_weights(const float *unknown, const float *known, int B, int n, int m,
+                                     float *weight, int32_t *idx, cpfn_stream_t stream) {
+  using namespace cpfn;
+  if (B < 0 || n < 0 || m < 0) return CPFN_EINVAL;
+  if (B == 0 || n == 0) return CPFN_OK;
+  if (!unknown || !weight || !idx || (m > 0 && !known) || B > 65535) return CPFN_EINVAL;
+  dim3 grid((n + kGlueThreads - 1) / kGlueThreads, B);
+  three_nn_weights_kernel<<<grid, kGlueThreads, 0, as_stream(stream)>>>(unknown, known, n, m, weight, idx);
+  return check_launch();
+}
+
+extern "C" int cpfn_gather_xyz(const float *xyz, const int32_t *idx, int B, int N, int S, float *out,
+                               cpfn_stream_t stream) {
+  using namespace cpfn;
+  if (B < 0 || N < 0 || S < 0) return CPFN_EINVAL;
+  if (B == 0 || S == 0) return CPFN_OK;
+  if (!xyz || !idx || !out || N == 0) return CPFN_EINVAL;
+  const long long total = static_cast<long long>(B) * S * 3;
+  gather_xyz_kernel<<<static_cast<unsigned>((total + kGlueThreads - 1) / kGlueThreads), kGlueThreads, 0,
+                      as_stream(stream)>>>(xyz, idx, N, S, total, out);
+  return check_launch();
+}
+
+extern "C" int cpfn_spfn_post(const float *heads, long long rows, int ld, int x_off, int w_off, int K, float *X,
+                              float *W, cpfn_stream_t stream) {
+  using namespace cpfn;
+  if (rows < 0 || K <= 0 || K > 64 || ld < 3 || x_off < 0 || w_off < 0 || x_off + 3 > ld || w_off + K > ld) return CPFN_EINVAL;
+  if (rows == 0) return CPFN_OK;
+  if (!heads || !X || !W) return CPFN_EINVAL;
+  const unsigned grid = static_cast<unsigned>((rows + kGlueThreads - 1) / kGlueThreads);
+  if (K <= 32) spfn_post_kernel<32><<<grid, kGlueThreads, 0, as_stream(stream)>>>(heads, rows, ld, x_off, w_off, K, X, W);
+  else spfn_post_kernel<64><<<grid, kGlueThreads, 0, as_stream(stream)>>>(heads, rows, ld, x_off, w_off, K, X, W);
+  return check_launch();
+}

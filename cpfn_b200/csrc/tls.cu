@@ -175,8 +175,8 @@ tls_pass_kernel(const float *__restrict__ P, const float *__restrict__ X,
       } else {
         // cone_fitter.py:25-33: dir = normalize(p - apex, eps 1e-12); dot = axis . dir
         const float vx = p.x - c0, vy = p.y - c1, vz = p.z - c2;
-        const float nrm = fmaxf(sqrtf(vx * vx + vy * vy + vz * vz), 1e-12f);
-        const float dot = (e0 * (vx / nrm) + e1 * (vy / nrm)) + e2 * (vz / nrm);
+        const float inv = 1.0f / fmaxf(sqrtf(vx * vx + vy * vy + vz * vz), 1e-12f);
+        const float dot = (e0 * (vx * inv) + e1 * (vy * inv)) + e2 * (vz * inv);
         acc[0] = fmaf(w, dot, acc[0]);
         const float cl = fminf(fmaxf(fabsf(dot), -1.0f + 1e-6f), 1.0f - 1e-6f);
         acc[1] = fmaf(w, acosf(cl), acc[1]);
@@ -214,26 +214,33 @@ tls_pass_kernel(const float *__restrict__ P, const float *__restrict__ X,
 // Cyclic Jacobi for a symmetric 3x3 (a = xx,xy,xz,yy,yz,zz).  lam[i], V[r][i] = i-th eigenpair.
 __device__ void eig_sym3(const double a[6], double lam[3], double V[3][3]) {
   double A[3][3] = {{a[0], a[1], a[2]}, {a[1], a[3], a[4]}, {a[2], a[4], a[5]}};
+#pragma unroll
   for (int i = 0; i < 3; ++i)
+#pragma unroll
     for (int j = 0; j < 3; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
   for (int sweep = 0; sweep < 12; ++sweep) {
     const double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
     const double diag = fabs(A[0][0]) + fabs(A[1][1]) + fabs(A[2][2]);
     if (off <= 1e-18 * diag || off == 0.0) break;
+#pragma unroll
     for (int p = 0; p < 2; ++p)
+#pragma unroll
       for (int q = p + 1; q < 3; ++q) {
         if (A[p][q] == 0.0) continue;
         const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
         const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
         const double c = 1.0 / sqrt(tt * tt + 1.0), s = tt * c;
+#pragma unroll
         for (int r = 0; r < 3; ++r) {   // A <- A J
           const double arp = A[r][p], arq = A[r][q];
           A[r][p] = c * arp - s * arq; A[r][q] = s * arp + c * arq;
         }
+#pragma unroll
         for (int r = 0; r < 3; ++r) {   // A <- J^T A
           const double apr = A[p][r], aqr = A[q][r];
           A[p][r] = c * apr - s * aqr; A[q][r] = s * apr + c * aqr;
         }
+#pragma unroll
         for (int r = 0; r < 3; ++r) {
           const double vrp = V[r][p], vrq = V[r][q];
           V[r][p] = c * vrp - s * vrq; V[r][q] = s * vrp + c * vrq;
@@ -251,7 +258,9 @@ __device__ void min_eigvec3(const double a[6], double n[3]) {
   int m = 2;
   if (fabs(lam[1]) < fabs(lam[m])) m = 1;
   if (fabs(lam[0]) < fabs(lam[m])) m = 0;
-  double x = V[0][m], y = V[1][m], z = V[2][m];
+  double x = m == 0 ? V[0][0] : (m == 1 ? V[0][1] : V[0][2]);
+  double y = m == 0 ? V[1][0] : (m == 1 ? V[1][1] : V[1][2]);
+  double z = m == 0 ? V[2][0] : (m == 1 ? V[2][1] : V[2][2]);
   const double nn = sqrt(x * x + y * y + z * z);
   if (nn > 0.0) { x /= nn; y /= nn; z /= nn; }
   // deterministic sign: the component of largest magnitude is positive
@@ -269,21 +278,16 @@ __device__ void guarded_solve3(const double a[6], const double rhs[3], double x[
   const double s0 = fabs(lam[0]), s1 = fabs(lam[1]), s2 = fabs(lam[2]);
   const double smax = fmax(s0, fmax(s1, s2)), smin = fmin(s0, fmin(s1, s2));
   const double mask = (smax / smin < 1e5) ? 1.0 : 0.0;   // NaN / inf compare false
-  double M[3][4] = {{a[0] * mask + 1e-8, a[1] * mask, a[2] * mask, rhs[0] * mask},
-                    {a[1] * mask, a[3] * mask + 1e-8, a[4] * mask, rhs[1] * mask},
-                    {a[2] * mask, a[4] * mask, a[5] * mask + 1e-8, rhs[2] * mask}};
-  for (int c = 0; c < 3; ++c) {
-    int piv = c;
-    for (int r = c + 1; r < 3; ++r) if (fabs(M[r][c]) > fabs(M[piv][c])) piv = r;
-    if (piv != c) for (int j = 0; j < 4; ++j) { const double tmp = M[c][j]; M[c][j] = M[piv][j]; M[piv][j] = tmp; }
-    for (int r = c + 1; r < 3; ++r) {
-      const double f = M[r][c] / M[c][c];
-      for (int j = c; j < 4; ++j) M[r][j] -= f * M[c][j];
-    }
-  }
-  x[2] = M[2][3] / M[2][2];
-  x[1] = (M[1][3] - M[1][2] * x[2]) / M[1][1];
-  x[0] = (M[0][3] - M[0][1] * x[1] - M[0][2] * x[2]) / M[0][0];
+  // symmetric 3x3 solve by cofactors in fp64 (cond <= 1e5 by the mask, or the ridge alone)
+  const double m00 = a[0] * mask + 1e-8, m01 = a[1] * mask, m02 = a[2] * mask, m11 = a[3] * mask + 1e-8,
+               m12 = a[4] * mask, m22 = a[5] * mask + 1e-8;
+  const double r0 = rhs[0] * mask, r1 = rhs[1] * mask, r2 = rhs[2] * mask;
+  const double c00 = m11 * m22 - m12 * m12, c01 = m02 * m12 - m01 * m22, c02 = m01 * m12 - m02 * m11;
+  const double c11 = m00 * m22 - m02 * m02, c12 = m01 * m02 - m00 * m12, c22 = m00 * m11 - m01 * m01;
+  const double det = m00 * c00 + m01 * c01 + m02 * c02;
+  x[0] = (c00 * r0 + c01 * r1 + c02 * r2) / det;
+  x[1] = (c01 * r0 + c11 * r1 + c12 * r2) / det;
+  x[2] = (c02 * r0 + c12 * r1 + c22 * r2) / det;
 }
 
 __device__ void guarded_solve2(double axx, double axy, double ayy, const double rhs[2], double x[2]) {
@@ -341,6 +345,7 @@ tls_solve1_kernel(const double *__restrict__ part, double *__restrict__ state, i
     const double sw = m[0];
     const double denom = static_cast<double>(fmaxf(static_cast<float>(sw), 1e-10f));
     st[ST_SW] = sw; st[ST_DENOM] = denom;
+#pragma unroll
     for (int i = 0; i < 3; ++i) {
       const double mu = static_cast<double>(static_cast<float>(m[1 + i] / denom));   // the reference's mean is fp32
       st[ST_MU + i] = mu;
@@ -386,6 +391,7 @@ tls_solve2_kernel(const double *__restrict__ part, double *__restrict__ state,
     // plane: normal = TLS of the centred points, c = n . mean
     double n[3];
     min_eigvec3(S, n);
+#pragma unroll
     for (int i = 0; i < 3; ++i) o_pn[bk * 3 + i] = static_cast<float>(n[i]);
     o_pc[bk] = static_cast<float>(n[0] * mu[0] + n[1] * mu[1] + n[2] * mu[2]);
     return;
@@ -394,6 +400,7 @@ tls_solve2_kernel(const double *__restrict__ part, double *__restrict__ state,
     // cone: apex from solve1; axis = plane-fit normal of the normals (sign fixed in solve3)
     double ax[3];
     min_eigvec3(Cx, ax);
+#pragma unroll
     for (int i = 0; i < 3; ++i) {
       st[ST_CONEAX + i] = static_cast<double>(static_cast<float>(ax[i]));
       o_ap[bk * 3 + i] = static_cast<float>(st[ST_APEX + i]);
@@ -405,7 +412,9 @@ tls_solve2_kernel(const double *__restrict__ part, double *__restrict__ state,
   // sphere: AtA = 4 S', Atb = -2 m2 s1' + 2 (|mu|^2 s1' + 2 S' mu + t'),  t'_i = sum_j T'_ijj
   const double mu2 = mu[0] * mu[0] + mu[1] * mu[1] + mu[2] * mu[2];
   double AtA[6], Atb[3], c[3];
+#pragma unroll
   for (int i = 0; i < 6; ++i) AtA[i] = 4.0 * Sp[i];
+#pragma unroll
   for (int i = 0; i < 3; ++i) {
     const double Smu = sym6(Sp, i, 0) * mu[0] + sym6(Sp, i, 1) * mu[1] + sym6(Sp, i, 2) * mu[2];
     const double t = sym10(T, i, 0, 0) + sym10(T, i, 1, 1) + sym10(T, i, 2, 2);
@@ -416,6 +425,7 @@ tls_solve2_kernel(const double *__restrict__ part, double *__restrict__ state,
     const double e[3] = {mu[0] - c[0], mu[1] - c[1], mu[2] - c[2]};
     const double r2 = (S[0] + S[3] + S[5]) + 2.0 * (e[0] * s1[0] + e[1] * s1[1] + e[2] * s1[2]) +
                       (e[0] * e[0] + e[1] * e[1] + e[2] * e[2]) * sw;
+#pragma unroll
     for (int i = 0; i < 3; ++i) o_sc[bk * 3 + i] = static_cast<float>(c[i]);
     o_sr[bk] = static_cast<float>(r2 / denom);
   }
@@ -428,6 +438,7 @@ tls_solve2_kernel(const double *__restrict__ part, double *__restrict__ state,
     const double cand[3][3] = {{0.0, a[2], -a[1]}, {-a[2], 0.0, a[0]}, {a[1], -a[0], 0.0}};  // a x e_c
     int best = 0;
     double bn = -1.0;
+#pragma unroll
     for (int q = 0; q < 3; ++q) {
       const double nn = cand[q][0] * cand[q][0] + cand[q][1] * cand[q][1] + cand[q][2] * cand[q][2];
       if (nn > bn) { bn = nn; best = q; }
@@ -437,13 +448,17 @@ tls_solve2_kernel(const double *__restrict__ part, double *__restrict__ state,
     const double xa[3] = {ya[1] * a[2] - ya[2] * a[1], ya[2] * a[0] - ya[0] * a[2], ya[0] * a[1] - ya[1] * a[0]};
     const double *Fm[2] = {xa, ya};
     double Sq[2][2], Spq[2][2], muq[2], s1q[2], s1pq[2], tq[2];
+#pragma unroll
     for (int u = 0; u < 2; ++u) {
       muq[u] = Fm[u][0] * mu[0] + Fm[u][1] * mu[1] + Fm[u][2] * mu[2];
       s1q[u] = Fm[u][0] * s1[0] + Fm[u][1] * s1[1] + Fm[u][2] * s1[2];
       s1pq[u] = Fm[u][0] * s1p[0] + Fm[u][1] * s1p[1] + Fm[u][2] * s1p[2];
+#pragma unroll
       for (int v = 0; v < 2; ++v) {
         double acc = 0.0, accp = 0.0;
+#pragma unroll
         for (int i = 0; i < 3; ++i)
+#pragma unroll
           for (int j = 0; j < 3; ++j) {
             acc += Fm[u][i] * sym6(S, i, j) * Fm[v][j];
             accp += Fm[u][i] * sym6(Sp, i, j) * Fm[v][j];
@@ -451,20 +466,26 @@ tls_solve2_kernel(const double *__restrict__ part, double *__restrict__ state,
         Sq[u][v] = acc; Spq[u][v] = accp;
       }
       double t = 0.0;
+#pragma unroll
       for (int v = 0; v < 2; ++v)
+#pragma unroll
         for (int i = 0; i < 3; ++i)
+#pragma unroll
           for (int j = 0; j < 3; ++j)
+#pragma unroll
             for (int l = 0; l < 3; ++l) t += Fm[u][i] * Fm[v][j] * Fm[v][l] * sym10(T, i, j, l);
       tq[u] = t;
     }
     const double muq2 = muq[0] * muq[0] + muq[1] * muq[1];
     const double m2q = ((Sq[0][0] + Sq[1][1]) + 2.0 * (muq[0] * s1q[0] + muq[1] * s1q[1]) + sw * muq2) / denom;
     double rhs[2], cq[2];
+#pragma unroll
     for (int u = 0; u < 2; ++u)
       rhs[u] = -2.0 * m2q * s1pq[u] + 2.0 * (muq2 * s1pq[u] + 2.0 * (Spq[u][0] * muq[0] + Spq[u][1] * muq[1]) + tq[u]);
     guarded_solve2(4.0 * Spq[0][0], 4.0 * Spq[0][1], 4.0 * Spq[1][1], rhs, cq);
     const double e[2] = {muq[0] - cq[0], muq[1] - cq[1]};
     const double r2 = (Sq[0][0] + Sq[1][1]) + 2.0 * (e[0] * s1q[0] + e[1] * s1q[1]) + (e[0] * e[0] + e[1] * e[1]) * sw;
+#pragma unroll
     for (int i = 0; i < 3; ++i) {
       o_ca[bk * 3 + i] = static_cast<float>(a[i]);
       o_cc[bk * 3 + i] = static_cast<float>(cq[0] * xa[i] + cq[1] * ya[i]);
@@ -487,6 +508,7 @@ tls_solve3_kernel(const double *__restrict__ part, const double *__restrict__ st
   float *o_ax = out + 18 * BKs, *o_ha = out + 21 * BKs;
   const float sf = static_cast<float>(s);
   const float sgn = sf > 0.f ? 1.f : (sf < 0.f ? -1.f : 1.f);   // sign(), 0 -> +1 (cone_fitter.py:29-30)
+#pragma unroll
   for (int i = 0; i < 3; ++i) o_ax[bk * 3 + i] *= sgn;
   const float wsum = static_cast<float>(state[static_cast<size_t>(bk) * kState + ST_SW]);
   float half = static_cast<float>(a) / (wsum + 1e-10f);

@@ -148,6 +148,49 @@ def mlp_chain(*args, **kwargs):
     return run_chain(*args, **kwargs)
 
 
+# ---- small fused helpers (csrc/glue.cu) ---------------------------------------------------------
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def three_nn_weights(unknown, known):
+    """unknown [B,n,3], known [B,m,3] -> (weights f32 [B,n,3], idx int32 [B,n,3]): three_nn + sqrt +
+    normalised inverse-distance weights in one kernel."""
+    B, n, _ = unknown.shape
+    w = torch.empty(B, n, 3, dtype=torch.float32, device=unknown.device)
+    idx = torch.empty(B, n, 3, dtype=torch.int32, device=unknown.device)
+    with torch.cuda.device(unknown.device):
+        _lib.check(_lib.lib().cpfn_three_nn_weights(unknown.data_ptr(), known.data_ptr(), B, n, known.shape[1],
+                                                    w.data_ptr(), idx.data_ptr(), _stream(unknown)), "three_nn_weights")
+    cuda_ops.count_launches(1)
+    return w, idx
+
+
+def gather_xyz(xyz, idx):
+    """xyz [B,N,3], idx int32 [B,S] -> [B,S,3]."""
+    B, N, _ = xyz.shape
+    S = idx.shape[1]
+    out = torch.empty(B, S, 3, dtype=torch.float32, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        _lib.check(_lib.lib().cpfn_gather_xyz(xyz.data_ptr(), idx.data_ptr(), B, N, S, out.data_ptr(), _stream(xyz)),
+                   "gather_xyz")
+    cuda_ops.count_launches(1)
+    return out
+
+
+def spfn_post(heads, x_off, w_off, K):
+    """heads [B,N,ld] contiguous -> (X [B,N,3] unit normals, W [B,N,K] softmax memberships)."""
+    B, N, ld = heads.shape
+    X = torch.empty(B, N, 3, dtype=torch.float32, device=heads.device)
+    W = torch.empty(B, N, K, dtype=torch.float32, device=heads.device)
+    with torch.cuda.device(heads.device):
+        _lib.check(_lib.lib().cpfn_spfn_post(heads.data_ptr(), B * N, ld, x_off, w_off, K, X.data_ptr(), W.data_ptr(),
+                                             _stream(heads)), "spfn_post")
+    cuda_ops.count_launches(1)
+    return X, W
+
+
 # ---- PointNet2 on the fused chains --------------------------------------------------------------
 
 _CACHE_ATTR = "_cpfn_fused_cache"
@@ -195,7 +238,7 @@ def sa_forward_pm(module, xyz, feats_pm):
         return None, out
     S, K = module.num_points, module.num_samples_list[0]
     fps_idx = cuda_ops.farthest_point_sampling(xyz, S)
-    new_xyz = torch.gather(xyz, 1, fps_idx.long().unsqueeze(-1).expand(-1, -1, 3))
+    new_xyz = gather_xyz(xyz, fps_idx)
     group_idx = cuda_ops.ball_query(new_xyz, xyz, module.radius_list[0], K)
     out = torch.empty(B, S, cout, dtype=torch.float32, device=dev)
     run_chain(pc, B, S * K, out, cout, tile_cols=pick_tile(pc.dims, S * K, name=('SA1' if D == 0 else 'SA2'), prefer=(128 if D == 0 else 64)), in_mode=IN_GROUP, a_src=feats_pm, a_ch=D, a_rows=N,
@@ -242,9 +285,7 @@ def fp_forward_pm(module, xyz1, xyz2, feats1_pm, feats2_pm):
                   biases=[bias0] + [None] * (len(pc.dims) - 1), bias_per_cloud=(0,))
         return out
     pc, _ = _fp_chain(module, dev)
-    dist2, idx = cuda_ops.three_nn(xyz1, xyz2)
-    recip = 1.0 / (torch.sqrt(dist2) + 1e-8)
-    w = (recip / torch.sum(recip, dim=2, keepdim=True)).contiguous()
+    w, idx = three_nn_weights(xyz1, xyz2)
     out = torch.empty(B, N, pc.dims[-1][1], dtype=torch.float32, device=dev)
     run_chain(pc, B, N, out, out.shape[2], tile_cols=pick_tile(pc.dims, N), in_mode=IN_INTERP, a_src=feats1_pm, a_ch=D1, a_rows=N,
               idx=idx, b_src=feats2_pm, b_ch=feats2_pm.shape[2], b_rows=feats2_pm.shape[1], nn_w=w)
@@ -299,9 +340,7 @@ def pointnet2_forward(model, P, dropout=True):
     l5 = fp_forward_pm(model.sfp2, l1_xyz, l2_xyz, l1, l4)
     pc, head_sizes = _head_chain(model, dev)
     n_out = sum(head_sizes)
-    dist2, idx = cuda_ops.three_nn(P, l1_xyz)
-    recip = 1.0 / (torch.sqrt(dist2) + 1e-8)
-    w = (recip / torch.sum(recip, dim=2, keepdim=True)).contiguous()
+    w, idx = three_nn_weights(P, l1_xyz)
     heads = torch.empty(B, N, n_out, dtype=torch.float32, device=dev)
     output_feat = torch.empty(B, 128, N, dtype=torch.float32, device=dev)
     fc1_layer = len(pc.dims) - 2
@@ -315,4 +354,4 @@ def pointnet2_forward(model, P, dropout=True):
     for n in head_sizes:
         outs.append(heads[:, :, o:o + n])
         o += n
-    return outs, l3.reshape(B, -1, 1), output_feat, l1_xyz, l2_xyz
+    return outs, l3.reshape(B, -1, 1), output_feat, l1_xyz, l2_xyz, heads

@@ -177,6 +177,26 @@ CPFN_API size_t cpfn_mlp_packed_bytes(int cout, int cin);
 CPFN_API int cpfn_mlp_pack_weights_host(const float *W_host, int cout, int cin, void *packed_host);
 CPFN_API int cpfn_mlp_chain(const cpfn_mlp_chain_t *chain, cpfn_stream_t stream);
 
+/* ---------------------------------------------------------------------------
+ * Small fused helpers of the inference forward.
+ * ------------------------------------------------------------------------- */
+
+/* three_nn followed by the inverse-distance weights of the FP layer: replaces
+ * three_nn + sqrt (modules/geometry_utils.py:184) + 1/(d+1e-8) normalised
+ * (pointset_feature_propagation.py:38-42).  weight, idx: [B,n,3]. */
+CPFN_API int cpfn_three_nn_weights(const float *unknown, const float *known, int B, int n, int m,
+                                   float *weight, int32_t *idx, cpfn_stream_t stream);
+
+/* new_xyz[b,s,:] = xyz[b, idx[b,s], :] (select_point_subset on positions,
+ * pointset_abstraction.py:50).  xyz [B,N,3], idx [B,S] -> out [B,S,3]. */
+CPFN_API int cpfn_gather_xyz(const float *xyz, const int32_t *idx, int B, int N, int S, float *out,
+                             cpfn_stream_t stream);
+
+/* X = normalize(heads[:, x_off:x_off+3]), W = softmax(heads[:, w_off:w_off+K])
+ * (Utils/training_utils.py:141-142).  heads [rows, ld] -> X [rows,3], W [rows,K]; K <= 64. */
+CPFN_API int cpfn_spfn_post(const float *heads, long long rows, int ld, int x_off, int w_off, int K,
+                            float *X, float *W, cpfn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -189,3 +189,26 @@ def test_live_against_reference_extension(cuda_dev, ref_ext):
     assert torch.equal(cuda_ops.gather_points(f2, a), ref_ext.gather_points(f2, a))
     lat = _t(synth.lattice_cloud(4, 5000, seed=9, pitch=12), cuda_dev)
     assert torch.equal(cuda_ops.farthest_point_sampling(lat, 700), ref_ext.farthest_point_sampling(lat, 700))
+
+
+def test_three_nn_weights_and_gather_xyz_and_post(cuda_dev, oracle_ops):
+    """Fused helpers (csrc/glue.cu) against the op sequences they replace."""
+    from cpfn_b200 import fused
+    rng = np.random.default_rng(7)
+    u = synth.uniform_cloud(3, 1000, seed=3)
+    k = synth.lattice_cloud(3, 77, seed=4, pitch=8)
+    w, idx = fused.three_nn_weights(_t(u, cuda_dev), _t(k, cuda_dev))
+    d2, ridx = oracle_ops.three_nn(u, k)
+    np.testing.assert_array_equal(idx.cpu().numpy(), ridx)
+    d = torch.sqrt(torch.from_numpy(d2))
+    r = 1.0 / (d + 1e-8)
+    ref_w = (r / torch.sum(r, dim=2, keepdim=True)).numpy()
+    np.testing.assert_allclose(w.cpu().numpy(), ref_w, rtol=3e-7, atol=0)
+    fi = rng.integers(0, 1000, size=(3, 50)).astype(np.int32)
+    g = fused.gather_xyz(_t(u, cuda_dev), _t(fi, cuda_dev)).cpu().numpy()
+    np.testing.assert_array_equal(g, np.take_along_axis(u, fi.astype(np.int64)[:, :, None], axis=1))
+    h = rng.normal(size=(2, 333, 35)).astype(np.float32) * 3
+    X, W = fused.spfn_post(_t(h, cuda_dev), 0, 7, 28)
+    ht = torch.from_numpy(h)
+    np.testing.assert_allclose(X.cpu().numpy(), torch.nn.functional.normalize(ht[:, :, :3], dim=2).numpy(), rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(W.cpu().numpy(), torch.softmax(ht[:, :, 7:], dim=2).numpy(), rtol=2e-6, atol=1e-9)
