@@ -46,6 +46,7 @@ SIGNATURES = {
     "cpfn_three_weighted_sum_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                              c_int, c_void_p, c_void_p]),
     "cpfn_three_nn_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "cpfn_linear_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "cpfn_gather_xyz": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "cpfn_spfn_post": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "cpfn_mlp_packed_bytes": (c_size_t, [c_int, c_int]),

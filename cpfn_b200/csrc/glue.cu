@@ -104,8 +104,36 @@ spfn_post_kernel(const float *__restrict__ heads, long long rows, int ld, int x_
     if (k < K) w[k] = v[k] / sum;
 }
 
+// out[r, co] = bias[co] + sum_k W[co, k] * x[r, k]  (fp32, one warp per output): the per-cloud
+// constant part of FP1's first layer (the broadcast global feature, 16 rows x 1024 -> 256).
+__global__ void __launch_bounds__(kGlueThreads)
+linear_rows_kernel(const float *__restrict__ x, const float *__restrict__ W, const float *__restrict__ bias,
+                   int rows, int cin, int cout, int ldo, float *__restrict__ out) {
+  const int warp = (blockIdx.x * kGlueThreads + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows * cout) return;
+  const int r = warp / cout, co = warp - r * cout;
+  const float *xr = x + static_cast<size_t>(r) * cin, *w = W + static_cast<size_t>(co) * cin;
+  float acc = 0.f;
+  for (int k = lane; k < cin; k += 32) acc = fmaf(__ldg(w + k), __ldg(xr + k), acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) out[static_cast<size_t>(r) * ldo + co] = acc + __ldg(bias + co);
+}
+
 }  // namespace
 }  // namespace cpfn
+
+extern "C" int cpfn_linear_rows(const float *x, const float *W, const float *bias, int rows, int cin, int cout,
+                                int ldo, float *out, cpfn_stream_t stream) {
+  using namespace cpfn;
+  if (rows < 0 || cin <= 0 || cout <= 0 || ldo < cout) return CPFN_EINVAL;
+  if (rows == 0) return CPFN_OK;
+  if (!x || !W || !bias || !out) return CPFN_EINVAL;
+  const long long warps = static_cast<long long>(rows) * cout;
+  const unsigned grid = static_cast<unsigned>((warps * 32 + kGlueThreads - 1) / kGlueThreads);
+  linear_rows_kernel<<<grid, kGlueThreads, 0, as_stream(stream)>>>(x, W, bias, rows, cin, cout, ldo, out);
+  return check_launch();
+}
 
 extern "C" int cpfn_three_nn_weights(const float *unknown, const float *known, int B, int n, int m,
                                      float *weight, int32_t *idx, cpfn_stream_t stream) {

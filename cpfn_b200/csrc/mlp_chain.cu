@@ -57,6 +57,7 @@ struct LayerP {
 };
 
 struct ChainP {
+  int split_cout;     // single-layer chains only: gridDim.y = cout chunks, one chunk per CTA
   int n_layers;
   LayerP L[kMaxLayers];
   const uint8_t *weights;
@@ -322,10 +323,12 @@ mlp_chain_kernel(const __grid_constant__ ChainP p) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        for (int blk = 0; blk < p.total_blocks; ++blk) {
+        const int nblk = p.split_cout ? p.L[0].cin_atoms * 2 : p.total_blocks;
+        const size_t blk0 = p.split_cout ? static_cast<size_t>(blockIdx.y) * nblk : 0;
+        for (int blk = 0; blk < nblk; ++blk) {
           mbar_wait(empty + stage, phase ^ 1);
           mbar_arrive_expect_tx(full + stage, kStageBytes);
-          bulk_g2s(ring + stage * kStageBytes, p.weights + static_cast<size_t>(blk) * kStageBytes, kStageBytes,
+          bulk_g2s(ring + stage * kStageBytes, p.weights + (blk0 + blk) * kStageBytes, kStageBytes,
                    full + stage);
           if (++stage == p.nstage) { stage = 0; phase ^= 1; }
         }
@@ -342,8 +345,9 @@ mlp_chain_kernel(const __grid_constant__ ChainP p) {
         for (int l = 0; l < p.n_layers; ++l) {
           const LayerP &L = p.L[l];
           const uint32_t in_buf = smem_u32(act0);   // in-place: a layer's output overwrites its (fully consumed) input
-          for (int m0 = 0; m0 < L.cout_chunks; m0 += wave_max) {
-            const int mc = min(wave_max, L.cout_chunks - m0);
+          const int n_chunks = p.split_cout ? 1 : L.cout_chunks;
+          for (int m0 = 0; m0 < n_chunks; m0 += wave_max) {
+            const int mc = min(wave_max, n_chunks - m0);
             mbar_wait(act_ready, act_phase);
             act_phase ^= 1;
             tc_fence_after();
@@ -402,13 +406,15 @@ mlp_chain_kernel(const __grid_constant__ ChainP p) {
         const uint32_t out_buf = smem_u32(act0);
         const int cout_pad = L.cout_chunks * 128;
         const bool slow = (L.mask != nullptr) || (L.out_cm != nullptr);
-        for (int m0 = 0; m0 < L.cout_chunks; m0 += wave_max) {
-          const int mc = min(wave_max, L.cout_chunks - m0);
+        const int n_chunks = p.split_cout ? 1 : L.cout_chunks;
+        const int chunk_base = p.split_cout ? static_cast<int>(blockIdx.y) : 0;
+        for (int m0 = 0; m0 < n_chunks; m0 += wave_max) {
+          const int mc = min(wave_max, n_chunks - m0);
           mbar_wait(acc_full, acc_phase);
           acc_phase ^= 1;
           tc_fence_after();
           for (int m = 0; m < mc; ++m) {
-            const int ch = (m0 + m) * 128 + row_in_chunk;
+            const int ch = (chunk_base + m0 + m) * 128 + row_in_chunk;
             const bool ch_real = ch < L.cout;
             const float bias = __ldg(L.bias + (L.bias_per_cloud ? cloud * cout_pad : 0) + ch);
             const bool to_smem = !last && (ch & ~1) < L.next_k16;
@@ -476,7 +482,7 @@ mlp_chain_kernel(const __grid_constant__ ChainP p) {
               atomicMax(reinterpret_cast<int *>(p.out + ((col0 + half * HC) / p.pool_g) * p.ldo + ch), __float_as_int(pool));
           }
           tc_fence_before();
-          const bool final_wave = last && (m0 + wave_max >= L.cout_chunks);
+          const bool final_wave = last && (m0 + wave_max >= n_chunks);
           if (!final_wave) {
             fence_proxy_async();
             mbar_arrive(act_ready);
@@ -624,8 +630,9 @@ mlp_chain_pm_kernel(const __grid_constant__ ChainP p) {
           for (int m = 0; m < mc; ++m) {
             const int chunk0 = (m0 + m) * 128;
             const int nch = min(128, cout16 - chunk0);
+            const int split = ((nch / 16 + 1) / 2) * 16;     // the quarter's two warps share the chunk's channels
 #pragma unroll 1
-            for (int cb = half * 64; cb < min(nch, half * 64 + 64); cb += 16) {
+            for (int cb = half ? split : 0; cb < (half ? nch : split); cb += 16) {
               const int ch0 = chunk0 + cb;
               uint32_t r[16];
               tmem_ld16(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + m * 128 + cb, r);
@@ -775,6 +782,9 @@ int launch_chain(const cpfn_mlp_chain_t *c, cudaStream_t st) {
       atomic_pool = true;
     }
   }
+  p.split_cout = (c->split_cout && NT != 128) ? 1 : 0;
+  if (c->split_cout && (c->n_layers != 1 || NT == 128)) return CPFN_EINVAL;
+  if (p.split_cout) max_chunks = 1;
   p.tmem_cols = NT == 128 ? pow2_at_least(128 * (max_chunks < 4 ? max_chunks : 4))
                           : pow2_at_least(NT * (max_chunks < 512 / NT ? max_chunks : 512 / NT));
   p.act_bytes0 = static_cast<int>(act_need[0]);
@@ -804,7 +814,8 @@ int launch_chain(const cpfn_mlp_chain_t *c, cudaStream_t st) {
   if (grid <= 0) return CPFN_OK;
   if (atomic_pool)
     CPFN_CUDA_TRY(cudaMemsetAsync(c->out, 0, sizeof(float) * static_cast<size_t>(p.cols / c->pool_g) * c->ldo, st));
-  kern<<<grid, kChainThreads, smem, st>>>(p);
+  const dim3 grid2(grid, p.split_cout ? p.L[0].cout_chunks : 1);
+  kern<<<grid2, kChainThreads, smem, st>>>(p);
   return check_launch();
 }
 

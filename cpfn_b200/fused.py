@@ -38,7 +38,7 @@ class _Chain(ctypes.Structure):
                 ("b_src", ctypes.c_void_p), ("b_ch", ctypes.c_int32), ("b_rows", ctypes.c_int32),
                 ("nn_w", ctypes.c_void_p),
                 ("out_mode", ctypes.c_int32), ("out", ctypes.c_void_p), ("ldo", ctypes.c_int32),
-                ("pool_g", ctypes.c_int32)]
+                ("pool_g", ctypes.c_int32), ("split_cout", ctypes.c_int32)]
 
 
 def available():
@@ -87,11 +87,20 @@ class PackedChain:
         blob = np.concatenate([pack_weights(w) for w, _, _ in layers])
         self.weights = torch.from_numpy(blob).to(device)
         self.biases = [torch.from_numpy(pad_bias(b)).to(device) for _, b, _ in layers]
+        self._layers = layers
+        self._single = None
+
+    def single_layer_chains(self):
+        """The same layers as one-layer chains (for the layer-by-layer, channel-split execution of
+        chains with few columns and wide layers: SA3, FP1)."""
+        if self._single is None:
+            self._single = [PackedChain([l], self.weights.device) for l in self._layers]
+        return self._single
 
 
 def run_chain(pc, B, cols_per_cloud, out, ldo, tile_cols=128, in_mode=IN_DENSE, a_src=None, a_ch=0, a_rows=0,
               idx=None, xyz=None, centers=None, group_k=0, b_src=None, b_ch=0, b_rows=0, nn_w=None,
-              out_mode=OUT_ROWS, pool_g=0, biases=None, bias_per_cloud=(), masks=None, out_cm=None):
+              out_mode=OUT_ROWS, pool_g=0, biases=None, bias_per_cloud=(), masks=None, out_cm=None, split_cout=False):
     """Enqueue one fused chain on torch's current stream."""
     c = _Chain()
     c.n_layers = len(pc.dims)
@@ -111,6 +120,7 @@ def run_chain(pc, B, cols_per_cloud, out, ldo, tile_cols=128, in_mode=IN_DENSE, 
     c.idx, c.xyz, c.centers, c.group_k = p(idx), p(xyz), p(centers), group_k
     c.b_src, c.b_ch, c.b_rows, c.nn_w = p(b_src), b_ch, b_rows, p(nn_w)
     c.out_mode, c.out, c.ldo, c.pool_g = out_mode, out.data_ptr(), ldo, pool_g
+    c.split_cout = int(split_cout)
     with torch.cuda.device(out.device):
         _lib.check(_lib.lib().cpfn_mlp_chain(ctypes.byref(c), torch.cuda.current_stream(out.device).cuda_stream),
                    "mlp_chain")
@@ -141,6 +151,41 @@ def _pick_tile(dims, cols_per_cloud, need_cloud_aligned=False, prefer=128):
         if need + 1024 + 4096 + 3 * 16384 <= 227 * 1024:
             return tile
     raise RuntimeError("cpfn_b200.fused: chain does not fit shared memory: %r" % (dims,))
+
+
+def run_layerwise(pc, B, cols_per_cloud, out, first, out_mode=OUT_ROWS, pool_g=0, bias0=None):
+    """Few columns, wide layers: run the chain one layer per launch with one CTA per (64-column tile,
+    128-channel chunk) so that the weight stream is spread over many SMs; activations between the
+    layers are point-major fp32 rows in HBM (a few MB, L2 resident).  `first` = kwargs of the input
+    (in_mode, a_src, ...) for the first layer."""
+    dev = out.device
+    chains = pc.single_layer_chains()
+    x_kwargs = dict(first)
+    for l, c in enumerate(chains):
+        last = l == len(chains) - 1
+        cout = c.dims[0][1]
+        dst = out if last else torch.empty(B, cols_per_cloud, cout, dtype=torch.float32, device=dev)
+        extra = {}
+        if l == 0 and bias0 is not None:
+            extra = dict(biases=[bias0], bias_per_cloud=(0,))
+        tile = 64 if cols_per_cloud % 64 == 0 else 32
+        if (c.dims[0][0] + 63) // 64 * 2 * tile * 128 + 5120 + 3 * 16384 > 227 * 1024:
+            tile = 32
+        run_chain(c, B, cols_per_cloud, dst, cout, tile_cols=tile, split_cout=True,
+                  out_mode=(out_mode if last else OUT_ROWS), pool_g=(pool_g if last else 0), **x_kwargs, **extra)
+        x_kwargs = dict(in_mode=IN_DENSE, a_src=dst, a_ch=cout, a_rows=cols_per_cloud)
+    return out
+
+
+def linear_rows(x, W, bias, out):
+    """out[r, :cout] = bias + x[r] @ W.T in fp32 (x [rows, cin], W [cout, cin])."""
+    rows, cin = x.shape
+    cout = W.shape[0]
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().cpfn_linear_rows(x.data_ptr(), W.data_ptr(), bias.data_ptr(), rows, cin, cout,
+                                               out.shape[1], out.data_ptr(), _stream(x)), "linear_rows")
+    cuda_ops.count_launches(1)
+    return out
 
 
 def mlp_chain(*args, **kwargs):
@@ -232,9 +277,12 @@ def sa_forward_pm(module, xyz, feats_pm):
         idx = torch.arange(N, dtype=torch.int32, device=dev).repeat(B)
         centers = torch.zeros(B, 3, dtype=torch.float32, device=dev)
         out = torch.empty(B, 1, cout, dtype=torch.float32, device=dev)
-        tile = pick_tile(pc.dims, N, need_cloud_aligned=True, prefer=32 if cout > 512 else 128)
-        run_chain(pc, B, N, out, cout, tile_cols=tile, in_mode=IN_GROUP, a_src=feats_pm, a_ch=D, a_rows=N,
-                  idx=idx, xyz=xyz, centers=centers, group_k=N, out_mode=OUT_POOL, pool_g=N)
+        first = dict(in_mode=IN_GROUP, a_src=feats_pm, a_ch=D, a_rows=N, idx=idx, xyz=xyz, centers=centers, group_k=N)
+        if N % 32 == 0 and B * N <= 16384:
+            run_layerwise(pc, B, N, out, first, out_mode=OUT_POOL, pool_g=N)
+        else:
+            tile = pick_tile(pc.dims, N, need_cloud_aligned=True, prefer=32 if cout > 512 else 128)
+            run_chain(pc, B, N, out, cout, tile_cols=tile, out_mode=OUT_POOL, pool_g=N, **first)
         return None, out
     S, K = module.num_points, module.num_samples_list[0]
     fps_idx = cuda_ops.farthest_point_sampling(xyz, S)
@@ -257,7 +305,8 @@ def _fp_chain(module, device, split=None):
             w, b = fold_bn(conv.weight, conv.bias, bn)
             if j == 0 and split:
                 # the constant part becomes its own one-layer chain (with the layer's bias)
-                wconst = PackedChain([(np.ascontiguousarray(w[:, split[0]:split[1]]), b, False)], device)
+                wconst = (torch.from_numpy(np.ascontiguousarray(w[:, split[0]:split[1]])).to(device),
+                          torch.from_numpy(np.ascontiguousarray(b)).to(device))
                 w = np.concatenate([w[:, :split[0]], w[:, split[1]:]], axis=1)
             layers.append((w, b, True))
         pc = (PackedChain(layers, device), wconst)
@@ -278,11 +327,15 @@ def fp_forward_pm(module, xyz1, xyz2, feats1_pm, feats2_pm):
         pc, wconst = _fp_chain(module, dev, split=(D1, D1 + D2))
         g = feats2_pm.reshape(B, D2).contiguous()
         bias0 = torch.zeros(B, pc.biases[0].numel(), dtype=torch.float32, device=dev)
-        run_chain(wconst, B, 1, bias0, bias0.shape[1], tile_cols=32, in_mode=IN_DENSE, a_src=g, a_ch=D2, a_rows=1)
+        linear_rows(g, wconst[0], wconst[1], bias0)          # fp32: W_global @ g + b, one vector per cloud
         out = torch.empty(B, N, pc.dims[-1][1], dtype=torch.float32, device=dev)
-        tile = pick_tile(pc.dims, N, need_cloud_aligned=True)
-        run_chain(pc, B, N, out, out.shape[2], tile_cols=tile, in_mode=IN_DENSE, a_src=feats1_pm, a_ch=D1, a_rows=N,
-                  biases=[bias0] + [None] * (len(pc.dims) - 1), bias_per_cloud=(0,))
+        first = dict(in_mode=IN_DENSE, a_src=feats1_pm, a_ch=D1, a_rows=N)
+        if N % 32 == 0 and B * N <= 16384:
+            run_layerwise(pc, B, N, out, first, bias0=bias0)
+        else:
+            tile = pick_tile(pc.dims, N, need_cloud_aligned=True)
+            run_chain(pc, B, N, out, out.shape[2], tile_cols=tile, biases=[bias0] + [None] * (len(pc.dims) - 1),
+                      bias_per_cloud=(0,), **first)
         return out
     pc, _ = _fp_chain(module, dev)
     w, idx = three_nn_weights(xyz1, xyz2)

@@ -169,6 +169,7 @@ typedef struct {
   const float *nn_w;          /* INTERP: [B,N,3] interpolation weights */
   int32_t out_mode;           /* CPFN_MLP_OUT_* */
   float *out; int32_t ldo; int32_t pool_g;
+  int32_t split_cout;         /* 1: single-layer chain, tile_cols 64/32: one CTA per (column tile, 128-channel chunk) */
 } cpfn_mlp_chain_t;
 
 /* Replaces the conv+BN+ReLU(+max) chains of pointset_abstraction.py:61-74,
@@ -191,6 +192,12 @@ CPFN_API int cpfn_three_nn_weights(const float *unknown, const float *known, int
  * pointset_abstraction.py:50).  xyz [B,N,3], idx [B,S] -> out [B,S,3]. */
 CPFN_API int cpfn_gather_xyz(const float *xyz, const int32_t *idx, int B, int N, int S, float *out,
                              cpfn_stream_t stream);
+
+/* out[r, co] = bias[co] + sum_k W[co,k] x[r,k] in fp32 (few rows): the per-cloud constant part of
+ * the first FP layer when pos2 is None (pointset_feature_propagation.py:33-34: feats2 repeated over
+ * all points contributes the same vector to every point of a cloud). */
+CPFN_API int cpfn_linear_rows(const float *x, const float *W, const float *bias, int rows, int cin,
+                              int cout, int ldo, float *out, cpfn_stream_t stream);
 
 /* X = normalize(heads[:, x_off:x_off+3]), W = softmax(heads[:, w_off:w_off+K])
  * (Utils/training_utils.py:141-142).  heads [rows, ld] -> X [rows,3], W [rows,K]; K <= 64. */

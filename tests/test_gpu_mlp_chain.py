@@ -149,3 +149,41 @@ def test_invalid_arguments(cuda_dev):
         fused.run_chain(pc, 1, 64, out, 32, tile_cols=48, a_src=x, a_ch=16, a_rows=64)          # bad tile
     with pytest.raises(RuntimeError):
         fused.run_chain(pc, 1, 64, out, 32, tile_cols=64, a_src=x, a_ch=12, a_rows=64)          # width mismatch
+
+
+@pytest.mark.parametrize("dims,tile", [([512, 1024], 64), ([260, 256], 64), ([100, 300], 32)])
+def test_single_layer_channel_split(cuda_dev, dims, tile):
+    """split_cout: one CTA per (column tile, 128-channel chunk); rows and pooled outputs."""
+    rng = np.random.default_rng(dims[1])
+    pc, layers = _chain(dims, rng, cuda_dev)
+    B, n = 4, 128
+    x = torch.from_numpy(rng.normal(size=(B, n, dims[0])).astype(np.float32)).to(cuda_dev)
+    out = torch.full((B, n, dims[1]), float("nan"), device=cuda_dev)
+    fused.run_chain(pc, B, n, out, dims[1], tile_cols=tile, in_mode=fused.IN_DENSE, a_src=x, a_ch=dims[0], a_rows=n,
+                    split_cout=True)
+    ref = _ref(x, layers)
+    assert _rel(out, ref) < TOL, _rel(out, ref)
+    pooled = torch.full((B, 1, dims[1]), float("nan"), device=cuda_dev)
+    fused.run_chain(pc, B, n, pooled, dims[1], tile_cols=tile, in_mode=fused.IN_DENSE, a_src=x, a_ch=dims[0], a_rows=n,
+                    split_cout=True, out_mode=fused.OUT_POOL, pool_g=n)
+    assert _rel(pooled, ref.max(dim=1, keepdim=True)[0]) < TOL
+
+
+def test_layerwise_equals_fused_chain(cuda_dev):
+    rng = np.random.default_rng(9)
+    dims = [256, 256, 256]
+    pc, layers = _chain(dims, rng, cuda_dev)
+    B, n = 16, 128
+    x = torch.from_numpy(rng.normal(size=(B, n, 256)).astype(np.float32)).to(cuda_dev)
+    bias0 = torch.from_numpy(rng.normal(size=(B, 256)).astype(np.float32)).to(cuda_dev)
+    a = torch.empty(B, n, 256, device=cuda_dev)
+    fused.run_layerwise(pc, B, n, a, dict(in_mode=fused.IN_DENSE, a_src=x, a_ch=256, a_rows=n), bias0=bias0)
+    h = torch.relu(x @ torch.from_numpy(layers[0][0]).to(cuda_dev).t() + bias0[:, None, :])
+    ref = torch.relu(h @ torch.from_numpy(layers[1][0]).to(cuda_dev).t() + torch.from_numpy(layers[1][1]).to(cuda_dev))
+    assert _rel(a, ref) < TOL
+    w = torch.from_numpy(rng.normal(size=(40, 1000)).astype(np.float32)).to(cuda_dev)
+    g = torch.from_numpy(rng.normal(size=(5, 1000)).astype(np.float32)).to(cuda_dev)
+    bb = torch.from_numpy(rng.normal(size=40).astype(np.float32)).to(cuda_dev)
+    o = torch.zeros(5, 128, device=cuda_dev)
+    fused.linear_rows(g, w, bb, o)
+    assert _rel(o[:, :40], g @ w.t() + bb) < 1e-5 and float(o[:, 40:].abs().max()) == 0.0
