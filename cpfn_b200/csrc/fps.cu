@@ -186,36 +186,24 @@ __device__ __forceinline__ void fps_mbar_wait_cluster(unsigned long long *bar, u
       "}\n" ::"r"(fps_smem_u32(bar)), "r"(parity) : "memory");
 }
 
-// Block-wide argmax returning the whole 64-bit key (hi = distance bits, lo = ~rank; 0 = no candidate).
-__device__ __forceinline__ unsigned long long block_argmax_key(uint32_t hi, uint32_t lo,
-                                                               unsigned long long (*slot)[32], int buf,
-                                                               int nwarps) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t M = __reduce_max_sync(0xffffffffu, hi);
-  uint32_t L = __reduce_max_sync(0xffffffffu, hi == M ? lo : 0u);
-  if (lane == 0) slot[buf][warp] = (static_cast<unsigned long long>(M) << 32) | L;
-  __syncthreads();
-  const unsigned long long v = lane < nwarps ? slot[buf][lane] : 0ull;
-  const uint32_t h2 = static_cast<uint32_t>(v >> 32), l2 = static_cast<uint32_t>(v);
-  M = __reduce_max_sync(0xffffffffu, h2);
-  L = __reduce_max_sync(0xffffffffu, h2 == M ? l2 : 0u);
-  return (static_cast<unsigned long long>(M) << 32) | L;
-}
+constexpr int kFpsClusterThreads = 256;
+constexpr int kFpsClusterWarps = kFpsClusterThreads / 32;
 
-constexpr int kFpsClusterThreads = 512;   // == the reference's block size T for N >= 512, see fps_rank
-
+// Thread t owns k = r*Nc + t + i*256 (Nc a multiple of 512).  With the reference's T = 512 the rank of
+// point i is (bitrev9(k mod 512) << 20) | (k >> 9): even i share k mod 512 = t, odd i have t + 256 whose
+// bit-reversal is one larger, so scanning the even i first and then the odd i visits a thread's points
+// in increasing reference rank and the strict '>' keeps the right one on ties.
 template <int PPT>
 __global__ void __launch_bounds__(kFpsClusterThreads, 1)
 fps_cluster_kernel(const float *__restrict__ xyz, int N, int m, int log2T, int Nc,
                    int32_t *__restrict__ idx) {
   extern __shared__ float s_xyz[];
-  __shared__ unsigned long long slot[2][32];
-  __shared__ __align__(8) unsigned long long xslot[2][8];
+  __shared__ __align__(8) unsigned long long xslot[2][8 * kFpsClusterWarps];   // [parity][sender CTA * 8 + sender warp]
   __shared__ __align__(8) unsigned long long xbar[2];
   const uint32_t C = cluster_nctarank(), r = cluster_ctarank();
   const int cloud = blockIdx.x / C;
-  const int t = threadIdx.x;
-  constexpr int NT = kFpsClusterThreads, nwarps = NT / 32;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  constexpr int NT = kFpsClusterThreads;
   const int Np = (N + 31) & ~31;
   const float *p = xyz + static_cast<size_t>(cloud) * N * 3;
   int32_t *out = idx + static_cast<size_t>(cloud) * m;
@@ -227,11 +215,10 @@ fps_cluster_kernel(const float *__restrict__ xyz, int N, int m, int log2T, int N
     fps_mbar_init(&xbar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  for (int i = t; i < 2 * 8 * kFpsClusterWarps; i += NT) (&xslot[0][0])[i] = 0ull;
   __syncthreads();
   cluster_sync_all();                    // all barriers exist before any peer can complete_tx on them
 
-  // thread t owns k = r*Nc + t + i*512: k mod 512 is the same for all i, so scanning i upward visits
-  // the thread's points in increasing reference rank and strict '>' keeps the right one on ties
   float px[PPT], py[PPT], pz[PPT], tmp[PPT];
   const int k0 = static_cast<int>(r) * Nc + t;
 #pragma unroll
@@ -246,14 +233,15 @@ fps_cluster_kernel(const float *__restrict__ xyz, int N, int m, int log2T, int N
     px[i] = x; py[i] = y; pz[i] = z;
     tmp[i] = live ? 1e10f : -1.0f;
   }
-  // where this thread (t < C) delivers: CTA t's xslot[parity][r] and xbar[parity]
+  // lane l < C of every warp delivers the warp's key to CTA l: slot [parity][r*8 + warp], barrier [parity]
   uint32_t my_slot0 = 0, my_slot1 = 0, my_bar0 = 0, my_bar1 = 0;
-  if (t < static_cast<int>(C)) {
-    my_slot0 = mapa_u32(fps_smem_u32(&xslot[0][r]), t);
-    my_slot1 = mapa_u32(fps_smem_u32(&xslot[1][r]), t);
-    my_bar0 = mapa_u32(fps_smem_u32(&xbar[0]), t);
-    my_bar1 = mapa_u32(fps_smem_u32(&xbar[1]), t);
+  if (lane < static_cast<int>(C)) {
+    my_slot0 = mapa_u32(fps_smem_u32(&xslot[0][r * kFpsClusterWarps + warp]), lane);
+    my_slot1 = mapa_u32(fps_smem_u32(&xslot[1][r * kFpsClusterWarps + warp]), lane);
+    my_bar0 = mapa_u32(fps_smem_u32(&xbar[0]), lane);
+    my_bar1 = mapa_u32(fps_smem_u32(&xbar[1]), lane);
   }
+  const int nkeys = static_cast<int>(C) * kFpsClusterWarps;      // <= 64: two per lane
 
   if (r == 0 && t == 0) out[0] = 0;
   float cx = sx[0], cy = sy[0], cz = sz[0];
@@ -261,23 +249,29 @@ fps_cluster_kernel(const float *__restrict__ xyz, int N, int m, int log2T, int N
     float best = -1.0f;
     int bi = 0;
 #pragma unroll
-    for (int i = 0; i < PPT; ++i) {
-      const float d2 = fminf(sqdist3(px[i], py[i], pz[i], cx, cy, cz), tmp[i]);
-      tmp[i] = d2;
-      if (d2 > best) { best = d2; bi = i; }
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+      for (int i = h; i < PPT; i += 2) {     // even i first, then odd i: increasing reference rank
+        const float d2 = fminf(sqdist3(px[i], py[i], pz[i], cx, cy, cz), tmp[i]);
+        tmp[i] = d2;
+        if (d2 > best) { best = d2; bi = i; }
+      }
     }
     uint32_t hi = 0u, lo = 0u;
     if (best >= 0.0f) {
       hi = __float_as_uint(best);
       lo = ~fps_rank(static_cast<uint32_t>(k0 + bi * NT), log2T);
     }
-    const unsigned long long key = block_argmax_key(hi, lo, slot, j & 1, nwarps);
+    const uint32_t Mw = __reduce_max_sync(0xffffffffu, hi);
+    const uint32_t Lw = __reduce_max_sync(0xffffffffu, hi == Mw ? lo : 0u);
+    const unsigned long long key = (static_cast<unsigned long long>(Mw) << 32) | Lw;
     const int par = j & 1;
-    if (t == 0) fps_mbar_expect_tx(&xbar[par], 8u * C);
-    if (t < static_cast<int>(C)) st_async_u64(par ? my_slot1 : my_slot0, key, par ? my_bar1 : my_bar0);
+    if (t == 0) fps_mbar_expect_tx(&xbar[par], 8u * nkeys);
+    if (lane < static_cast<int>(C)) st_async_u64(par ? my_slot1 : my_slot0, key, par ? my_bar1 : my_bar0);
     fps_mbar_wait_cluster(&xbar[par], ((j - 1) >> 1) & 1);   // (j-1)/2-th use of this barrier
-    const int lane = t & 31;
-    const unsigned long long v = lane < static_cast<int>(C) ? xslot[par][lane] : 0ull;
+    const unsigned long long v0 = lane < nkeys ? xslot[par][lane] : 0ull;
+    const unsigned long long v1 = lane + 32 < nkeys ? xslot[par][lane + 32] : 0ull;
+    const unsigned long long v = v0 > v1 ? v0 : v1;
     const uint32_t h2 = static_cast<uint32_t>(v >> 32), l2 = static_cast<uint32_t>(v);
     const uint32_t M = __reduce_max_sync(0xffffffffu, h2);
     const uint32_t L = __reduce_max_sync(0xffffffffu, h2 == M ? l2 : 0u);
@@ -400,11 +394,11 @@ extern "C" int cpfn_furthest_point_sampling(const float *xyz, int B, int N, int 
     while (C > 1 && static_cast<long long>(B) * C > sms) C >>= 1;
     if (C > 1) {
       const int Nc = ((N + C - 1) / C + 511) / 512 * 512;
-      const int ppt = Nc / 512;
-      if (ppt <= 1) return launch_cluster<1>(xyz, B, N, nsamples, log2T, C, Nc, idx, st);
+      const int ppt = Nc / 256;
       if (ppt <= 2) return launch_cluster<2>(xyz, B, N, nsamples, log2T, C, Nc, idx, st);
       if (ppt <= 4) return launch_cluster<4>(xyz, B, N, nsamples, log2T, C, Nc, idx, st);
       if (ppt <= 8) return launch_cluster<8>(xyz, B, N, nsamples, log2T, C, Nc, idx, st);
+      if (ppt <= 16) return launch_cluster<16>(xyz, B, N, nsamples, log2T, C, Nc, idx, st);
     }
   }
   // Block size: a multiple of T (>= one warp); N >= 1024 always uses 1024.
