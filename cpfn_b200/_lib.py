@@ -45,6 +45,11 @@ SIGNATURES = {
                                         c_void_p, c_void_p]),
     "cpfn_three_weighted_sum_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                              c_int, c_void_p, c_void_p]),
+    "cpfn_moments_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "cpfn_weighted_moments": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t,
+                                      c_void_p]),
+    "cpfn_weighted_moments_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
+                                           c_void_p, c_void_p]),
     "cpfn_three_nn_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "cpfn_linear_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "cpfn_gather_xyz": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),

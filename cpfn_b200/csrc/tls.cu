@@ -41,7 +41,7 @@ namespace {
 constexpr int kTlsThreads = 256;
 constexpr int kMaxCP = 1024;      // points staged per sub-chunk
 constexpr int kPPT = 32;          // points per thread and sub-chunk (weights preloaded in registers)
-constexpr int kF1 = 23, kF2 = 31, kF3 = 2;
+constexpr int kF1 = 23, kF2 = 31, kF3 = 2, kF4 = 32;   // kF4: raw moments up to third order (training path)
 constexpr int kFP = 32;           // padded feature stride of the partial arrays
 constexpr int kState = 24;        // doubles per (b,k)
 // state layout
@@ -70,7 +70,7 @@ TlsGeom tls_geom(int B, int N, int K, int sms) {
   return g;
 }
 
-template <int PASS> struct NFeat { static constexpr int F = PASS == 1 ? kF1 : (PASS == 2 ? kF2 : kF3); };
+template <int PASS> struct NFeat { static constexpr int F = PASS == 1 ? kF1 : (PASS == 2 ? kF2 : (PASS == 3 ? kF3 : kF4)); };
 
 template <int PASS>
 __global__ void __launch_bounds__(kTlsThreads, 2)
@@ -91,7 +91,7 @@ tls_pass_kernel(const float *__restrict__ P, const float *__restrict__ X,
   const int ppt = CP / G;
 
   float c0 = 0.f, c1 = 0.f, c2 = 0.f, e0 = 0.f, e1 = 0.f, e2 = 0.f;   // per-slot constants
-  if (PASS >= 2) {
+  if (PASS == 2 || PASS == 3) {
     const double *st = state + (static_cast<size_t>(b) * K + k) * kState;
     if (PASS == 2) {
       c0 = static_cast<float>(st[ST_MU]); c1 = static_cast<float>(st[ST_MU + 1]); c2 = static_cast<float>(st[ST_MU + 2]);
@@ -172,6 +172,22 @@ tls_pass_kernel(const float *__restrict__ P, const float *__restrict__ X,
         const float qx = w * ax, qy = w * ay, qz = w * az;
         acc[25] = fmaf(qx, ax, acc[25]); acc[26] = fmaf(qx, ay, acc[26]); acc[27] = fmaf(qx, az, acc[27]);
         acc[28] = fmaf(qy, ay, acc[28]); acc[29] = fmaf(qy, az, acc[29]); acc[30] = fmaf(qz, az, acc[30]);
+      } else if (PASS == 4) {
+        // raw moments  sum w * [1, p, p p^T, p p p, x, x x^T, x (p.x)]  (feature order of cpfn_weighted_moments)
+        const float4 x = sx[j];
+        const float wx = w * p.x, wy = w * p.y, wz = w * p.z;
+        acc[0] += w; acc[1] += wx; acc[2] += wy; acc[3] += wz;
+        const float uxx = wx * p.x, uxy = wx * p.y, uxz = wx * p.z, uyy = wy * p.y, uyz = wy * p.z, uzz = wz * p.z;
+        acc[4] += uxx; acc[5] += uxy; acc[6] += uxz; acc[7] += uyy; acc[8] += uyz; acc[9] += uzz;
+        acc[10] = fmaf(uxx, p.x, acc[10]); acc[11] = fmaf(uxx, p.y, acc[11]); acc[12] = fmaf(uxx, p.z, acc[12]);
+        acc[13] = fmaf(uxy, p.y, acc[13]); acc[14] = fmaf(uxy, p.z, acc[14]); acc[15] = fmaf(uxz, p.z, acc[15]);
+        acc[16] = fmaf(uyy, p.y, acc[16]); acc[17] = fmaf(uyy, p.z, acc[17]); acc[18] = fmaf(uyz, p.z, acc[18]);
+        acc[19] = fmaf(uzz, p.z, acc[19]);
+        const float vx = w * x.x, vy = w * x.y, vz = w * x.z;
+        acc[20] += vx; acc[21] += vy; acc[22] += vz;
+        acc[23] = fmaf(vx, x.x, acc[23]); acc[24] = fmaf(vx, x.y, acc[24]); acc[25] = fmaf(vx, x.z, acc[25]);
+        acc[26] = fmaf(vy, x.y, acc[26]); acc[27] = fmaf(vy, x.z, acc[27]); acc[28] = fmaf(vz, x.z, acc[28]);
+        acc[29] = fmaf(vx, x.w, acc[29]); acc[30] = fmaf(vy, x.w, acc[30]); acc[31] = fmaf(vz, x.w, acc[31]);
       } else {
         // cone_fitter.py:25-33: dir = normalize(p - apex, eps 1e-12); dot = axis . dir
         const float vx = p.x - c0, vy = p.y - c1, vz = p.z - c2;
@@ -516,6 +532,87 @@ tls_solve3_kernel(const double *__restrict__ part, const double *__restrict__ st
   o_ha[bk] = half;
 }
 
+// ---- training path: raw weighted moments and their gradients -----------------------------------
+// M[b,k,f] = sum_n Wt[b,n,k] * psi_f(p_n, x_n), psi = [1, p(3), p p^T(6), p p p(10), x(3), x x^T(6), x (p.x)(3)].
+// Linear in the weights, so the backward is dWt[b,n,k] = sum_f psi_f(n) dM[b,k,f] (same thread mapping as
+// the forward: coalesced over k) and dX[b,n,:] = sum_k Wt[b,n,k] * sum_{f>=20} dM[b,k,f] dpsi_f/dx.
+__global__ void __launch_bounds__(kSolveWarps * 32)
+tls_sum_partials_kernel(const double *__restrict__ part, double *__restrict__ out, int BK, int K, int chunks) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bk = blockIdx.x * kSolveWarps + warp;
+  if (bk >= BK) return;
+  const int b = bk / K, k = bk - b * K;
+  out[static_cast<size_t>(bk) * kFP + lane] = sum_partials(part, b, k, K, chunks, lane);
+}
+
+__global__ void __launch_bounds__(kTlsThreads)
+moments_grad_w_kernel(const float *__restrict__ P, const float *__restrict__ X, const double *__restrict__ dM,
+                      int N, int K, int G, int CP, float *__restrict__ dW) {
+  extern __shared__ float4 s_pts[];
+  float4 *sp = s_pts, *sx = s_pts + CP;
+  const int b = blockIdx.y, t = threadIdx.x;
+  const bool active = t < G * K;
+  const int k = active ? t % K : 0, g = t / K;
+  const int n0 = blockIdx.x * CP;
+  const int cn = imin(CP, N - n0);
+  float d[kF4];
+  const double *dm = dM + (static_cast<size_t>(b) * K + k) * kFP;
+#pragma unroll
+  for (int f = 0; f < kF4; ++f) d[f] = static_cast<float>(dm[f]);
+  for (int i = t; i < cn; i += kTlsThreads) {
+    const float *p = P + (static_cast<size_t>(b) * N + n0 + i) * 3;
+    const float *x = X + (static_cast<size_t>(b) * N + n0 + i) * 3;
+    const float px = __ldg(p), py = __ldg(p + 1), pz = __ldg(p + 2);
+    const float xx = __ldg(x), xy = __ldg(x + 1), xz = __ldg(x + 2);
+    sp[i] = make_float4(px, py, pz, 0.f);
+    sx[i] = make_float4(xx, xy, xz, px * xx + py * xy + pz * xz);
+  }
+  __syncthreads();
+  if (!active) return;
+  float *o = dW + (static_cast<size_t>(b) * N + n0) * K + k;
+  for (int j = g; j < cn; j += G) {
+    const float4 p = sp[j], x = sx[j];
+    float a = d[0] + d[1] * p.x + d[2] * p.y + d[3] * p.z;
+    const float pxx = p.x * p.x, pxy = p.x * p.y, pxz = p.x * p.z, pyy = p.y * p.y, pyz = p.y * p.z, pzz = p.z * p.z;
+    a += d[4] * pxx + d[5] * pxy + d[6] * pxz + d[7] * pyy + d[8] * pyz + d[9] * pzz;
+    a += d[10] * pxx * p.x + d[11] * pxx * p.y + d[12] * pxx * p.z + d[13] * pxy * p.y + d[14] * pxy * p.z +
+         d[15] * pxz * p.z + d[16] * pyy * p.y + d[17] * pyy * p.z + d[18] * pyz * p.z + d[19] * pzz * p.z;
+    a += d[20] * x.x + d[21] * x.y + d[22] * x.z;
+    a += d[23] * x.x * x.x + d[24] * x.x * x.y + d[25] * x.x * x.z + d[26] * x.y * x.y + d[27] * x.y * x.z + d[28] * x.z * x.z;
+    a += (d[29] * x.x + d[30] * x.y + d[31] * x.z) * x.w;
+    o[static_cast<size_t>(j) * K] = a;
+  }
+}
+
+// one thread per point: dX[n,:] = sum_k w[n,k] * (dMx + D x + dMxp (p.x) + (dMxp.x) p)
+__global__ void __launch_bounds__(kTlsThreads)
+moments_grad_x_kernel(const float *__restrict__ P, const float *__restrict__ X, const float *__restrict__ W,
+                      const double *__restrict__ dM, int N, int K, float *__restrict__ dX) {
+  extern __shared__ float s_dm[];            // [K][12]: features 20..31 of this cloud
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < K * 12; i += kTlsThreads)
+    s_dm[i] = static_cast<float>(dM[(static_cast<size_t>(b) * K + i / 12) * kFP + 20 + i % 12]);
+  __syncthreads();
+  const int n = blockIdx.x * kTlsThreads + threadIdx.x;
+  if (n >= N) return;
+  const size_t row = static_cast<size_t>(b) * N + n;
+  const float px = __ldg(P + row * 3), py = __ldg(P + row * 3 + 1), pz = __ldg(P + row * 3 + 2);
+  const float xx = __ldg(X + row * 3), xy = __ldg(X + row * 3 + 1), xz = __ldg(X + row * 3 + 2);
+  const float pdx = px * xx + py * xy + pz * xz;
+  float gx = 0.f, gy = 0.f, gz = 0.f;
+  const float *w = W + row * K;
+  for (int k = 0; k < K; ++k) {
+    const float *d = s_dm + k * 12;          // 0-2: x, 3-8: xx xy xz yy yz zz, 9-11: x (p.x)
+    const float wk = __ldg(w + k);
+    const float s = d[9] * xx + d[10] * xy + d[11] * xz;
+    const float ax = d[0] + 2.f * d[3] * xx + d[4] * xy + d[5] * xz + d[9] * pdx + s * px;
+    const float ay = d[1] + d[4] * xx + 2.f * d[6] * xy + d[7] * xz + d[10] * pdx + s * py;
+    const float az = d[2] + d[5] * xx + d[7] * xy + 2.f * d[8] * xz + d[11] * pdx + s * pz;
+    gx = fmaf(wk, ax, gx); gy = fmaf(wk, ay, gy); gz = fmaf(wk, az, gz);
+  }
+  dX[row * 3] = gx; dX[row * 3 + 1] = gy; dX[row * 3 + 2] = gz;
+}
+
 struct TlsWs {
   double *state, *part;
   size_t bytes;
@@ -573,5 +670,50 @@ extern "C" int cpfn_fit_primitives(const float *P, const float *W, const float *
   tls_pass_kernel<3><<<grid, kTlsThreads, smem, st>>>(P, X, W, ws.state, ws.part, N, K, g.G, g.CP,
                                                       g.iters, g.chunks);
   tls_solve3_kernel<<<sgrid, kSolveWarps * 32, 0, st>>>(ws.part, ws.state, out, BK, K, g.chunks);
+  return check_launch();
+}
+
+extern "C" size_t cpfn_moments_workspace_bytes(int B, int N, int K) { return cpfn_fit_workspace_bytes(B, N, K); }
+
+extern "C" int cpfn_weighted_moments(const float *P, const float *X, const float *Wt, int B, int N, int K,
+                                     double *M, void *workspace, size_t workspace_bytes, cpfn_stream_t stream) {
+  using namespace cpfn;
+  if (B < 0 || N < 0 || K < 0) return CPFN_EINVAL;
+  if (B == 0 || K == 0) return CPFN_OK;
+  if (N == 0 || K > kTlsThreads || !P || !Wt || !X || !M || B > 65535) return CPFN_EINVAL;
+  const int sms = sm_count() > 0 ? sm_count() : 148;
+  const TlsGeom g = tls_geom(B, N, K, sms);
+  const TlsWs ws = tls_carve(workspace, B, K, g);
+  if (!workspace || workspace_bytes < ws.bytes) return CPFN_EWORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  const size_t smem = 2u * static_cast<size_t>(g.CP) * sizeof(float4) +
+                      static_cast<size_t>(kTlsThreads) * 8 * sizeof(double) + static_cast<size_t>(K) * kFP * sizeof(double);
+  if (smem > 48 * 1024)
+    CPFN_CUDA_TRY(cudaFuncSetAttribute(tls_pass_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  tls_pass_kernel<4><<<dim3(g.chunks, B), kTlsThreads, smem, st>>>(P, X, Wt, ws.state, ws.part, N, K, g.G, g.CP, g.iters,
+                                                               g.chunks);
+  const int BK = B * K;
+  tls_sum_partials_kernel<<<(BK + kSolveWarps - 1) / kSolveWarps, kSolveWarps * 32, 0, st>>>(ws.part, M, BK, K, g.chunks);
+  return check_launch();
+}
+
+extern "C" int cpfn_weighted_moments_grad(const float *P, const float *X, const float *Wt, const double *dM, int B,
+                                          int N, int K, float *dWt, float *dX, cpfn_stream_t stream) {
+  using namespace cpfn;
+  if (B < 0 || N < 0 || K < 0) return CPFN_EINVAL;
+  if (B == 0 || K == 0 || N == 0) return CPFN_OK;
+  if (K > kTlsThreads || !P || !Wt || !X || !dM || B > 65535) return CPFN_EINVAL;
+  cudaStream_t st = as_stream(stream);
+  if (dWt) {
+    const int G = imax(1, kTlsThreads / K);
+    const int CP = G * 32;
+    const size_t smem = 2u * static_cast<size_t>(CP) * sizeof(float4);
+    if (smem > 48 * 1024)
+      CPFN_CUDA_TRY(cudaFuncSetAttribute(moments_grad_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    moments_grad_w_kernel<<<dim3((N + CP - 1) / CP, B), kTlsThreads, smem, st>>>(P, X, dM, N, K, G, CP, dWt);
+  }
+  if (dX)
+    moments_grad_x_kernel<<<dim3((N + kTlsThreads - 1) / kTlsThreads, B), kTlsThreads, static_cast<size_t>(K) * 12 * sizeof(float), st>>>(
+        P, X, Wt, dM, N, K, dX);
   return check_launch();
 }

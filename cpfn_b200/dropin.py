@@ -47,6 +47,7 @@ def install(level="full"):
         "SPFN.plane_fitter": plane_fitter, "SPFN.sphere_fitter": sphere_fitter,
         "SPFN.cylinder_fitter": cylinder_fitter, "SPFN.cone_fitter": cone_fitter,
         "SPFN.fitter_factory": fitter_factory, "SPFN.losses_implementation": losses_implementation,
+        "SPFN.differentiable_tls": spfn.differentiable_tls, "SPFN.geometry_utils": spfn.geometry_utils,
     }
     sys.modules.update(table)
 

@@ -1,7 +1,8 @@
 """One C-ABI call (cpfn_fit_primitives, include/cpfn_b200.h) fits all four primitive types
 for every (cloud, instance slot): the fused replacement of
 ``SPFN/losses_implementation.py:255-278`` and the four ``compute_parameters`` it calls.
-No CPU or torch fallback: CPU tensors raise."""
+Under autograd (W or X requires grad) the differentiable path of ``spfn/_train.py`` is used.
+No CPU fallback: CPU tensors raise."""
 import torch
 
 from .. import _lib, cuda_ops
@@ -29,9 +30,9 @@ def fit_primitives(P, W, X):
     if not P.is_cuda:
         raise RuntimeError("CPU not supported")
     if torch.is_grad_enabled() and (W.requires_grad or X.requires_grad):
-        raise NotImplementedError(
-            "cpfn_b200.spfn: the fitter backward pass is not implemented yet; call under "
-            "torch.no_grad() (evaluation / GlobalSPFN forward)")
+        # training: CUDA moment kernels with a backward + float64 autograd algebra (spfn/_train.py)
+        from . import _train
+        return _train.compute_parameters(P, W, X, ("plane", "sphere", "cylinder", "cone"))
     B, N, _ = P.shape
     K = W.shape[2]
     P = P.detach().float().contiguous()

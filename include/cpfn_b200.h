@@ -132,6 +132,19 @@ CPFN_API int cpfn_fit_primitives(const float *P, const float *W, const float *X,
                                  int N, int K, float *out, void *workspace,
                                  size_t workspace_bytes, cpfn_stream_t stream);
 
+/* Training path of the fitters.  Raw weighted moments up to third order, fp64 accumulation:
+ *   M[b,k,f] = sum_n Wt[b,n,k] * psi_f(P[b,n], X[b,n]),  f = 0..31:
+ *   [1 | p (3) | p p^T xx,xy,xz,yy,yz,zz | p p p xxx,xxy,xxz,xyy,xyz,xzz,yyy,yyz,yzz,zzz | x (3) | x x^T (6) | x (p.x) (3)]
+ * (everything SPFN/differentiable_tls.py:200-209 and SPFN/geometry_utils.py:74-84,121-142,209-223 sum over
+ * the points, without tiling P / X K times), and the backward of that linear map:
+ *   dWt[b,n,k] = sum_f psi_f dM[b,k,f],  dX[b,n,:] = sum_k Wt[b,n,k] sum_f dM[b,k,f] dpsi_f/dx.
+ * M, dM: [B,K,32] doubles.  dWt / dX may be NULL to skip them.  P receives no gradient (as in the reference). */
+CPFN_API size_t cpfn_moments_workspace_bytes(int B, int N, int K);
+CPFN_API int cpfn_weighted_moments(const float *P, const float *X, const float *Wt, int B, int N, int K,
+                                   double *M, void *workspace, size_t workspace_bytes, cpfn_stream_t stream);
+CPFN_API int cpfn_weighted_moments_grad(const float *P, const float *X, const float *Wt, const double *dM,
+                                        int B, int N, int K, float *dWt, float *dX, cpfn_stream_t stream);
+
 /* ---------------------------------------------------------------------------
  * Fused shared-MLP chains (set abstraction, feature propagation, heads) on the
  * tcgen05 tensor cores.  Inference only: BatchNorm is folded into the weights.

@@ -140,3 +140,30 @@ def network_state(template, seed=7):
 
 def network_input(batch=2, n_points=1024, seed=51):
     return synth.shape_batch(batch, n_points, seed=seed)[0]
+
+
+def grad_case():
+    """(P, W, X) for the fitter-gradient parity: every slot is a live primitive."""
+    P, X, W, _ = synth.shape_batch(2, 1024, seed=77, k_slots=12)
+    return P, W, X
+
+
+def fitter_loss(params, W_np, torch):
+    """Scalar, sign-invariant loss over the well-posed slots of grad_case() (torch tensors in `params`):
+    linear in the sign-determinate parameters, quadratic (n n^T, c^2) in the sign-ambiguous ones."""
+    rng = np.random.default_rng(5)
+    total = 0.0
+    for key in sorted(params):
+        v = params[key]
+        mask = torch.as_tensor(fit_mask("grad", key, W_np).astype(np.float32), device=v.device)
+        if key in ("plane_normal", "cylinder_axis"):
+            G = torch.as_tensor(rng.normal(size=(3, 3)).astype(np.float32), device=v.device)
+            total = total + (mask * torch.einsum("bki,ij,bkj->bk", v, G, v)).sum()
+        elif key == "plane_center":
+            g = float(rng.normal())
+            total = total + (mask * g * v * v).sum()
+        else:
+            G = torch.as_tensor(rng.normal(size=tuple(v.shape)).astype(np.float32), device=v.device)
+            m = mask if v.dim() == 2 else mask.unsqueeze(-1)
+            total = total + (m * G * v).sum()
+    return total

@@ -52,6 +52,17 @@ def main():
     out["tls/g"] = g.numpy()
     out["tls/grad_W"] = Wt.grad.numpy()
     out["tls/grad_A"] = At.grad.numpy()
+    # gradients of a scalar loss through all four fitters (reference autograd incl. Custom_svd_v_colum)
+    P, W, X = cases.grad_case()
+    Pt = torch.from_numpy(P)
+    Wt = torch.from_numpy(W).requires_grad_(True)
+    Xt = torch.from_numpy(X).requires_grad_(True)
+    params = losses_implementation.compute_parameters(Pt, Wt, Xt)
+    loss = cases.fitter_loss(params, W, torch)
+    loss.backward()
+    out["grad/loss"] = np.float64(loss.item())
+    out["grad/dW"] = Wt.grad.numpy()
+    out["grad/dX"] = Xt.grad.numpy()
     path = os.path.join(ROOT, "tests", "golden", "ref_fitters.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes;", len(out), "arrays")

@@ -135,3 +135,82 @@ def test_fit_edge_cases(cuda_dev):
         assert all(np.isfinite(v).all() for v in got.values()) or N < 4
     assert spfn.fit.fit_primitives(torch.zeros(0, 16, 3, device=cuda_dev), torch.zeros(0, 16, 4, device=cuda_dev),
                                    torch.zeros(0, 16, 3, device=cuda_dev))["plane_center"].shape == (0, 4)
+
+
+# ---- training path (CUDA moment kernels + float64 autograd algebra) ---------------------------
+
+def test_weighted_moments_forward_and_backward(cuda_dev):
+    from cpfn_b200.spfn import _train
+    from tests.test_train_algebra_cpu import torch_moments
+    rng = np.random.default_rng(4)
+    for (B, N, K) in [(2, 1000, 12), (1, 333, 1), (3, 64, 40)]:
+        P = torch.from_numpy(rng.normal(size=(B, N, 3)).astype(np.float32)).to(cuda_dev)
+        X = torch.from_numpy(rng.normal(size=(B, N, 3)).astype(np.float32)).to(cuda_dev).requires_grad_(True)
+        W = torch.from_numpy(rng.uniform(size=(B, N, K)).astype(np.float32)).to(cuda_dev).requires_grad_(True)
+        G = torch.from_numpy(rng.normal(size=(B, K, 32))).to(cuda_dev)
+        M = _train.weighted_moments(W, P, X)
+        (M * G).sum().backward()
+        dW, dX = W.grad.clone(), X.grad.clone()
+        W.grad = None; X.grad = None
+        Mr = torch_moments(W, P, X)
+        (Mr * G).sum().backward()
+        assert float((M - Mr).abs().max() / Mr.abs().max()) < 1e-6
+        assert float((dW - W.grad).abs().max() / W.grad.abs().max()) < 1e-5
+        assert float((dX - X.grad).abs().max() / X.grad.abs().max()) < 1e-5
+
+
+def test_training_path_forward_equals_inference_and_reference_gradients(cuda_dev):
+    g = np.load(GOLDEN)
+    P, W, X = cases.grad_case()
+    t = lambda a: torch.from_numpy(a).to(cuda_dev)
+    with torch.no_grad():
+        inf = spfn.losses_implementation.compute_parameters(t(P), t(W), t(X))
+    Wt, Xt = t(W).requires_grad_(True), t(X).requires_grad_(True)
+    tr = spfn.losses_implementation.compute_parameters(t(P), Wt, Xt)
+    ref = {k: v.cpu().numpy() for k, v in inf.items()}
+    _compare({k: v.detach().cpu().numpy() for k, v in tr.items()}, ref, "grad", W, 1e-5)
+    loss = cases.fitter_loss(tr, W, torch)
+    loss.backward()
+    assert abs(loss.item() - float(g["grad/loss"])) <= 1e-4 * max(1.0, abs(float(g["grad/loss"])))
+    for name, got in (("dW", Wt.grad.cpu().numpy()), ("dX", Xt.grad.cpu().numpy())):
+        err = np.abs(got - g["grad/" + name]).max() / np.abs(g["grad/" + name]).max()
+        assert err < 2e-3, (name, err)
+
+
+def test_b3_function_api(cuda_dev):
+    """solve_weighted_tls / weighted_plane_fitting / weighted_sphere_fitting / guarded_matrix_solve_ls /
+    compute_consistent_plane_frame against the numpy oracle on the reference's self-check inputs."""
+    P, W, X = cases.fitter_cases()["selfcheck"]
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda_dev)
+    w0 = np.ascontiguousarray(W[:, :, 0])
+    x = spfn.differentiable_tls.solve_weighted_tls(t(P), t(w0)).cpu().numpy()
+    xr = ofit.solve_weighted_tls(P, w0)
+    np.testing.assert_allclose(x * np.sign(np.sum(x * xr, 1, keepdims=True)), xr, atol=2e-3)
+    g = np.load(GOLDEN)
+    A = t(P).requires_grad_(True)
+    Wt = t(w0).requires_grad_(True)
+    xx = spfn.differentiable_tls.solve_weighted_tls(A, Wt)
+    s = torch.sign((xx.detach() * t(g["tls/x"])).sum(1, keepdim=True))
+    (xx * s * t(g["tls/g"])).sum().backward()
+    for got, ref in ((Wt.grad, g["tls/grad_W"]), (A.grad, g["tls/grad_A"])):
+        err = np.abs(got.cpu().numpy() - ref).max() / np.abs(ref).max()
+        assert err < 5e-3, err
+    n, c = spfn.geometry_utils.weighted_plane_fitting(t(P), t(w0))
+    nr, cr = ofit.weighted_plane_fitting(P, w0)
+    sg = np.sign(np.sum(n.cpu().numpy() * nr, 1))
+    np.testing.assert_allclose(n.cpu().numpy() * sg[:, None], nr, atol=2e-3)
+    np.testing.assert_allclose(c.cpu().numpy() * sg, cr, atol=2e-3)
+    ce, r2 = spfn.geometry_utils.weighted_sphere_fitting(t(P), t(w0))
+    cer, r2r = ofit.weighted_sphere_fitting(P, w0)
+    np.testing.assert_allclose(ce.cpu().numpy(), cer, atol=2e-3)
+    np.testing.assert_allclose(r2.cpu().numpy(), r2r, rtol=2e-3)
+    ce2, r22 = spfn.geometry_utils.weighted_sphere_fitting(t(P[:, :, :2]), t(w0))
+    ce2r, r22r = ofit.weighted_sphere_fitting(P[:, :, :2], w0)
+    np.testing.assert_allclose(ce2.cpu().numpy(), ce2r, atol=2e-3)
+    b = (P ** 2).sum(2, keepdims=True).astype(np.float32)
+    xs = spfn.geometry_utils.guarded_matrix_solve_ls(t(P), t(b), t(w0)).cpu().numpy()
+    np.testing.assert_allclose(xs, ofit.guarded_matrix_solve_ls(P, b, w0), atol=2e-3)
+    xa, ya = spfn.geometry_utils.compute_consistent_plane_frame(t(nr))
+    xar, yar = ofit.compute_consistent_plane_frame(nr)
+    np.testing.assert_allclose(xa.cpu().numpy(), xar, atol=1e-6)
+    np.testing.assert_allclose(ya.cpu().numpy(), yar, atol=1e-6)
