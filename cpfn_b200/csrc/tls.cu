@@ -706,7 +706,7 @@ extern "C" int cpfn_weighted_moments_grad(const float *P, const float *X, const 
   cudaStream_t st = as_stream(stream);
   if (dWt) {
     const int G = imax(1, kTlsThreads / K);
-    const int CP = G * 32;
+    const int CP = G * imin(32, imax(1, kMaxCP / G));
     const size_t smem = 2u * static_cast<size_t>(CP) * sizeof(float4);
     if (smem > 48 * 1024)
       CPFN_CUDA_TRY(cudaFuncSetAttribute(moments_grad_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
