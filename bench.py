@@ -179,8 +179,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step(i):
+    use_graph = not os.environ.get("CPFN_BENCH_NO_GRAPH")
+
+    def step(i, graphed=None):
         torch.manual_seed(1000 + i)
+        if use_graph if graphed is None else graphed:
+            return eng.forward_graphed(dev_inputs[i % n_in])
         return eng.forward(dev_inputs[i % n_in])
 
     for i in range(max(3, args.warmup)):
@@ -204,13 +208,13 @@ def run_ours(args):
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     # end-to-end through the public host-buffer API (H2D + forward + fit + D2H every step)
     for i in range(2):
-        eng.run_host(host_inputs[i % n_in])
+        eng.run_host(host_inputs[i % n_in], graphed=use_graph)
     barrier()
     t0 = time.perf_counter()
     h2d = d2h = 0
     for i in range(args.steps):
         torch.manual_seed(2000 + i)
-        _, h2d, d2h = eng.run_host(host_inputs[i % n_in])
+        _, h2d, d2h = eng.run_host(host_inputs[i % n_in], graphed=use_graph)
     barrier()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
@@ -240,7 +244,7 @@ def run_ours(args):
         flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        step(i)
+        step(i, graphed=False)
         b.record()
         tot.append((a, b))
     per_op = timer.summary()
@@ -276,7 +280,8 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3-split operands, f32 accumulate (MLPs); f32 (index ops); f32 sums / f64 solves (fitters)", "data": "synthetic",
         "config": {"workload": WORKLOAD, "batch_per_gpu": B_PER_GPU, "n_points": N_POINTS, "k_slots": K_SLOTS,
                    "heads": [3, 4, K_SLOTS], "l2": "flushed between timed iterations (512 MB memset outside the event pairs)",
-                   "sharding": "clouds sharded across ranks, no data-path collective", "fused_mlp": bool(fused.available())},
+                   "sharding": "clouds sharded across ranks, no data-path collective", "fused_mlp": bool(fused.available()),
+                   "cuda_graph": bool(use_graph)},
         "e2e": {"value": total_points / (e2e_ms * 1e-3 / args.steps), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": launches, "wall_ms_per_step_incl_flush": t_wall * 1e3 / args.steps,

@@ -21,12 +21,14 @@ class GlobalSPFN:
         for p in self.model.parameters():
             p.requires_grad_(False)
         self._pin = {}
+        self._graphs = {}
 
     def load_state_dict(self, sd, strict=True):
         """Reference-layout state dict (training_SPFN.py:72-74 loads with strict=True)."""
         out = self.model.load_state_dict(sd, strict=strict)
         from . import fused
         fused.invalidate(self.model)
+        self._graphs.clear()
         return out
 
     @torch.no_grad()
@@ -72,6 +74,36 @@ class GlobalSPFN:
             out["parameters"] = L.compute_parameters(P, out["W"], out["X"], self.classes)
         return out
 
+    @torch.no_grad()
+    def forward_graphed(self, P, dropout=True, fit=True):
+        """``forward`` replayed from a CUDA graph (captured once per input shape): the ~50 kernel
+        launches of a step become one graph launch.  The returned tensors are STATIC buffers that
+        the next call overwrites; the always-on dropout still draws a fresh mask per call (torch's
+        graph-safe generator)."""
+        key = (tuple(P.shape), bool(dropout), bool(fit))
+        entry = self._graphs.get(key)
+        if entry is None:
+            static_in = P.clone()
+            cur = torch.cuda.current_stream(self.device)
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for _ in range(2):                       # warm-up: packs weights, sizes workspaces, sets kernel attributes
+                    self.forward(static_in, dropout=dropout, fit=fit)
+            cur.wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            n0 = cuda_ops.LAUNCHES
+            with torch.cuda.graph(graph):
+                out = self.forward(static_in, dropout=dropout, fit=fit)
+            entry = (graph, static_in, out, cuda_ops.LAUNCHES - n0)
+            self._graphs[key] = entry
+        graph, static_in, out, n_launch = entry
+        static_in.copy_(P, non_blocking=True)
+        graph.replay()
+        cuda_ops.count_launches(n_launch)
+        return out
+
     def _pinned(self, name, shape, dtype):
         t = self._pin.get(name)
         if t is None or t.shape != tuple(shape) or t.dtype != dtype:
@@ -80,7 +112,7 @@ class GlobalSPFN:
         return t
 
     @torch.no_grad()
-    def run_host(self, P_host, dropout=True):
+    def run_host(self, P_host, dropout=True, graphed=False):
         """P_host: CPU float32 [B,N,3] (pinned or pageable).  Copies it to the device, runs
         forward + fitters, and returns HOST tensors: the parameter dictionary, per-point
         instance labels (int32 [B,N], argmax of W), per-point type labels and unit normals --
@@ -90,7 +122,7 @@ class GlobalSPFN:
         stage = self._pinned("P", P_host.shape, torch.float32)
         stage.copy_(P_host)
         P = stage.to(self.device, non_blocking=True)
-        out = self.forward(P, dropout=dropout)
+        out = self.forward_graphed(P, dropout=dropout) if graphed else self.forward(P, dropout=dropout)
         res_dev = dict(out["parameters"])
         res_dev["instance"] = torch.argmax(out["W"], dim=2).to(torch.int32)
         res_dev["type"] = torch.argmax(out["T"], dim=2).to(torch.int32)

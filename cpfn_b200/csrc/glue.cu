@@ -73,35 +73,54 @@ gather_xyz_kernel(const float *__restrict__ xyz, const int32_t *__restrict__ idx
   out[e] = __ldg(xyz + (b * N + __ldg(idx + row)) * 3 + c);
 }
 
-// One thread per point.  heads [rows, ld]: columns [x_off, x_off+3) = normals, [w_off, w_off+K) = logits.
-// X = x / max(||x||, 1e-12) (F.normalize, p=2); W = softmax(logits).
+// One thread per point; the block's rows are staged through shared memory so that both the read of
+// heads [rows, ld] and the writes of X [rows,3] / W [rows,K] are coalesced (ld and K are odd multiples
+// of a word in practice -- 35 and 28 -- so the per-thread strided shared-memory accesses are
+// conflict-free or 4-way at worst).  X = x / max(||x||, 1e-12) (F.normalize, p=2); W = softmax(logits).
 template <int KMAX>
 __global__ void __launch_bounds__(kGlueThreads)
 spfn_post_kernel(const float *__restrict__ heads, long long rows, int ld, int x_off, int w_off, int K,
                  float *__restrict__ X, float *__restrict__ W) {
-  const long long r = static_cast<long long>(blockIdx.x) * kGlueThreads + threadIdx.x;
-  if (r >= rows) return;
-  const float *h = heads + r * ld;
-  const float x = __ldg(h + x_off), y = __ldg(h + x_off + 1), z = __ldg(h + x_off + 2);
-  const float nrm = fmaxf(sqrtf(x * x + y * y + z * z), 1e-12f);
-  X[r * 3] = x / nrm; X[r * 3 + 1] = y / nrm; X[r * 3 + 2] = z / nrm;
+  extern __shared__ float s_rows[];          // [kGlueThreads * max(ld, K)]
+  const long long r0 = static_cast<long long>(blockIdx.x) * kGlueThreads;
+  const int nr = static_cast<int>(min(static_cast<long long>(kGlueThreads), rows - r0));
+  const float *src = heads + r0 * ld;
+  for (int i = threadIdx.x; i < nr * ld; i += kGlueThreads) s_rows[i] = __ldg(src + i);
+  __syncthreads();
   float v[KMAX];
-  float mx = -INFINITY;
+  float xn = 0.f, yn = 0.f, zn = 0.f;
+  if (threadIdx.x < nr) {
+    const float *h = s_rows + threadIdx.x * ld;
+    const float x = h[x_off], y = h[x_off + 1], z = h[x_off + 2];
+    const float nrm = fmaxf(sqrtf(x * x + y * y + z * z), 1e-12f);
+    xn = x / nrm; yn = y / nrm; zn = z / nrm;
+    float mx = -INFINITY;
 #pragma unroll
-  for (int k = 0; k < KMAX; ++k) {
-    v[k] = k < K ? __ldg(h + w_off + k) : -INFINITY;
-    mx = fmaxf(mx, v[k]);
+    for (int k = 0; k < KMAX; ++k) {
+      v[k] = k < K ? h[w_off + k] : -INFINITY;
+      mx = fmaxf(mx, v[k]);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      v[k] = k < K ? expf(v[k] - mx) : 0.f;
+      sum += v[k];
+    }
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) v[k] = v[k] * inv;
   }
-  float sum = 0.f;
+  __syncthreads();
+  if (threadIdx.x < nr) {
+    float *o = s_rows + threadIdx.x * K;
 #pragma unroll
-  for (int k = 0; k < KMAX; ++k) {
-    v[k] = k < K ? expf(v[k] - mx) : 0.f;
-    sum += v[k];
+    for (int k = 0; k < KMAX; ++k)
+      if (k < K) o[k] = v[k];
+    X[(r0 + threadIdx.x) * 3] = xn; X[(r0 + threadIdx.x) * 3 + 1] = yn; X[(r0 + threadIdx.x) * 3 + 2] = zn;
   }
-  float *w = W + r * K;
-#pragma unroll
-  for (int k = 0; k < KMAX; ++k)
-    if (k < K) w[k] = v[k] / sum;
+  __syncthreads();
+  float *dst = W + r0 * K;
+  for (int i = threadIdx.x; i < nr * K; i += kGlueThreads) dst[i] = s_rows[i];
 }
 
 // out[r, co] = bias[co] + sum_k W[co, k] * x[r, k]  (fp32, one warp per output): the per-cloud
@@ -165,7 +184,14 @@ extern "C" int cpfn_spfn_post(const float *heads, long long rows, int ld, int x_
   if (rows == 0) return CPFN_OK;
   if (!heads || !X || !W) return CPFN_EINVAL;
   const unsigned grid = static_cast<unsigned>((rows + kGlueThreads - 1) / kGlueThreads);
-  if (K <= 32) spfn_post_kernel<32><<<grid, kGlueThreads, 0, as_stream(stream)>>>(heads, rows, ld, x_off, w_off, K, X, W);
-  else spfn_post_kernel<64><<<grid, kGlueThreads, 0, as_stream(stream)>>>(heads, rows, ld, x_off, w_off, K, X, W);
+  if (ld > 128) return CPFN_EINVAL;
+  const size_t smem = static_cast<size_t>(kGlueThreads) * (ld > K ? ld : K) * sizeof(float);
+  if (K <= 32) {
+    if (smem > 48 * 1024) CPFN_CUDA_TRY(cudaFuncSetAttribute(spfn_post_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    spfn_post_kernel<32><<<grid, kGlueThreads, smem, as_stream(stream)>>>(heads, rows, ld, x_off, w_off, K, X, W);
+  } else {
+    if (smem > 48 * 1024) CPFN_CUDA_TRY(cudaFuncSetAttribute(spfn_post_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    spfn_post_kernel<64><<<grid, kGlueThreads, smem, as_stream(stream)>>>(heads, rows, ld, x_off, w_off, K, X, W);
+  }
   return check_launch();
 }

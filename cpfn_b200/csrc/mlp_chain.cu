@@ -33,6 +33,7 @@
 // per-product error of ~2^-16 instead of TF32's 2^-11.  Measured end-to-end error of the
 // 14-layer GlobalSPFN forward against the fp32 oracle: ~1e-5 of the tensor scale (plain TF32:
 // 2e-3 .. 5e-3, which misses the 1e-3 tolerance of the north star).
+#include <stdlib.h>
 #include <string.h>
 
 #include <cuda_bf16.h>
@@ -798,7 +799,8 @@ int launch_chain(const cpfn_mlp_chain_t *c, cudaStream_t st) {
   // Two CTAs per SM (one's epilogue overlaps the other's MMAs) when shared memory and TMEM allow.
   int per_sm = 1;
   int nstage = static_cast<int>((max_smem - fixed) / kStageBytes);
-  if (p.tmem_cols <= 256 && fixed + 2 * kStageBytes <= max_smem / 2 - 1024) {
+  const char *force1 = getenv("CPFN_CHAIN_ONE_PER_SM");      // tuning knob: deep weight ring instead of 2 CTAs/SM
+  if (!(force1 && force1[0] == '1') && p.tmem_cols <= 256 && fixed + 2 * kStageBytes <= max_smem / 2 - 1024) {
     per_sm = 2;
     nstage = static_cast<int>((max_smem / 2 - 1024 - fixed) / kStageBytes);
   }

@@ -338,8 +338,18 @@ __device__ __forceinline__ double sym10(const double t[10], int i, int j, int k)
 __device__ __forceinline__ double sum_partials(const double *part, int b, int k, int K, int chunks,
                                                int lane) {
   const double *p = part + (static_cast<size_t>(b) * chunks * K + k) * kFP + lane;
+  // fixed summation order, eight independent loads in flight
+  const size_t stride = static_cast<size_t>(K) * kFP;
   double s = 0.0;
-  for (int c = 0; c < chunks; ++c) s += p[static_cast<size_t>(c) * K * kFP];
+  int c = 0;
+  for (; c + 8 <= chunks; c += 8) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = p[(c + u) * stride];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s += v[u];
+  }
+  for (; c < chunks; ++c) s += p[c * stride];
   return s;
 }
 

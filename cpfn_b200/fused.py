@@ -345,6 +345,18 @@ def fp_forward_pm(module, xyz1, xyz2, feats1_pm, feats2_pm):
     return out
 
 
+_ones_cache = {}
+
+
+def _ones(B, C, N, dev):
+    key = (B, C, N, dev)
+    t = _ones_cache.get(key)
+    if t is None:
+        _ones_cache.clear()
+        t = _ones_cache[key] = torch.ones(B, C, N, device=dev)
+    return t
+
+
 def _pm(t):
     return None if t is None else t.permute(0, 2, 1).contiguous()
 
@@ -400,7 +412,7 @@ def pointnet2_forward(model, P, dropout=True):
     masks = None
     if dropout:
         # the reference's always-on dropout (pn2_network.py:63): same generator, same shape, same mask
-        masks = {fc1_layer: torch.nn.functional.dropout(torch.ones(B, 128, N, device=dev), p=0.5)}
+        masks = {fc1_layer: torch.nn.functional.dropout(_ones(B, 128, N, dev), p=0.5)}
     run_chain(pc, B, N, heads, n_out, tile_cols=pick_tile(pc.dims, N, need_cloud_aligned=True, name='HEAD'), in_mode=IN_INTERP, a_src=None, a_ch=0, a_rows=N, idx=idx,
               b_src=l5, b_ch=l5.shape[2], b_rows=l5.shape[1], nn_w=w, masks=masks, out_cm={fc1_layer: output_feat})
     outs, o = [], 0

@@ -88,3 +88,22 @@ def test_run_host_end_to_end(engine, cuda_dev):
     Xn, _, Wn = onet.spfn_postprocess(ref["heads"])
     agree = float((res["instance"].numpy() == Wn.argmax(2)).mean())
     assert agree > 0.99, agree
+
+
+def test_cuda_graph_replay_matches_eager(engine, cuda_dev):
+    eng, sd = engine
+    P = torch.from_numpy(cases.network_input()).to(cuda_dev)
+    ref = eng.forward(P, dropout=False)
+    out = eng.forward_graphed(P, dropout=False)
+    for k in ("X", "W", "T"):
+        assert torch.equal(out[k], ref[k]), k
+    for k, v in ref["parameters"].items():
+        assert torch.equal(out["parameters"][k], v), k
+    P2 = torch.from_numpy(cases.network_input(seed=52)).to(cuda_dev)
+    ref2 = {k: v.clone() for k, v in eng.forward(P2, dropout=False)["parameters"].items()}
+    out2 = eng.forward_graphed(P2, dropout=False)         # replay with new data
+    for k, v in ref2.items():
+        assert torch.equal(out2["parameters"][k], v), k
+    m1 = eng.forward_graphed(P, dropout=True)["output_feat"].clone()
+    m2 = eng.forward_graphed(P, dropout=True)["output_feat"].clone()
+    assert not torch.equal(m1, m2)                         # a fresh dropout mask per replay
