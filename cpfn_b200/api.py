@@ -44,7 +44,9 @@ class GlobalSPFN:
                    "output_feat": feat, "l1_pos": l1_xyz.permute(0, 2, 1), "l2_pos": l2_xyz.permute(0, 2, 1)}
             if len(heads) == 3 and heads[0].shape[2] == 3 and heads[2].shape[2] <= 64:
                 # SPFN post-processing (Utils/training_utils.py:141-142) in one kernel
-                out["X"], out["W"] = fused.spfn_post(packed, 0, 3 + heads[1].shape[2], heads[2].shape[2])
+                nt = heads[1].shape[2]
+                out["X"], out["W"], out["instance"], out["type"] = fused.spfn_post(packed, 0, 3 + nt, heads[2].shape[2],
+                                                                                   t_off=3, n_types=nt)
             else:
                 out["X"] = torch.nn.functional.normalize(heads[0], p=2, dim=2, eps=1e-12)
                 out["W"] = torch.softmax(heads[2], dim=2)
@@ -119,15 +121,30 @@ class GlobalSPFN:
         what evaluation_globalSPFN.py:97-110 of the reference saves per shape.
         Returns (results, h2d_bytes, d2h_bytes)."""
         B, N, _ = P_host.shape
-        stage = self._pinned("P", P_host.shape, torch.float32)
-        stage.copy_(P_host)
+        if P_host.is_pinned():
+            stage = P_host
+        else:
+            stage = self._pinned("P", P_host.shape, torch.float32)
+            stage.copy_(P_host)
         P = stage.to(self.device, non_blocking=True)
         out = self.forward_graphed(P, dropout=dropout) if graphed else self.forward(P, dropout=dropout)
-        res_dev = dict(out["parameters"])
-        res_dev["instance"] = torch.argmax(out["W"], dim=2).to(torch.int32)
-        res_dev["type"] = torch.argmax(out["T"], dim=2).to(torch.int32)
-        res_dev["normals"] = out["X"]
+        params = out["parameters"]
+        res_dev = {"instance": out["instance"] if "instance" in out else torch.argmax(out["W"], dim=2).to(torch.int32),
+                   "type": out["type"] if "type" in out else torch.argmax(out["T"], dim=2).to(torch.int32),
+                   "normals": out["X"]}
+        first = next(iter(params.values()))
+        packed = first._base if first._base is not None and first._base.numel() == sum(v.numel() for v in params.values()) else None
         res, d2h = {}, 0
+        if packed is not None:                     # the ten parameter tensors are views of ONE buffer: one copy
+            hp = self._pinned("out_params", packed.shape, packed.dtype)
+            hp.copy_(packed, non_blocking=True)
+            d2h += packed.numel() * 4
+            o = 0
+            for k, v in params.items():
+                res[k] = hp[o:o + v.numel()].view(v.shape)
+                o += v.numel()
+        else:
+            res_dev.update(params)
         for k, v in res_dev.items():
             h = self._pinned("out_" + k, v.shape, v.dtype)
             h.copy_(v, non_blocking=True)

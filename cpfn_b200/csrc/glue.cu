@@ -79,8 +79,9 @@ gather_xyz_kernel(const float *__restrict__ xyz, const int32_t *__restrict__ idx
 // conflict-free or 4-way at worst).  X = x / max(||x||, 1e-12) (F.normalize, p=2); W = softmax(logits).
 template <int KMAX>
 __global__ void __launch_bounds__(kGlueThreads)
-spfn_post_kernel(const float *__restrict__ heads, long long rows, int ld, int x_off, int w_off, int K,
-                 float *__restrict__ X, float *__restrict__ W) {
+spfn_post_kernel(const float *__restrict__ heads, long long rows, int ld, int x_off, int t_off, int n_types,
+                 int w_off, int K, float *__restrict__ X, float *__restrict__ W, int32_t *__restrict__ inst,
+                 int32_t *__restrict__ type) {
   extern __shared__ float s_rows[];          // [kGlueThreads * max(ld, K)]
   const long long r0 = static_cast<long long>(blockIdx.x) * kGlueThreads;
   const int nr = static_cast<int>(min(static_cast<long long>(kGlueThreads), rows - r0));
@@ -95,10 +96,21 @@ spfn_post_kernel(const float *__restrict__ heads, long long rows, int ld, int x_
     const float nrm = fmaxf(sqrtf(x * x + y * y + z * z), 1e-12f);
     xn = x / nrm; yn = y / nrm; zn = z / nrm;
     float mx = -INFINITY;
+    int amax = 0;
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
       v[k] = k < K ? h[w_off + k] : -INFINITY;
-      mx = fmaxf(mx, v[k]);
+      if (v[k] > mx) { mx = v[k]; amax = k; }          // first maximum, like torch.argmax
+    }
+    if (inst != nullptr) inst[r0 + threadIdx.x] = amax;
+    if (type != nullptr) {
+      float tm = -INFINITY;
+      int ta = 0;
+      for (int k = 0; k < n_types; ++k) {
+        const float tv = h[t_off + k];
+        if (tv > tm) { tm = tv; ta = k; }
+      }
+      type[r0 + threadIdx.x] = ta;
     }
     float sum = 0.f;
 #pragma unroll
@@ -177,10 +189,12 @@ extern "C" int cpfn_gather_xyz(const float *xyz, const int32_t *idx, int B, int 
   return check_launch();
 }
 
-extern "C" int cpfn_spfn_post(const float *heads, long long rows, int ld, int x_off, int w_off, int K, float *X,
-                              float *W, cpfn_stream_t stream) {
+extern "C" int cpfn_spfn_post(const float *heads, long long rows, int ld, int x_off, int t_off, int n_types,
+                              int w_off, int K, float *X, float *W, int32_t *inst, int32_t *type,
+                              cpfn_stream_t stream) {
   using namespace cpfn;
-  if (rows < 0 || K <= 0 || K > 64 || ld < 3 || x_off < 0 || w_off < 0 || x_off + 3 > ld || w_off + K > ld) return CPFN_EINVAL;
+  if (rows < 0 || K <= 0 || K > 64 || ld < 3 || x_off < 0 || w_off < 0 || x_off + 3 > ld || w_off + K > ld ||
+      (type != nullptr && (t_off < 0 || n_types <= 0 || t_off + n_types > ld))) return CPFN_EINVAL;
   if (rows == 0) return CPFN_OK;
   if (!heads || !X || !W) return CPFN_EINVAL;
   const unsigned grid = static_cast<unsigned>((rows + kGlueThreads - 1) / kGlueThreads);
@@ -188,10 +202,10 @@ extern "C" int cpfn_spfn_post(const float *heads, long long rows, int ld, int x_
   const size_t smem = static_cast<size_t>(kGlueThreads) * (ld > K ? ld : K) * sizeof(float);
   if (K <= 32) {
     if (smem > 48 * 1024) CPFN_CUDA_TRY(cudaFuncSetAttribute(spfn_post_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    spfn_post_kernel<32><<<grid, kGlueThreads, smem, as_stream(stream)>>>(heads, rows, ld, x_off, w_off, K, X, W);
+    spfn_post_kernel<32><<<grid, kGlueThreads, smem, as_stream(stream)>>>(heads, rows, ld, x_off, t_off, n_types, w_off, K, X, W, inst, type);
   } else {
     if (smem > 48 * 1024) CPFN_CUDA_TRY(cudaFuncSetAttribute(spfn_post_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    spfn_post_kernel<64><<<grid, kGlueThreads, smem, as_stream(stream)>>>(heads, rows, ld, x_off, w_off, K, X, W);
+    spfn_post_kernel<64><<<grid, kGlueThreads, smem, as_stream(stream)>>>(heads, rows, ld, x_off, t_off, n_types, w_off, K, X, W, inst, type);
   }
   return check_launch();
 }

@@ -268,9 +268,7 @@ __device__ void eig_sym3(const double a[6], double lam[3], double V[3][3]) {
 
 // Right-singular vector of the smallest singular value of a symmetric matrix = eigenvector
 // of the eigenvalue smallest in magnitude (ties -> last, like the last column of V).
-__device__ void min_eigvec3(const double a[6], double n[3]) {
-  double lam[3], V[3][3];
-  eig_sym3(a, lam, V);
+__device__ void pick_min_eigvec(const double lam[3], const double V[3][3], double n[3]) {
   int m = 2;
   if (fabs(lam[1]) < fabs(lam[m])) m = 1;
   if (fabs(lam[0]) < fabs(lam[m])) m = 0;
@@ -286,15 +284,13 @@ __device__ void min_eigvec3(const double a[6], double n[3]) {
   n[0] = sg * x; n[1] = sg * y; n[2] = sg * z;
 }
 
-// guarded_matrix_solve_ls (SPFN/geometry_utils.py:121-142) on the normal equations:
-// mask = cond(AtA) < 1e5 (singular values = |eigenvalues|), solve (AtA*mask + 1e-8 I) x = Atb*mask.
-__device__ void guarded_solve3(const double a[6], const double rhs[3], double x[3]) {
-  double lam[3], V[3][3];
-  eig_sym3(a, lam, V);
+// guarded_matrix_solve_ls (SPFN/geometry_utils.py:121-142) on the normal equations, given the
+// eigenvalues of AtA: mask = cond(AtA) < 1e5 (singular values = |eigenvalues|), then
+// (AtA*mask + 1e-8 I) x = Atb*mask by cofactors in fp64.
+__device__ void guarded_solve3_eigs(const double a[6], const double rhs[3], const double lam[3], double x[3]) {
   const double s0 = fabs(lam[0]), s1 = fabs(lam[1]), s2 = fabs(lam[2]);
   const double smax = fmax(s0, fmax(s1, s2)), smin = fmin(s0, fmin(s1, s2));
   const double mask = (smax / smin < 1e5) ? 1.0 : 0.0;   // NaN / inf compare false
-  // symmetric 3x3 solve by cofactors in fp64 (cond <= 1e5 by the mask, or the ridge alone)
   const double m00 = a[0] * mask + 1e-8, m01 = a[1] * mask, m02 = a[2] * mask, m11 = a[3] * mask + 1e-8,
                m12 = a[4] * mask, m22 = a[5] * mask + 1e-8;
   const double r0 = rhs[0] * mask, r1 = rhs[1] * mask, r2 = rhs[2] * mask;
@@ -367,6 +363,10 @@ tls_solve1_kernel(const double *__restrict__ part, double *__restrict__ state, i
   __syncwarp();
   const double *m = sm[warp];
   double *st = state + static_cast<size_t>(bk) * kState;
+  // The two 3x3 eigen problems of a slot run on two lanes of the SAME branch (in lock step), not one
+  // after the other: lane 1 = cylinder axis (TLS on the normals, uncentred), lane 2 = cone apex.
+  double lam[3], V[3][3];
+  if (lane == 1 || lane == 2) eig_sym3(m + (lane == 1 ? 8 : 14), lam, V);
   if (lane == 0) {
     const double sw = m[0];
     const double denom = static_cast<double>(fmaxf(static_cast<float>(sw), 1e-10f));
@@ -381,11 +381,11 @@ tls_solve1_kernel(const double *__restrict__ part, double *__restrict__ state, i
     st[ST_M2] = m[4] / denom;
   } else if (lane == 1) {
     double n[3];
-    min_eigvec3(m + 8, n);                       // cylinder axis: TLS on the normals (uncentred)
+    pick_min_eigvec(lam, V, n);
     st[ST_CYLN] = n[0]; st[ST_CYLN + 1] = n[1]; st[ST_CYLN + 2] = n[2];
   } else if (lane == 2) {
     double apex[3];
-    guarded_solve3(m + 14, m + 20, apex);        // cone apex: rows sqrt(w') x, rhs sqrt(w') (p.x)
+    guarded_solve3_eigs(m + 14, m + 20, lam, apex);   // rows sqrt(w') x, rhs sqrt(w') (p.x)
     st[ST_APEX] = apex[0]; st[ST_APEX + 1] = apex[1]; st[ST_APEX + 2] = apex[2];
   }
 }
@@ -412,11 +412,16 @@ tls_solve2_kernel(const double *__restrict__ part, double *__restrict__ state,
         *o_ca = out + 8 * BKs, *o_cc = out + 11 * BKs, *o_cr = out + 14 * BKs,
         *o_ap = out + 15 * BKs, *o_ax = out + 18 * BKs;
 
-  // The four sub-problems of a slot are independent: lanes 0..3 take one each.
+  // The four sub-problems of a slot are independent: lanes 0..3 take one each.  The three 3x3 eigen
+  // problems (plane S, sphere 4S', cone Cx) run in lock step on lanes 0, 1, 3 in ONE branch.
+  double lam[3], V[3][3], AtA[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) AtA[i] = lane == 0 ? S[i] : (lane == 1 ? 4.0 * Sp[i] : Cx[i]);
+  if (lane != 2) eig_sym3(AtA, lam, V);
   if (lane == 0) {
     // plane: normal = TLS of the centred points, c = n . mean
     double n[3];
-    min_eigvec3(S, n);
+    pick_min_eigvec(lam, V, n);
 #pragma unroll
     for (int i = 0; i < 3; ++i) o_pn[bk * 3 + i] = static_cast<float>(n[i]);
     o_pc[bk] = static_cast<float>(n[0] * mu[0] + n[1] * mu[1] + n[2] * mu[2]);
@@ -425,7 +430,7 @@ tls_solve2_kernel(const double *__restrict__ part, double *__restrict__ state,
   if (lane == 3) {
     // cone: apex from solve1; axis = plane-fit normal of the normals (sign fixed in solve3)
     double ax[3];
-    min_eigvec3(Cx, ax);
+    pick_min_eigvec(lam, V, ax);
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       st[ST_CONEAX + i] = static_cast<double>(static_cast<float>(ax[i]));
@@ -437,16 +442,14 @@ tls_solve2_kernel(const double *__restrict__ part, double *__restrict__ state,
   if (lane == 1) {
   // sphere: AtA = 4 S', Atb = -2 m2 s1' + 2 (|mu|^2 s1' + 2 S' mu + t'),  t'_i = sum_j T'_ijj
   const double mu2 = mu[0] * mu[0] + mu[1] * mu[1] + mu[2] * mu[2];
-  double AtA[6], Atb[3], c[3];
-#pragma unroll
-  for (int i = 0; i < 6; ++i) AtA[i] = 4.0 * Sp[i];
+  double Atb[3], c[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     const double Smu = sym6(Sp, i, 0) * mu[0] + sym6(Sp, i, 1) * mu[1] + sym6(Sp, i, 2) * mu[2];
     const double t = sym10(T, i, 0, 0) + sym10(T, i, 1, 1) + sym10(T, i, 2, 2);
     Atb[i] = -2.0 * m2 * s1p[i] + 2.0 * (mu2 * s1p[i] + 2.0 * Smu + t);
   }
-  guarded_solve3(AtA, Atb, c);
+  guarded_solve3_eigs(AtA, Atb, lam, c);
   {
     const double e[3] = {mu[0] - c[0], mu[1] - c[1], mu[2] - c[2]};
     const double r2 = (S[0] + S[3] + S[5]) + 2.0 * (e[0] * s1[0] + e[1] * s1[1] + e[2] * s1[2]) +

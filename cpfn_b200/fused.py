@@ -224,16 +224,21 @@ def gather_xyz(xyz, idx):
     return out
 
 
-def spfn_post(heads, x_off, w_off, K):
-    """heads [B,N,ld] contiguous -> (X [B,N,3] unit normals, W [B,N,K] softmax memberships)."""
+def spfn_post(heads, x_off, w_off, K, t_off=None, n_types=0):
+    """heads [B,N,ld] contiguous -> (X [B,N,3] unit normals, W [B,N,K] softmax memberships,
+    instance int32 [B,N] = argmax W, type int32 [B,N] = argmax of the type logits | None)."""
     B, N, ld = heads.shape
-    X = torch.empty(B, N, 3, dtype=torch.float32, device=heads.device)
-    W = torch.empty(B, N, K, dtype=torch.float32, device=heads.device)
-    with torch.cuda.device(heads.device):
-        _lib.check(_lib.lib().cpfn_spfn_post(heads.data_ptr(), B * N, ld, x_off, w_off, K, X.data_ptr(), W.data_ptr(),
-                                             _stream(heads)), "spfn_post")
+    dev = heads.device
+    X = torch.empty(B, N, 3, dtype=torch.float32, device=dev)
+    W = torch.empty(B, N, K, dtype=torch.float32, device=dev)
+    inst = torch.empty(B, N, dtype=torch.int32, device=dev)
+    typ = torch.empty(B, N, dtype=torch.int32, device=dev) if t_off is not None else None
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().cpfn_spfn_post(heads.data_ptr(), B * N, ld, x_off, t_off or 0, n_types, w_off, K,
+                                             X.data_ptr(), W.data_ptr(), inst.data_ptr(),
+                                             typ.data_ptr() if typ is not None else None, _stream(heads)), "spfn_post")
     cuda_ops.count_launches(1)
-    return X, W
+    return X, W, inst, typ
 
 
 # ---- PointNet2 on the fused chains --------------------------------------------------------------

@@ -213,9 +213,12 @@ CPFN_API int cpfn_linear_rows(const float *x, const float *W, const float *bias,
                               int cout, int ldo, float *out, cpfn_stream_t stream);
 
 /* X = normalize(heads[:, x_off:x_off+3]), W = softmax(heads[:, w_off:w_off+K])
- * (Utils/training_utils.py:141-142).  heads [rows, ld] -> X [rows,3], W [rows,K]; K <= 64. */
-CPFN_API int cpfn_spfn_post(const float *heads, long long rows, int ld, int x_off, int w_off, int K,
-                            float *X, float *W, cpfn_stream_t stream);
+ * (Utils/training_utils.py:141-142); optionally inst = argmax_k W (hard_W_encoding's argmax) and
+ * type = argmax of the n_types type logits at t_off (what evaluation_globalSPFN.py:97-110 saves).
+ * heads [rows, ld] -> X [rows,3], W [rows,K], inst / type int32 [rows] (NULL to skip); K <= 64. */
+CPFN_API int cpfn_spfn_post(const float *heads, long long rows, int ld, int x_off, int t_off, int n_types,
+                            int w_off, int K, float *X, float *W, int32_t *inst, int32_t *type,
+                            cpfn_stream_t stream);
 
 #ifdef __cplusplus
 }

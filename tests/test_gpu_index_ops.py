@@ -208,7 +208,9 @@ def test_three_nn_weights_and_gather_xyz_and_post(cuda_dev, oracle_ops):
     g = fused.gather_xyz(_t(u, cuda_dev), _t(fi, cuda_dev)).cpu().numpy()
     np.testing.assert_array_equal(g, np.take_along_axis(u, fi.astype(np.int64)[:, :, None], axis=1))
     h = rng.normal(size=(2, 333, 35)).astype(np.float32) * 3
-    X, W = fused.spfn_post(_t(h, cuda_dev), 0, 7, 28)
+    X, W, inst, typ = fused.spfn_post(_t(h, cuda_dev), 0, 7, 28, t_off=3, n_types=4)
+    np.testing.assert_array_equal(inst.cpu().numpy(), h[:, :, 7:].argmax(2))
+    np.testing.assert_array_equal(typ.cpu().numpy(), h[:, :, 3:7].argmax(2))
     ht = torch.from_numpy(h)
     np.testing.assert_allclose(X.cpu().numpy(), torch.nn.functional.normalize(ht[:, :, :3], dim=2).numpy(), rtol=1e-6, atol=1e-7)
     np.testing.assert_allclose(W.cpu().numpy(), torch.softmax(ht[:, :, 7:], dim=2).numpy(), rtol=2e-6, atol=1e-9)
