@@ -48,7 +48,7 @@ constexpr int kWorkers = 256;
 constexpr int kStageBytes = 16384;   // one weight block: 128 rows x 128 B (64 bf16)
 constexpr int kMaxLayers = CPFN_MLP_MAX_LAYERS;
 constexpr int kMaxStages = 8;
-constexpr int kMiscBytes = 4096;     // barriers, TMEM slot, per-row loader scratch
+constexpr int kMiscBytes = 8192;     // barriers, TMEM slot, per-row loader scratch
 
 struct LayerP {
   int cin_atoms, ksteps, cout_chunks, cout, relu, bias_per_cloud, next_k16;
@@ -106,7 +106,6 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t *slot, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -199,9 +198,9 @@ __device__ __forceinline__ void store_quad(uint32_t buf, int row, int c4, float4
 // Phase A: one thread per row resolves the row's source indices (one dependent-load chain for
 // the whole tile) and writes the 3 recentred coordinates / the zero padding.  Phase B: one warp
 // per row copies (or interpolates) the feature rows, 8 rows in flight.
-template <int NT>
+template <int NT, int NW>
 __device__ void load_tile(const ChainP &p, uint32_t buf, long long col0, int w8, int lane, int *s_arow,
-                          int *s_brow, float *s_w) {
+                          int *s_brow, float *s_w, int bar_id) {
   const int t = w8 * 32 + lane;
   const int cin = p.a_ch + (p.in_mode == CPFN_MLP_IN_GROUP ? 3 : (p.in_mode == CPFN_MLP_IN_INTERP ? p.b_ch : 0));
   const int k16 = p.L[0].ksteps * 16;
@@ -232,14 +231,14 @@ __device__ void load_tile(const ChainP &p, uint32_t buf, long long col0, int w8,
     s_arow[t] = valid ? arow : -1;
     for (int ch = pad_from; ch < k16; ++ch) store_scalar<NT>(buf, t, ch, 0.f);   // K padding must be finite zeros
   }
-  worker_bar();
+  asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(NW * 32) : "memory");
   constexpr int RB = 8;
   const int nA4 = p.a_ch >> 2;
   if (nA4 > 0) {
-    for (int r0 = w8; r0 < NT; r0 += 8 * RB) {
+    for (int r0 = w8; r0 < NT; r0 += NW * RB) {
       int arow[RB];
 #pragma unroll
-      for (int u = 0; u < RB; ++u) arow[u] = (r0 + 8 * u < NT) ? s_arow[r0 + 8 * u] : -1;
+      for (int u = 0; u < RB; ++u) arow[u] = (r0 + NW * u < NT) ? s_arow[r0 + NW * u] : -1;
       for (int c4 = lane; c4 < nA4; c4 += 32) {
         float4 v[RB];
 #pragma unroll
@@ -248,7 +247,7 @@ __device__ void load_tile(const ChainP &p, uint32_t buf, long long col0, int w8,
                               : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int u = 0; u < RB; ++u)
-          if (r0 + 8 * u < NT) store_quad<NT>(buf, r0 + 8 * u, c4, v[u]);
+          if (r0 + NW * u < NT) store_quad<NT>(buf, r0 + NW * u, c4, v[u]);
       }
     }
   }
@@ -256,14 +255,14 @@ __device__ void load_tile(const ChainP &p, uint32_t buf, long long col0, int w8,
     // three_weighted_sum (interpolate_gpu.cu:98-99 as compiled): fma(p3,w3, fma(p1,w1, p2*w2))
     constexpr int RI = 4;
     const int nB4 = p.b_ch >> 2, a4 = p.a_ch >> 2;
-    for (int r0 = w8; r0 < NT; r0 += 8 * RI) {
+    for (int r0 = w8; r0 < NT; r0 += NW * RI) {
       for (int c4 = lane; c4 < nB4; c4 += 32) {
         float4 f[RI][3];
         float w[RI][3];
         bool ok[RI];
 #pragma unroll
         for (int u = 0; u < RI; ++u) {
-          const int r = r0 + 8 * u;
+          const int r = r0 + NW * u;
           ok[u] = r < NT && s_arow[r < NT ? r : 0] >= 0;
 #pragma unroll
           for (int q = 0; q < 3; ++q) {
@@ -274,7 +273,7 @@ __device__ void load_tile(const ChainP &p, uint32_t buf, long long col0, int w8,
         }
 #pragma unroll
         for (int u = 0; u < RI; ++u) {
-          const int r = r0 + 8 * u;
+          const int r = r0 + NW * u;
           if (r >= NT) continue;
           float4 o;
           o.x = __fmaf_rn(f[u][2].x, w[u][2], __fmaf_rn(f[u][0].x, w[u][0], __fmul_rn(f[u][1].x, w[u][1])));
@@ -398,7 +397,7 @@ mlp_chain_kernel(const __grid_constant__ ChainP p) {
       const long long col0 = static_cast<long long>(tile) * NT;
       const long long cloud = col0 / p.cols_per_cloud;
       const long long n_in_cloud = col0 - cloud * p.cols_per_cloud;
-      load_tile<NT>(p, smem_u32(act0), col0, w8, lane, s_arow, s_brow, s_w);
+      load_tile<NT, 8>(p, smem_u32(act0), col0, w8, lane, s_arow, s_brow, s_w, 1);
       fence_proxy_async();
       mbar_arrive(act_ready);
       for (int l = 0; l < p.n_layers; ++l) {
@@ -510,8 +509,11 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// Single-tile form of the points-as-M kernel (8 epilogue warps, each lane quarter's two warps share a
+// chunk's channels): used when one 128-column tile per CTA lets two CTAs share an SM but two sub-tiles
+// would not (the FP3 + fc1 + heads chain: 64 KB of activations per tile).
 __global__ void __launch_bounds__(kChainThreads, 2)
-mlp_chain_pm_kernel(const __grid_constant__ ChainP p) {
+mlp_chain_pm1_kernel(const __grid_constant__ ChainP p) {
   constexpr int NT = 128;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -613,7 +615,7 @@ mlp_chain_pm_kernel(const __grid_constant__ ChainP p) {
       const bool row_ok = col < p.cols;
       const long long cloud = col0 / p.cols_per_cloud;
       const long long n_in_cloud = col0 - cloud * p.cols_per_cloud;
-      load_tile<NT>(p, smem_u32(act0), col0, w8, lane, s_arow, s_brow, s_w);
+      load_tile<NT, 8>(p, smem_u32(act0), col0, w8, lane, s_arow, s_brow, s_w, 1);
       fence_proxy_async();
       mbar_arrive(act_ready);
       for (int l = 0; l < p.n_layers; ++l) {
@@ -714,6 +716,213 @@ mlp_chain_pm_kernel(const __grid_constant__ ChainP p) {
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
+// Two sub-tiles of 128 columns per CTA: worker group g (4 warps, thread = point) owns sub-tile g from
+// its gather to its last epilogue, the MMA thread alternates between the two, so the tensor pipe works
+// on one sub-tile while the other is in its epilogue.
+__global__ void __launch_bounds__(kChainThreads, 2)
+mlp_chain_pm_kernel(const __grid_constant__ ChainP p) {
+  constexpr int NT = 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t *ring = smem;
+  uint8_t *act = ring + p.nstage * kStageBytes;                       // [2][act_bytes0]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(act + 2 * p.act_bytes0);
+  uint64_t *full = bars, *empty = bars + kMaxStages, *act_ready = bars + 2 * kMaxStages,   // [2]
+           *acc_full = bars + 2 * kMaxStages + 2;                                          // [2]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kMaxStages + 4);
+  int *s_scratch = reinterpret_cast<int *>(bars + 32);                // per group: arow[128], brow[384], w[384]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.nstage; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int g = 0; g < 2; ++g) { mbar_init(act_ready + g, 128); mbar_init(acc_full + g, 1); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int sub_cols = p.tmem_cols / 2;                               // TMEM columns of one sub-tile
+  const int n_pairs = (p.n_tiles + 1) / 2;
+
+  if (warp == 0) {
+    // ===== weight producer: layer by layer, once per valid sub-tile =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+        const int nsub = (2 * pair + 1 < p.n_tiles) ? 2 : 1;
+        int blk0 = 0;
+        for (int l = 0; l < p.n_layers; ++l) {
+          const int nblk = p.L[l].cout_chunks * p.L[l].cin_atoms * 2;
+          for (int g = 0; g < nsub; ++g)
+            for (int blk = 0; blk < nblk; ++blk) {
+              mbar_wait(empty + stage, phase ^ 1);
+              mbar_arrive_expect_tx(full + stage, kStageBytes);
+              bulk_g2s(ring + stage * kStageBytes, p.weights + static_cast<size_t>(blk0 + blk) * kStageBytes,
+                       kStageBytes, full + stage);
+              if (++stage == p.nstage) { stage = 0; phase ^= 1; }
+            }
+          blk0 += nblk;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(128 >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0, act_phase[2] = {0, 0};
+      for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+        const int nsub = (2 * pair + 1 < p.n_tiles) ? 2 : 1;
+        for (int l = 0; l < p.n_layers; ++l) {
+          const LayerP &L = p.L[l];
+          const int cout16 = (L.cout + 15) & ~15;
+          for (int g = 0; g < nsub; ++g) {
+            const uint32_t in_buf = smem_u32(act + g * p.act_bytes0);
+            mbar_wait(act_ready + g, act_phase[g]);
+            act_phase[g] ^= 1;
+            tc_fence_after();
+            for (int m = 0; m < L.cout_chunks; ++m) {
+              const uint32_t d_tmem = tmem_base + g * sub_cols + m * 128;
+              const int nch = min(128, cout16 - m * 128);
+              const uint32_t idesc = idesc0 | (static_cast<uint32_t>(nch >> 3) << 17);
+              for (int j = 0; j < L.cin_atoms; ++j) {
+                const int ks = min(4, L.ksteps - 4 * j);
+                const uint32_t a_hi = in_buf + part_base<NT>(j, 0), a_lo = a_hi + NT * 128;
+                mbar_wait(full + stage, phase);            // W_hi block
+                tc_fence_after();
+                uint32_t w_base = smem_u32(ring + stage * kStageBytes);
+                for (int kk = 0; kk < ks; ++kk) {
+                  umma_bf16(d_tmem, make_desc(a_hi + kk * 32), make_desc(w_base + kk * 32), idesc, (j | kk) != 0 ? 1u : 0u);
+                  umma_bf16(d_tmem, make_desc(a_lo + kk * 32), make_desc(w_base + kk * 32), idesc, 1u);
+                }
+                umma_commit(empty + stage);
+                if (++stage == p.nstage) { stage = 0; phase ^= 1; }
+                mbar_wait(full + stage, phase);            // W_lo block
+                tc_fence_after();
+                w_base = smem_u32(ring + stage * kStageBytes);
+                for (int kk = 0; kk < ks; ++kk)
+                  umma_bf16(d_tmem, make_desc(a_hi + kk * 32), make_desc(w_base + kk * 32), idesc, 1u);
+                umma_commit(empty + stage);
+                if (++stage == p.nstage) { stage = 0; phase ^= 1; }
+              }
+            }
+            umma_commit(acc_full + g);
+          }
+        }
+      }
+    }
+  } else {
+    const int g = (warp - 2) >> 2;                    // worker group = sub-tile
+    const int w4 = (warp - 2) & 3;
+    const int wq = warp & 3;                          // TMEM lane quarter = rows wq*32 .. wq*32+31 of the sub-tile
+    const int row = wq * 32 + lane;
+    const uint32_t row_base = static_cast<uint32_t>((row >> 3) * 1024 + (row & 7) * 128);
+    const int r7 = row & 7;
+    const uint32_t my_act = smem_u32(act + g * p.act_bytes0);
+    int *s_arow = s_scratch + g * 896, *s_brow = s_arow + 128;
+    float *s_w = reinterpret_cast<float *>(s_brow + 384);
+    uint32_t acc_phase = 0;
+    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      const int tile = 2 * pair + g;
+      if (tile >= p.n_tiles) continue;
+      const long long col0 = static_cast<long long>(tile) * NT;
+      const long long col = col0 + row;
+      const bool row_ok = col < p.cols;
+      const long long cloud = col0 / p.cols_per_cloud;
+      const long long n_in_cloud = col0 - cloud * p.cols_per_cloud;
+      load_tile<NT, 4>(p, my_act, col0, w4, lane, s_arow, s_brow, s_w, 1 + g);
+      fence_proxy_async();
+      mbar_arrive(act_ready + g);
+      for (int l = 0; l < p.n_layers; ++l) {
+        const LayerP &L = p.L[l];
+        const bool last = (l == p.n_layers - 1);
+        const int cout_pad = L.cout_chunks * 128, cout16 = (L.cout + 15) & ~15;
+        const bool slow = (L.mask != nullptr) || (L.out_cm != nullptr);
+        const float *bias_base = L.bias + (L.bias_per_cloud ? cloud * cout_pad : 0);
+        mbar_wait(acc_full + g, acc_phase);
+        acc_phase ^= 1;
+        tc_fence_after();
+#pragma unroll 1
+        for (int ch0 = 0; ch0 < cout16; ch0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + g * sub_cols + ch0, r);
+          float v[16];
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bias_base + ch0) + i4);
+            v[i4 * 4] = __uint_as_float(r[i4 * 4]) + b4.x;
+            v[i4 * 4 + 1] = __uint_as_float(r[i4 * 4 + 1]) + b4.y;
+            v[i4 * 4 + 2] = __uint_as_float(r[i4 * 4 + 2]) + b4.z;
+            v[i4 * 4 + 3] = __uint_as_float(r[i4 * 4 + 3]) + b4.w;
+          }
+          if (L.relu) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          if (slow && row_ok) {                    // dropout mask / channel-major copy: coalesced over the warp
+            const size_t o0 = (static_cast<size_t>(cloud) * L.cout + ch0) * p.cols_per_cloud + n_in_cloud + row;
+            const size_t cs = static_cast<size_t>(p.cols_per_cloud);
+            if (L.mask != nullptr) {
+              float mk[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) mk[i] = (ch0 + i < L.cout) ? __ldg(L.mask + o0 + i * cs) : 1.f;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] *= mk[i];
+            }
+            if (L.out_cm != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (ch0 + i < L.cout) L.out_cm[o0 + i * cs] = v[i];
+            }
+          }
+          if (!last) {
+            if (ch0 < L.next_k16) {
+              uint32_t H[8], Lo[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) split2(v[2 * i], v[2 * i + 1], H[i], Lo[i]);
+              const uint32_t base = my_act + part_base<NT>(ch0 >> 6, 0) + row_base;
+              const int c8 = (ch0 & 63) >> 3;
+              const uint32_t a0 = base + (((c8) ^ r7) << 4), a1 = base + (((c8 + 1) ^ r7) << 4);
+              st_shared_v4(a0, H[0], H[1], H[2], H[3]);
+              st_shared_v4(a1, H[4], H[5], H[6], H[7]);
+              st_shared_v4(a0 + NT * 128, Lo[0], Lo[1], Lo[2], Lo[3]);
+              st_shared_v4(a1 + NT * 128, Lo[4], Lo[5], Lo[6], Lo[7]);
+            }
+          } else if (p.out_mode == CPFN_MLP_OUT_ROWS) {
+            if (row_ok) {
+              float *o = p.out + col * p.ldo + ch0;
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (ch0 + i < L.cout) o[i] = v[i];
+            }
+          } else {
+            // max over the warp's 32 rows: one REDUX per channel (post-ReLU floats order like uint32)
+            uint32_t mine = 0u;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const uint32_t u = __reduce_max_sync(0xffffffffu, row_ok ? __float_as_uint(v[i]) : 0u);
+              if (lane == i) mine = u;
+            }
+            if (lane < 16 && ch0 + lane < L.cout && col0 + wq * 32 < p.cols)
+              atomicMax(reinterpret_cast<unsigned int *>(p.out) + ((col0 + wq * 32) / p.pool_g) * p.ldo + ch0 + lane, mine);
+          }
+        }
+        tc_fence_before();
+        if (!last) {
+          fence_proxy_async();
+          mbar_arrive(act_ready + g);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
 int pow2_at_least(int x) {
   int p = 32;
   while (p < x) p <<= 1;
@@ -786,15 +995,23 @@ int launch_chain(const cpfn_mlp_chain_t *c, cudaStream_t st) {
   p.split_cout = (c->split_cout && NT != 128) ? 1 : 0;
   if (c->split_cout && (c->n_layers != 1 || NT == 128)) return CPFN_EINVAL;
   if (p.split_cout) max_chunks = 1;
-  p.tmem_cols = NT == 128 ? pow2_at_least(128 * (max_chunks < 4 ? max_chunks : 4))
+  if (NT == 128 && max_chunks > 2) return CPFN_EINVAL;   // <= 256 TMEM columns per (sub-)tile
+  // 128-column tiles: two sub-tiles per CTA (ping-pong) when that still lets two CTAs share an SM,
+  // else one tile per CTA if THAT lets two CTAs share an SM, else two sub-tiles on one CTA per SM.
+  const size_t max_smem = 227 * 1024;
+  const size_t overhead = 1024 /*align*/ + kMiscBytes + 2 * kStageBytes;
+  bool two_sub = true;
+  if (NT == 128 && 2 * act_need[0] + overhead > max_smem / 2 - 1024 && act_need[0] + overhead <= max_smem / 2 - 1024 &&
+      pow2_at_least(128 * max_chunks) <= 256)
+    two_sub = false;
+  p.tmem_cols = NT == 128 ? (two_sub ? 2 : 1) * pow2_at_least(128 * max_chunks)
                           : pow2_at_least(NT * (max_chunks < 512 / NT ? max_chunks : 512 / NT));
   p.act_bytes0 = static_cast<int>(act_need[0]);
   p.act_bytes1 = 0;
   // the epilogue writes a layer's output over its input, so every non-final layer must fit one TMEM wave
   for (int l = 0; l + 1 < c->n_layers; ++l)
-    if (p.L[l].cout_chunks * (NT == 128 ? 128 : NT) > p.tmem_cols) return CPFN_EINVAL;
-  const size_t fixed = act_need[0] + act_need[1] + 1024 /*align*/ + kMiscBytes;
-  const size_t max_smem = 227 * 1024;
+    if (NT != 128 && p.L[l].cout_chunks * NT > p.tmem_cols) return CPFN_EINVAL;
+  const size_t fixed = act_need[0] * ((NT == 128 && two_sub) ? 2 : 1) + 1024 /*align*/ + kMiscBytes;
   if (fixed + 2 * kStageBytes > max_smem) return CPFN_EINVAL;
   // Two CTAs per SM (one's epilogue overlaps the other's MMAs) when shared memory and TMEM allow.
   int per_sm = 1;
@@ -809,10 +1026,11 @@ int launch_chain(const cpfn_mlp_chain_t *c, cudaStream_t st) {
   p.nstage = nstage;
   const size_t smem = fixed + static_cast<size_t>(nstage) * kStageBytes;
   void (*kern)(ChainP) = mlp_chain_kernel<NT>;
-  if (NT == 128) kern = mlp_chain_pm_kernel;
+  if (NT == 128) kern = two_sub ? mlp_chain_pm_kernel : mlp_chain_pm1_kernel;
   CPFN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const int sms = sm_count() > 0 ? sm_count() : 148;
-  const int grid = p.n_tiles < per_sm * sms ? p.n_tiles : per_sm * sms;
+  const int units = (NT == 128 && two_sub) ? (p.n_tiles + 1) / 2 : p.n_tiles;   // the ping-pong kernel takes tile pairs
+  const int grid = units < per_sm * sms ? units : per_sm * sms;
   if (grid <= 0) return CPFN_OK;
   if (atomic_pool)
     CPFN_CUDA_TRY(cudaMemsetAsync(c->out, 0, sizeof(float) * static_cast<size_t>(p.cols / c->pool_g) * c->ldo, st));

@@ -145,10 +145,14 @@ def _pick_tile(dims, cols_per_cloud, need_cloud_aligned=False, prefer=128):
         if need_cloud_aligned and cols_per_cloud % tile:
             continue
         need = max((cin + 63) // 64 * 2 * tile * 128 for cin, _, _ in dims)   # one in-place activation buffer
-        wave = 4 if tile == 128 else 512 // tile
-        if any((cout + 127) // 128 > wave for _, cout, _ in dims[:-1]):
+        if tile == 128:
+            # points-as-M kernel: two 128-column sub-tiles per CTA, <= 256 TMEM columns each
+            if any((cout + 127) // 128 > 2 for _, cout, _ in dims):
+                continue
+            need *= 2
+        elif any((cout + 127) // 128 > 512 // tile for _, cout, _ in dims[:-1]):
             continue
-        if need + 1024 + 4096 + 3 * 16384 <= 227 * 1024:
+        if need + 1024 + 8192 + 3 * 16384 <= 227 * 1024:
             return tile
     raise RuntimeError("cpfn_b200.fused: chain does not fit shared memory: %r" % (dims,))
 

@@ -57,7 +57,7 @@ def test_dense_rows(cuda_dev, dims, tile):
     assert _rel(out, ref) < TOL, _rel(out, ref)
 
 
-@pytest.mark.parametrize("feat_ch,K,tile", [(0, 64, 128), (128, 64, 128), (128, 32, 64), (256, 128, 32)])
+@pytest.mark.parametrize("feat_ch,K,tile", [(0, 64, 128), (64, 64, 128), (128, 64, 64), (128, 32, 64), (256, 128, 32)])
 def test_group_and_pool(cuda_dev, feat_ch, K, tile):
     rng = np.random.default_rng(feat_ch + K)
     B, N, S = 2, 500, 24
