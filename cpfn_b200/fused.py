@@ -273,7 +273,15 @@ def _sa_chain(module, device):
     return pc
 
 
-def sa_forward_pm(module, xyz, feats_pm):
+def sa_indices(module, xyz):
+    """FPS -> centroid gather -> ball query of a (non group_all) SA layer: (new_xyz [B,S,3], group_idx
+    int32 [B,S,K]).  Depends on positions only, so it can run ahead of the previous layer's MLP."""
+    fps_idx = cuda_ops.farthest_point_sampling(xyz, module.num_points)
+    new_xyz = gather_xyz(xyz, fps_idx)
+    return new_xyz, cuda_ops.ball_query(new_xyz, xyz, module.radius_list[0], module.num_samples_list[0])
+
+
+def sa_forward_pm(module, xyz, feats_pm, indices=None):
     """Point-major set abstraction.  xyz [B,N,3], feats_pm [B,N,D] | None ->
     (new_xyz [B,S,3] | None, new_feats_pm [B,S,D'])."""
     assert len(module.radius_list) == 1, "multi-scale grouping: use the per-op path"
@@ -294,9 +302,9 @@ def sa_forward_pm(module, xyz, feats_pm):
             run_chain(pc, B, N, out, cout, tile_cols=tile, out_mode=OUT_POOL, pool_g=N, **first)
         return None, out
     S, K = module.num_points, module.num_samples_list[0]
-    fps_idx = cuda_ops.farthest_point_sampling(xyz, S)
-    new_xyz = gather_xyz(xyz, fps_idx)
-    group_idx = cuda_ops.ball_query(new_xyz, xyz, module.radius_list[0], K)
+    if indices is None:
+        indices = sa_indices(module, xyz)
+    new_xyz, group_idx = indices
     out = torch.empty(B, S, cout, dtype=torch.float32, device=dev)
     run_chain(pc, B, S * K, out, cout, tile_cols=pick_tile(pc.dims, S * K, name=('SA1' if D == 0 else 'SA2'), prefer=(128 if D == 0 else 64)), in_mode=IN_GROUP, a_src=feats_pm, a_ch=D, a_rows=N,
               idx=group_idx, xyz=xyz, centers=new_xyz, group_k=K, out_mode=OUT_POOL, pool_g=K)
@@ -323,7 +331,7 @@ def _fp_chain(module, device, split=None):
     return pc
 
 
-def fp_forward_pm(module, xyz1, xyz2, feats1_pm, feats2_pm):
+def fp_forward_pm(module, xyz1, xyz2, feats1_pm, feats2_pm, nn=None):
     """Point-major feature propagation.  xyz1 [B,N,3], xyz2 [B,S,3] | None, feats1_pm [B,N,D1] | None,
     feats2_pm [B,S,D2] -> [B,N,D']."""
     B, N, _ = xyz1.shape
@@ -347,7 +355,7 @@ def fp_forward_pm(module, xyz1, xyz2, feats1_pm, feats2_pm):
                       bias_per_cloud=(0,), **first)
         return out
     pc, _ = _fp_chain(module, dev)
-    w, idx = three_nn_weights(xyz1, xyz2)
+    w, idx = nn if nn is not None else three_nn_weights(xyz1, xyz2)
     out = torch.empty(B, N, pc.dims[-1][1], dtype=torch.float32, device=dev)
     run_chain(pc, B, N, out, out.shape[2], tile_cols=pick_tile(pc.dims, N), in_mode=IN_INTERP, a_src=feats1_pm, a_ch=D1, a_rows=N,
               idx=idx, b_src=feats2_pm, b_ch=feats2_pm.shape[2], b_rows=feats2_pm.shape[1], nn_w=w)
@@ -355,6 +363,14 @@ def fp_forward_pm(module, xyz1, xyz2, feats1_pm, feats2_pm):
 
 
 _ones_cache = {}
+_side_streams = {}
+
+
+def _side_stream(dev):
+    key = (dev.type, dev.index)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=dev)
+    return _side_streams[key]
 
 
 def _ones(B, C, N, dev):
@@ -407,21 +423,38 @@ def pointnet2_forward(model, P, dropout=True):
     P = P.float().contiguous()
     B, N, _ = P.shape
     dev = P.device
-    l1_xyz, l1 = sa_forward_pm(model.sa1, P, None)
-    l2_xyz, l2 = sa_forward_pm(model.sa2, l1_xyz, l1)
+    # Everything that depends on positions only (SA2's sampling / ball query, the 3-NN weights of FP2 and
+    # FP3) runs on a side stream, concurrently with SA1's ball query and MLP chain on the main stream.
+    main = torch.cuda.current_stream(dev)
+    side = _side_stream(dev)
+    idx1 = sa_indices(model.sa1, P)
+    l1_xyz = idx1[0]
+    fork = torch.cuda.Event()
+    fork.record(main)
+    with torch.cuda.stream(side):
+        side.wait_event(fork)
+        idx2 = sa_indices(model.sa2, l1_xyz)
+        nn3 = three_nn_weights(P, l1_xyz)
+        nn2 = three_nn_weights(l1_xyz, idx2[0])
+        # the reference's always-on dropout (pn2_network.py:63): same generator, same shape, same mask
+        mask = torch.nn.functional.dropout(_ones(B, 128, N, dev), p=0.5) if dropout else None
+        join = torch.cuda.Event()
+        join.record(side)
+    _, l1 = sa_forward_pm(model.sa1, P, None, indices=idx1)
+    main.wait_event(join)
+    for t in (*idx2, *nn3, *nn2) + ((mask,) if mask is not None else ()):
+        t.record_stream(main)
+    l2_xyz, l2 = sa_forward_pm(model.sa2, l1_xyz, l1, indices=idx2)
     _, l3 = sa_forward_pm(model.sa3, l2_xyz, l2)
     l4 = fp_forward_pm(model.sfp1, l2_xyz, None, l2, l3)
-    l5 = fp_forward_pm(model.sfp2, l1_xyz, l2_xyz, l1, l4)
+    l5 = fp_forward_pm(model.sfp2, l1_xyz, l2_xyz, l1, l4, nn=nn2)
     pc, head_sizes = _head_chain(model, dev)
     n_out = sum(head_sizes)
-    w, idx = three_nn_weights(P, l1_xyz)
+    w, idx = nn3
     heads = torch.empty(B, N, n_out, dtype=torch.float32, device=dev)
     output_feat = torch.empty(B, 128, N, dtype=torch.float32, device=dev)
     fc1_layer = len(pc.dims) - 2
-    masks = None
-    if dropout:
-        # the reference's always-on dropout (pn2_network.py:63): same generator, same shape, same mask
-        masks = {fc1_layer: torch.nn.functional.dropout(_ones(B, 128, N, dev), p=0.5)}
+    masks = {fc1_layer: mask} if mask is not None else None
     run_chain(pc, B, N, heads, n_out, tile_cols=pick_tile(pc.dims, N, need_cloud_aligned=True, name='HEAD'), in_mode=IN_INTERP, a_src=None, a_ch=0, a_rows=N, idx=idx,
               b_src=l5, b_ch=l5.shape[2], b_rows=l5.shape[1], nn_w=w, masks=masks, out_cm={fc1_layer: output_feat})
     outs, o = [], 0
