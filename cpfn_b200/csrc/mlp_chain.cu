@@ -71,6 +71,7 @@ struct ChainP {
   const float *xyz, *centers; int group_k;
   const float *b_src; int b_ch, b_rows; const float *nn_w;
   int out_mode; float *out; int ldo, pool_g;
+  const float *l0_w, *l0_b; int l0_cout;   // GROUP mode without features: first layer (3 -> l0_cout) on CUDA cores
   int act_bytes0, act_bytes1, nstage, tmem_cols;
 };
 
@@ -202,7 +203,8 @@ template <int NT, int NW>
 __device__ void load_tile(const ChainP &p, uint32_t buf, long long col0, int w8, int lane, int *s_arow,
                           int *s_brow, float *s_w, int bar_id) {
   const int t = w8 * 32 + lane;
-  const int cin = p.a_ch + (p.in_mode == CPFN_MLP_IN_GROUP ? 3 : (p.in_mode == CPFN_MLP_IN_INTERP ? p.b_ch : 0));
+  const int cin = p.l0_w != nullptr ? p.l0_cout
+                                     : p.a_ch + (p.in_mode == CPFN_MLP_IN_GROUP ? 3 : (p.in_mode == CPFN_MLP_IN_INTERP ? p.b_ch : 0));
   const int k16 = p.L[0].ksteps * 16;
   if (t < NT) {
     const long long col = col0 + t;
@@ -216,10 +218,28 @@ __device__ void load_tile(const ChainP &p, uint32_t buf, long long col0, int w8,
       // recentred position (pointset_abstraction.py:62-63): xyz[idx] - centre
       const float *a = p.xyz + static_cast<long long>(arow) * 3;
       const float *ce = p.centers + (c / p.group_k) * 3;
+      float d3[3];
 #pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        const float d = valid ? __fsub_rn(__ldg(a + q), __ldg(ce + q)) : 0.f;
-        store_scalar<NT>(buf, t, p.a_ch + q, d);
+      for (int q = 0; q < 3; ++q) d3[q] = valid ? __fsub_rn(__ldg(a + q), __ldg(ce + q)) : 0.f;
+      if (p.l0_w != nullptr) {
+        // first shared-MLP layer (3 input channels) in fp32 on the CUDA cores: relu(W0 d + b0); a K = 3
+        // contraction would waste 13/16 of a tensor-core pass and a whole MMA / epilogue round trip
+        for (int c4 = 0; c4 < (p.l0_cout >> 2); ++c4) {
+          // 4 channels = 12 consecutive weights (three 16-byte loads, identical for the whole warp) + 4 biases
+          const float4 wa = __ldg(reinterpret_cast<const float4 *>(p.l0_w) + c4 * 3);
+          const float4 wb = __ldg(reinterpret_cast<const float4 *>(p.l0_w) + c4 * 3 + 1);
+          const float4 wc = __ldg(reinterpret_cast<const float4 *>(p.l0_w) + c4 * 3 + 2);
+          const float4 bb = __ldg(reinterpret_cast<const float4 *>(p.l0_b) + c4);
+          float o[4];
+          o[0] = fmaxf(fmaf(wa.z, d3[2], fmaf(wa.y, d3[1], fmaf(wa.x, d3[0], bb.x))), 0.f);
+          o[1] = fmaxf(fmaf(wb.y, d3[2], fmaf(wb.x, d3[1], fmaf(wa.w, d3[0], bb.y))), 0.f);
+          o[2] = fmaxf(fmaf(wc.x, d3[2], fmaf(wb.w, d3[1], fmaf(wb.z, d3[0], bb.z))), 0.f);
+          o[3] = fmaxf(fmaf(wc.w, d3[2], fmaf(wc.z, d3[1], fmaf(wc.y, d3[0], bb.w))), 0.f);
+          store_quad<NT>(buf, t, c4, valid ? make_float4(o[0], o[1], o[2], o[3]) : make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) store_scalar<NT>(buf, t, p.a_ch + q, d3[q]);
       }
     } else if (p.in_mode == CPFN_MLP_IN_INTERP) {
 #pragma unroll
@@ -971,6 +991,11 @@ int launch_chain(const cpfn_mlp_chain_t *c, cudaStream_t st) {
   int width = c->a_ch;
   if (c->in_mode == CPFN_MLP_IN_GROUP) width += 3;
   else if (c->in_mode == CPFN_MLP_IN_INTERP) width += c->b_ch;
+  p.l0_w = c->l0_w; p.l0_b = c->l0_b; p.l0_cout = c->l0_cout;
+  if (c->l0_w != nullptr) {
+    if (c->in_mode != CPFN_MLP_IN_GROUP || c->a_ch != 0 || !c->l0_b || c->l0_cout <= 0 || (c->l0_cout & 3)) return CPFN_EINVAL;
+    width = c->l0_cout;
+  }
   if (width != c->layers[0].cin || (c->a_ch & 3) || (c->b_ch & 3)) return CPFN_EINVAL;
   if (c->a_ch > 0 && !c->a_src) return CPFN_EINVAL;
   if (c->in_mode == CPFN_MLP_IN_GROUP && (!c->idx || !c->xyz || !c->centers || c->group_k <= 0)) return CPFN_EINVAL;

@@ -38,7 +38,8 @@ class _Chain(ctypes.Structure):
                 ("b_src", ctypes.c_void_p), ("b_ch", ctypes.c_int32), ("b_rows", ctypes.c_int32),
                 ("nn_w", ctypes.c_void_p),
                 ("out_mode", ctypes.c_int32), ("out", ctypes.c_void_p), ("ldo", ctypes.c_int32),
-                ("pool_g", ctypes.c_int32), ("split_cout", ctypes.c_int32)]
+                ("pool_g", ctypes.c_int32), ("split_cout", ctypes.c_int32),
+                ("l0_w", ctypes.c_void_p), ("l0_b", ctypes.c_void_p), ("l0_cout", ctypes.c_int32)]
 
 
 def available():
@@ -100,7 +101,8 @@ class PackedChain:
 
 def run_chain(pc, B, cols_per_cloud, out, ldo, tile_cols=128, in_mode=IN_DENSE, a_src=None, a_ch=0, a_rows=0,
               idx=None, xyz=None, centers=None, group_k=0, b_src=None, b_ch=0, b_rows=0, nn_w=None,
-              out_mode=OUT_ROWS, pool_g=0, biases=None, bias_per_cloud=(), masks=None, out_cm=None, split_cout=False):
+              out_mode=OUT_ROWS, pool_g=0, biases=None, bias_per_cloud=(), masks=None, out_cm=None, split_cout=False,
+              l0=None):
     """Enqueue one fused chain on torch's current stream."""
     c = _Chain()
     c.n_layers = len(pc.dims)
@@ -121,6 +123,8 @@ def run_chain(pc, B, cols_per_cloud, out, ldo, tile_cols=128, in_mode=IN_DENSE, 
     c.b_src, c.b_ch, c.b_rows, c.nn_w = p(b_src), b_ch, b_rows, p(nn_w)
     c.out_mode, c.out, c.ldo, c.pool_g = out_mode, out.data_ptr(), ldo, pool_g
     c.split_cout = int(split_cout)
+    if l0 is not None:
+        c.l0_w, c.l0_b, c.l0_cout = l0[0].data_ptr(), l0[1].data_ptr(), l0[0].shape[0]
     with torch.cuda.device(out.device):
         _lib.check(_lib.lib().cpfn_mlp_chain(ctypes.byref(c), torch.cuda.current_stream(out.device).cuda_stream),
                    "mlp_chain")
@@ -268,7 +272,13 @@ def _sa_chain(module, device):
                 # kernel builds rows as [feats, xyz]: permute the input channels of the first layer
                 w = np.concatenate([w[:, 3:], w[:, :3]], axis=1)
             layers.append((w, b, True))
+        l0 = None
+        if layers[0][0].shape[1] == 3 and layers[0][0].shape[0] % 4 == 0 and len(layers) > 1 and not module.group_all:
+            # bare positions: the 3 -> C first layer runs in fp32 on the CUDA cores inside the tile builder
+            w0, b0, _ = layers.pop(0)
+            l0 = (torch.from_numpy(np.ascontiguousarray(w0)).to(device), torch.from_numpy(np.ascontiguousarray(b0)).to(device))
         pc = PackedChain(layers, device)
+        pc.l0 = l0
         setattr(module, _CACHE_ATTR, pc)
     return pc
 
@@ -307,7 +317,7 @@ def sa_forward_pm(module, xyz, feats_pm, indices=None):
     new_xyz, group_idx = indices
     out = torch.empty(B, S, cout, dtype=torch.float32, device=dev)
     run_chain(pc, B, S * K, out, cout, tile_cols=pick_tile(pc.dims, S * K, name=('SA1' if D == 0 else 'SA2'), prefer=(128 if D == 0 else 64)), in_mode=IN_GROUP, a_src=feats_pm, a_ch=D, a_rows=N,
-              idx=group_idx, xyz=xyz, centers=new_xyz, group_k=K, out_mode=OUT_POOL, pool_g=K)
+              idx=group_idx, xyz=xyz, centers=new_xyz, group_k=K, out_mode=OUT_POOL, pool_g=K, l0=getattr(pc, "l0", None))
     return new_xyz, out
 
 

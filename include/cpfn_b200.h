@@ -183,6 +183,10 @@ typedef struct {
   int32_t out_mode;           /* CPFN_MLP_OUT_* */
   float *out; int32_t ldo; int32_t pool_g;
   int32_t split_cout;         /* 1: single-layer chain, tile_cols 64/32: one CTA per (column tile, 128-channel chunk) */
+  /* GROUP mode with a_ch == 0 (set abstraction on bare positions): optional fp32 first layer
+   * relu(l0_w [l0_cout,3] * (xyz[idx] - centre) + l0_b) evaluated on the CUDA cores while the tile is
+   * built; layers[0].cin must then equal l0_cout. */
+  const float *l0_w; const float *l0_b; int32_t l0_cout;
 } cpfn_mlp_chain_t;
 
 /* Replaces the conv+BN+ReLU(+max) chains of pointset_abstraction.py:61-74,

@@ -187,3 +187,22 @@ def test_layerwise_equals_fused_chain(cuda_dev):
     o = torch.zeros(5, 128, device=cuda_dev)
     fused.linear_rows(g, w, bb, o)
     assert _rel(o[:, :40], g @ w.t() + bb) < 1e-5 and float(o[:, 40:].abs().max()) == 0.0
+
+
+def test_first_layer_on_cuda_cores(cuda_dev):
+    """GROUP mode on bare positions with the 3 -> 64 first layer evaluated in fp32 by the tile builder."""
+    rng = np.random.default_rng(21)
+    B, N, S, K = 2, 700, 40, 64
+    dims = [3, 64, 64, 128]
+    pc_full, layers = _chain(dims, rng, cuda_dev)
+    pc = fused.PackedChain(layers[1:], cuda_dev)
+    l0 = (torch.from_numpy(layers[0][0]).to(cuda_dev), torch.from_numpy(layers[0][1]).to(cuda_dev))
+    xyz = torch.from_numpy(rng.normal(size=(B, N, 3)).astype(np.float32)).to(cuda_dev)
+    centers = torch.from_numpy(rng.normal(size=(B, S, 3)).astype(np.float32)).to(cuda_dev)
+    idx = torch.from_numpy(rng.integers(0, N, size=(B, S, K)).astype(np.int32)).to(cuda_dev)
+    out = torch.full((B, S, 128), float("nan"), device=cuda_dev)
+    fused.run_chain(pc, B, S * K, out, 128, tile_cols=128, in_mode=fused.IN_GROUP, a_src=None, a_ch=0, a_rows=N, idx=idx,
+                    xyz=xyz, centers=centers, group_k=K, out_mode=fused.OUT_POOL, pool_g=K, l0=l0)
+    g = torch.gather(xyz, 1, idx.long().reshape(B, S * K, 1).expand(-1, -1, 3)).reshape(B, S, K, 3) - centers[:, :, None, :]
+    ref = _ref(g, layers).max(dim=2)[0]
+    assert _rel(out, ref) < TOL, _rel(out, ref)
