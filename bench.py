@@ -264,9 +264,16 @@ def run_ours(args):
     fps_bytes = B_PER_GPU * (512 - 1) * N_POINTS * 16
     fps_t = float(np.mean(fps_big)) * 1e-6 if fps_big else float("nan")
     achieved = fps_bytes / fps_t / 1e9
-    roofline = {"kernel": "fps_cta_kernel (SA1: 16 clouds x 8192 pts -> 512 samples)", "bound": "hbm",
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")        # dram bytes per launch from the committed ncu capture
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            for k, v in json.load(f).items():
+                if k.startswith("fps_cluster_kernel"):
+                    traffic = v["dram_bytes"]
+    roofline = {"kernel": "fps_cluster_kernel (SA1: 16 clouds x 8192 pts -> 512 samples, 4-CTA clusters)", "bound": "hbm",
                 "achieved": round(achieved, 1), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": None,
+                "frac": round(achieved / peak, 4), "traffic": traffic,
                 "algorithmic_bytes": fps_bytes, "kernel_us": round(fps_t * 1e6, 2),
                 "note": "effective bytes B*(m-1)*N*16 (SURVEY 8d); data is register/SMEM resident, compulsory HBM is 1.6 MB"}
 

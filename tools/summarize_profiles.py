@@ -22,7 +22,7 @@ if os.path.exists(path):
     hdr = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
     h, data = rows[hdr], rows[hdr + 1:]
     ki, vi, gi, bi = h.index("Kernel Name"), h.index("Metric Value"), h.index("Grid Size"), h.index("Block Size")
-    starts = [i for i, r in enumerate(data) if "fps_cluster_kernel<4" in r[ki] or "fps_cta_kernel<8" in r[ki]]
+    starts = [i for i, r in enumerate(data) if "fps_cluster_kernel" in r[ki] or "fps_cta_kernel<8" in r[ki]]
     step = data[starts[-2]:starts[-1]] if len(starts) >= 2 else data
     lines, tot, ours = [], 0.0, 0.0
     agg = collections.OrderedDict()
@@ -77,3 +77,16 @@ for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "*.ncu-rep"))):
             f.write("\nwarp stall reasons (warps per issue-active cycle): " +
                     ", ".join("%s %.2f" % (n, v) for v, n in sorted(stalls, reverse=True)[:6]) + "\n\n")
     print("wrote", os.path.join(out_dir, "%s_ncu_%s.md" % (tag, name)))
+    tpath = os.path.join(out_dir, "%s_traffic.json" % tag)
+    traffic = json.load(open(tpath)) if os.path.exists(tpath) else {}
+    unit = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for r in rows[2:]:
+        try:
+            rd = float(r[idx["dram__bytes_read.sum"]].replace(",", "")) * unit[rows[1][idx["dram__bytes_read.sum"]]]
+            wr = float(r[idx["dram__bytes_write.sum"]].replace(",", "")) * unit[rows[1][idx["dram__bytes_write.sum"]]]
+        except (KeyError, ValueError):
+            continue
+        kname = r[idx["Kernel Name"]].split("(")[0].split("::")[-1]
+        key = "%s grid=%s" % (kname, r[idx["launch__grid_size"]])
+        traffic[key] = {"dram_bytes": rd + wr, "us": float(r[idx["gpu__time_duration.sum"]].replace(",", ""))}
+    json.dump(traffic, open(tpath, "w"), indent=1, sort_keys=True)
