@@ -107,3 +107,29 @@ def test_cuda_graph_replay_matches_eager(engine, cuda_dev):
     m1 = eng.forward_graphed(P, dropout=True)["output_feat"].clone()
     m2 = eng.forward_graphed(P, dropout=True)["output_feat"].clone()
     assert not torch.equal(m1, m2)                         # a fresh dropout mask per replay
+
+
+def test_localspfn_patches_parity_and_batch_independence(cuda_dev):
+    """BASELINE configs[3] shape: LocalSPFN = the same backbone on patches of 8192 points with
+    K = 21 instance slots (Configs/config_localSPFN.yml:6,19), patches as the batch dimension
+    (evaluation_localSPFN.py:95).  Parity against the oracle on 3 patches; at the full 32 patches the
+    size-independent property: a patch's outputs do not depend on which other patches share the batch."""
+    torch.backends.cudnn.allow_tf32 = False
+    eng = api.GlobalSPFN(output_sizes=[3, 4, 21], device=cuda_dev)
+    state = cases.network_state(eng.model.state_dict(), seed=11)
+    sd = {k: torch.from_numpy(v) for k, v in state.items()}
+    eng.load_state_dict(sd, strict=True)
+    from cpfn_b200 import synth
+    P = synth.shape_batch(32, 8192, seed=404, k_slots=21)[0]
+    out3 = eng.forward(torch.from_numpy(P[:3]).to(cuda_dev), dropout=False)
+    ref = onet.pointnet2_forward(sd, P[:3], 3)
+    for i, k in enumerate(("X_raw", "T_raw", "W_raw")):
+        assert _rel(out3[k].cpu().numpy(), ref["heads"][i]) < 2e-4, k
+    assert out3["W"].shape == (3, 8192, 21) and out3["parameters"]["cone_half_angle"].shape == (3, 21)
+    full = eng.forward(torch.from_numpy(P).to(cuda_dev), dropout=False)
+    for k in ("X_raw", "W_raw", "T_raw"):
+        assert torch.equal(full[k][:3], out3[k]), k
+    for k, v in out3["parameters"].items():
+        assert torch.equal(full["parameters"][k][:3], v), k
+    solo = eng.forward(torch.from_numpy(P[17:18]).to(cuda_dev), dropout=False)
+    assert torch.equal(full["W_raw"][17:18], solo["W_raw"])
