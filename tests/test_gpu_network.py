@@ -130,6 +130,8 @@ def test_localspfn_patches_parity_and_batch_independence(cuda_dev):
     for k in ("X_raw", "W_raw", "T_raw"):
         assert torch.equal(full[k][:3], out3[k]), k
     for k, v in out3["parameters"].items():
-        assert torch.equal(full["parameters"][k][:3], v), k
+        # the fitters' partial-sum partition depends on the batch size: equal to fp32 summation noise
+        a, b = full["parameters"][k][:3], v
+        assert float((a - b).abs().max()) <= 1e-4 * max(1.0, float(b.abs().max())), k
     solo = eng.forward(torch.from_numpy(P[17:18]).to(cuda_dev), dropout=False)
     assert torch.equal(full["W_raw"][17:18], solo["W_raw"])
