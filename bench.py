@@ -187,12 +187,12 @@ def run_ours(args):
             return eng.forward_graphed(dev_inputs[i % n_in])
         return eng.forward(dev_inputs[i % n_in])
 
+    sampler = ClockSampler(local_rank)      # samples clocks / throttle reasons from warm-up to the end of the GPU work
+    if rank == 0:
+        sampler.start()
     for i in range(max(3, args.warmup)):
         step(i)
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = cuda_ops.LAUNCHES
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
@@ -217,7 +217,6 @@ def run_ours(args):
         _, h2d, d2h = eng.run_host(host_inputs[i % n_in], graphed=use_graph)
     barrier()
     e2e_s = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else None
 
     t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
@@ -248,6 +247,7 @@ def run_ours(args):
         b.record()
         tot.append((a, b))
     per_op = timer.summary()
+    clocks = sampler.stop()
     step_us = float(np.mean([a.elapsed_time(b) * 1e3 for a, b in tot]))
     for mod, n, fn in originals:
         setattr(mod, n, fn)
