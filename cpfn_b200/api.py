@@ -52,7 +52,7 @@ class GlobalSPFN:
                 out["W"] = torch.softmax(heads[2], dim=2)
             out["T"] = heads[1]
             if fit:
-                out["parameters"] = L.compute_parameters(P, out["W"], out["X"], self.classes)
+                out["parameters"], out["parameters_packed"] = L.compute_parameters_packed(P, out["W"], out["X"], self.classes)
             return out
         m = self.model
         x = P.transpose(2, 1)
@@ -132,8 +132,9 @@ class GlobalSPFN:
         res_dev = {"instance": out["instance"] if "instance" in out else torch.argmax(out["W"], dim=2).to(torch.int32),
                    "type": out["type"] if "type" in out else torch.argmax(out["T"], dim=2).to(torch.int32),
                    "normals": out["X"]}
-        first = next(iter(params.values()))
-        packed = first._base if first._base is not None and first._base.numel() == sum(v.numel() for v in params.values()) else None
+        packed = out.get("parameters_packed")
+        if packed is not None and packed.numel() != sum(v.numel() for v in params.values()):
+            packed = None                           # a subset of the classes was requested: copy tensor by tensor
         res, d2h = {}, 0
         if packed is not None:                     # the ten parameter tensors are views of ONE buffer: one copy
             hp = self._pinned("out_params", packed.shape, packed.dtype)

@@ -27,12 +27,18 @@ def _workspace(nbytes, device):
 def fit_primitives(P, W, X):
     """P [B,N,3], W [B,N,K], X [B,N,3] float32 CUDA -> dict of the ten reference keys
     (each a contiguous view of one [22*B*K] buffer)."""
+    return fit_primitives_packed(P, W, X)[0]
+
+
+def fit_primitives_packed(P, W, X):
+    """As ``fit_primitives`` but also returns the single [22*B*K] buffer the ten tensors are views of
+    (one device-to-host copy moves all parameters); ``None`` on the differentiable path."""
     if not P.is_cuda:
         raise RuntimeError("CPU not supported")
     if torch.is_grad_enabled() and (W.requires_grad or X.requires_grad):
         # training: CUDA moment kernels with a backward + float64 autograd algebra (spfn/_train.py)
         from . import _train
-        return _train.compute_parameters(P, W, X, ("plane", "sphere", "cylinder", "cone"))
+        return _train.compute_parameters(P, W, X, ("plane", "sphere", "cylinder", "cone")), None
     B, N, _ = P.shape
     K = W.shape[2]
     P = P.detach().float().contiguous()
@@ -53,4 +59,4 @@ def fit_primitives(P, W, X):
     for name, off, width in KEYS:
         seg = out.narrow(0, off * BK, width * BK)
         res[name] = seg.view(B, K, 3) if width == 3 else seg.view(B, K)
-    return res
+    return res, out

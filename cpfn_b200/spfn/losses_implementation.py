@@ -15,9 +15,14 @@ def compute_parameters(P, W, X, classes=['plane', 'sphere', 'cylinder', 'cone'])
     for class_ in classes:
         if class_ not in _CLASS_KEYS:
             raise NotImplementedError
-    r = fit.fit_primitives(P, W, X)
+    return compute_parameters_packed(P, W, X, classes)[0]
+
+
+def compute_parameters_packed(P, W, X, classes=['plane', 'sphere', 'cylinder', 'cone']):
+    """(parameters dict, the one packed buffer behind it | None) -- see fit.fit_primitives_packed."""
+    r, packed = fit.fit_primitives_packed(P, W, X)
     parameters = {}
     for class_ in classes:
         for key in _CLASS_KEYS[class_]:
             parameters[key] = r[key]
-    return parameters
+    return parameters, packed

@@ -88,6 +88,9 @@ def test_run_host_end_to_end(engine, cuda_dev):
     Xn, _, Wn = onet.spfn_postprocess(ref["heads"])
     agree = float((res["instance"].numpy() == Wn.argmax(2)).mean())
     assert agree > 0.99, agree
+    res_g, _, _ = eng.run_host(P, dropout=False, graphed=True)          # same call replayed from a CUDA graph
+    for k in ("plane_normal", "sphere_center", "cone_half_angle", "instance", "normals"):
+        assert torch.equal(res_g[k], res[k].clone()) or torch.allclose(res_g[k].float(), res[k].float()), k
 
 
 def test_cuda_graph_replay_matches_eager(engine, cuda_dev):
