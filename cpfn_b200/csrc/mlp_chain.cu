@@ -633,8 +633,9 @@ mlp_chain_pm1_kernel(const __grid_constant__ ChainP p) {
       const long long col0 = static_cast<long long>(tile) * NT;
       const long long col = col0 + row;
       const bool row_ok = col < p.cols;
-      const long long cloud = col0 / p.cols_per_cloud;
-      const long long n_in_cloud = col0 - cloud * p.cols_per_cloud;
+      // thread = point: the cloud of THIS row (a tile may straddle two clouds when N is not a multiple of 128)
+      const long long cloud = (row_ok ? col : col0) / p.cols_per_cloud;
+      const long long n_in_cloud = (row_ok ? col : col0) - cloud * p.cols_per_cloud - row;
       load_tile<NT, 8>(p, smem_u32(act0), col0, w8, lane, s_arow, s_brow, s_w, 1);
       fence_proxy_async();
       mbar_arrive(act_ready);
@@ -851,8 +852,9 @@ mlp_chain_pm_kernel(const __grid_constant__ ChainP p) {
       const long long col0 = static_cast<long long>(tile) * NT;
       const long long col = col0 + row;
       const bool row_ok = col < p.cols;
-      const long long cloud = col0 / p.cols_per_cloud;
-      const long long n_in_cloud = col0 - cloud * p.cols_per_cloud;
+      // thread = point: the cloud of THIS row (a tile may straddle two clouds when N is not a multiple of 128)
+      const long long cloud = (row_ok ? col : col0) / p.cols_per_cloud;
+      const long long n_in_cloud = (row_ok ? col : col0) - cloud * p.cols_per_cloud - row;
       load_tile<NT, 4>(p, my_act, col0, w4, lane, s_arow, s_brow, s_w, 1 + g);
       fence_proxy_async();
       mbar_arrive(act_ready + g);
@@ -975,7 +977,7 @@ int launch_chain(const cpfn_mlp_chain_t *c, cudaStream_t st) {
     if (L.cout_chunks > max_chunks) max_chunks = L.cout_chunks;
     const size_t in_bytes = static_cast<size_t>(L.cin_atoms) * 2 * NT * 128;
     if (in_bytes > act_need[0]) act_need[0] = in_bytes;
-    if ((s.bias_per_cloud || s.mask || s.out_cm) && (c->cols_per_cloud % NT) != 0) return CPFN_EINVAL;
+    if (NT != 128 && (s.bias_per_cloud || s.mask || s.out_cm) && (c->cols_per_cloud % NT) != 0) return CPFN_EINVAL;
   }
   if (static_cast<size_t>(total_blocks) * kStageBytes != c->weight_bytes) return CPFN_EINVAL;
   p.weights = static_cast<const uint8_t *>(c->weights);

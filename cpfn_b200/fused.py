@@ -146,8 +146,8 @@ def _pick_tile(dims, cols_per_cloud, need_cloud_aligned=False, prefer=128):
     for tile in (128, 64, 32):
         if tile > prefer:
             continue
-        if need_cloud_aligned and cols_per_cloud % tile:
-            continue
+        if need_cloud_aligned and tile != 128 and cols_per_cloud % tile:
+            continue                      # the channels-as-M kernel indexes masks / per-cloud biases per tile
         need = max((cin + 63) // 64 * 2 * tile * 128 for cin, _, _ in dims)   # one in-place activation buffer
         if tile == 128:
             # points-as-M kernel: two 128-column sub-tiles per CTA, <= 256 TMEM columns each

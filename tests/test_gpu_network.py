@@ -138,3 +138,20 @@ def test_localspfn_patches_parity_and_batch_independence(cuda_dev):
         assert float((a - b).abs().max()) <= 1e-4 * max(1.0, float(b.abs().max())), k
     solo = eng.forward(torch.from_numpy(P[17:18]).to(cuda_dev), dropout=False)
     assert torch.equal(full["W_raw"][17:18], solo["W_raw"])
+
+
+@pytest.mark.parametrize("n_points", [1000, 2500, 20000])
+def test_ragged_point_counts(engine, cuda_dev, n_points):
+    """N that is not a multiple of the tile (evaluation_globalSPFN.py runs full-resolution clouds of
+    arbitrary size): tiles straddle clouds; indices and features still match the oracle."""
+    eng, sd = engine
+    P = cases.network_input(batch=3 if n_points < 10000 else 1, n_points=n_points, seed=60 + n_points)
+    out = eng.forward(torch.from_numpy(P).to(cuda_dev), dropout=False)
+    ref = onet.pointnet2_forward(sd, P, 3)
+    for i, k in enumerate(("X_raw", "T_raw", "W_raw")):
+        assert _rel(out[k].cpu().numpy(), ref["heads"][i]) < 2e-4, k
+    assert _rel(out["output_feat"].cpu().numpy(), ref["feat_pre_dropout"]) < 2e-4
+    torch.manual_seed(3)
+    d = eng.forward(torch.from_numpy(P).to(cuda_dev), dropout=True)
+    kept = d["output_feat"] != 0
+    assert torch.allclose(d["output_feat"][kept], 2 * out["output_feat"][kept], rtol=1e-5, atol=1e-6)   # mask is 0 or 2
