@@ -31,6 +31,9 @@ SIGNATURES = {
                                              c_size_t, c_void_p]),
     "cpfn_ball_query": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int,
                                 c_void_p, c_void_p]),
+    "cpfn_ball_query_grid_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "cpfn_ball_query_grid": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p, c_size_t,
+                                     c_void_p]),
     "cpfn_gather_points": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                                    c_void_p]),
     "cpfn_gather_points_grad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,

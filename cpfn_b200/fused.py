@@ -374,6 +374,7 @@ def fp_forward_pm(module, xyz1, xyz2, feats1_pm, feats2_pm, nn=None):
 
 _ones_cache = {}
 _side_streams = {}
+USE_SIDE_STREAM = True      # bench.py's per-op profiling pass serialises everything on one stream
 
 
 def _side_stream(dev):
@@ -436,7 +437,7 @@ def pointnet2_forward(model, P, dropout=True):
     # Everything that depends on positions only (SA2's sampling / ball query, the 3-NN weights of FP2 and
     # FP3) runs on a side stream, concurrently with SA1's ball query and MLP chain on the main stream.
     main = torch.cuda.current_stream(dev)
-    side = _side_stream(dev)
+    side = _side_stream(dev) if USE_SIDE_STREAM else main
     idx1 = sa_indices(model.sa1, P)
     l1_xyz = idx1[0]
     fork = torch.cuda.Event()
@@ -452,8 +453,9 @@ def pointnet2_forward(model, P, dropout=True):
         join.record(side)
     _, l1 = sa_forward_pm(model.sa1, P, None, indices=idx1)
     main.wait_event(join)
-    for t in (*idx2, *nn3, *nn2) + ((mask,) if mask is not None else ()):
-        t.record_stream(main)
+    if side is not main:
+        for t in (*idx2, *nn3, *nn2) + ((mask,) if mask is not None else ()):
+            t.record_stream(main)
     l2_xyz, l2 = sa_forward_pm(model.sa2, l1_xyz, l1, indices=idx2)
     _, l3 = sa_forward_pm(model.sa3, l2_xyz, l2)
     l4 = fp_forward_pm(model.sfp1, l2_xyz, None, l2, l3)

@@ -73,6 +73,15 @@ CPFN_API int cpfn_ball_query(const float *new_xyz, const float *xyz, int B, int 
                     float radius, int nsample, int32_t *idx,
                     cpfn_stream_t stream);
 
+/* Ball query on a uniform grid (cells >= radius, built per call in `workspace`): bit-identical output,
+ * a query only tests the points of its 27 neighbouring cells; hits are collected in an index bitmap so
+ * the "first nsample in index order" rule of the reference holds whatever order the grid yields them.
+ * Falls back to cpfn_ball_query for N < 2048 (the scan is faster there) or N > 32768. */
+CPFN_API size_t cpfn_ball_query_grid_workspace_bytes(int B, int N);
+CPFN_API int cpfn_ball_query_grid(const float *new_xyz, const float *xyz, int B, int N, int S,
+                                  float radius, int nsample, int32_t *idx, void *workspace,
+                                  size_t workspace_bytes, cpfn_stream_t stream);
+
 /* Gather / group (+ gradients).  Replace gather_points(_grad)
  * (src/sampling.cpp:15-64, src/sampling_gpu.cu:8-53) and group_points(_grad)
  * (src/group_points.cpp:12-60, src/group_points_gpu.cu:8-74).

@@ -214,3 +214,23 @@ def test_three_nn_weights_and_gather_xyz_and_post(cuda_dev, oracle_ops):
     ht = torch.from_numpy(h)
     np.testing.assert_allclose(X.cpu().numpy(), torch.nn.functional.normalize(ht[:, :, :3], dim=2).numpy(), rtol=1e-6, atol=1e-7)
     np.testing.assert_allclose(W.cpu().numpy(), torch.softmax(ht[:, :, 7:], dim=2).numpy(), rtol=2e-6, atol=1e-9)
+
+
+def test_ball_query_grid_equals_scan_kernel(cuda_dev, oracle_ops, monkeypatch):
+    """The uniform-grid kernel and the brute-force scan kernel give the same indices (and both equal
+    the oracle) on uniform, lattice (ties on the radius), clustered and out-of-box query sets."""
+    rng = np.random.default_rng(12)
+    for name, (N, S, r, K) in {"u": (8192, 512, 0.2, 64), "l": (3000, 300, 0.25, 16), "c": (5000, 128, 0.05, 32),
+                               "big_r": (2048, 64, 1.5, 64), "k1": (2700, 90, 0.3, 1), "max": (32768, 40, 0.1, 8)}.items():
+        xyz = synth.lattice_cloud(2, N, seed=N, pitch=8) if name == "l" else synth.uniform_cloud(2, N, seed=N)
+        if name == "c":
+            xyz = (xyz * 0.1 + rng.normal(scale=0.3, size=(2, 1, 3))).astype(np.float32)
+        q = xyz[:, rng.permutation(N)[:S]].copy()
+        q[:, :5] += np.float32(3.0)                       # queries far outside the bounding box: no hits
+        q[:, 5:10] += np.float32(r * 0.9)                 # just outside / near the boundary cells
+        monkeypatch.delenv("CPFN_BQ_NO_GRID", raising=False)
+        a = cuda_ops.ball_query(_t(q, cuda_dev), _t(xyz, cuda_dev), r, K).cpu().numpy()
+        monkeypatch.setenv("CPFN_BQ_NO_GRID", "1")
+        b = cuda_ops.ball_query(_t(q, cuda_dev), _t(xyz, cuda_dev), r, K).cpu().numpy()
+        np.testing.assert_array_equal(a, b, err_msg=name)
+        np.testing.assert_array_equal(a, oracle_ops.ball_query(q, xyz, r, K), err_msg=name)
