@@ -20,7 +20,7 @@ constexpr int kNnTile = 2048;
 __global__ void __launch_bounds__(kGlueThreads)
 three_nn_weights_kernel(const float *__restrict__ unknown, const float *__restrict__ known, int n, int m,
                         float *__restrict__ weight, int32_t *__restrict__ idx) {
-  __shared__ float4 s_known[kNnTile];
+  extern __shared__ float4 s_known[];      // min(m, kNnTile) records: small enough to co-reside with the MLP chains
   const int b = blockIdx.y;
   const int j = blockIdx.x * kGlueThreads + threadIdx.x;
   const float *kn = known + static_cast<size_t>(b) * m * 3;
@@ -173,7 +173,8 @@ extern "C" int cpfn_three_nn_weights(const float *unknown, const float *known, i
   if (B == 0 || n == 0) return CPFN_OK;
   if (!unknown || !weight || !idx || (m > 0 && !known) || B > 65535) return CPFN_EINVAL;
   dim3 grid((n + kGlueThreads - 1) / kGlueThreads, B);
-  three_nn_weights_kernel<<<grid, kGlueThreads, 0, as_stream(stream)>>>(unknown, known, n, m, weight, idx);
+  const size_t smem = sizeof(float4) * static_cast<size_t>(m < kNnTile ? (m > 0 ? m : 1) : kNnTile);
+  three_nn_weights_kernel<<<grid, kGlueThreads, smem, as_stream(stream)>>>(unknown, known, n, m, weight, idx);
   return check_launch();
 }
 

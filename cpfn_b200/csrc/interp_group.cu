@@ -30,7 +30,7 @@ constexpr int kNnTile = 2048;  // known points per shared tile (32 KB as float4)
 __global__ void __launch_bounds__(kNnThreads)
 three_nn_kernel(const float *__restrict__ unknown, const float *__restrict__ known, int n, int m,
                 float *__restrict__ dist2, int32_t *__restrict__ idx) {
-  __shared__ float4 s_known[kNnTile];
+  extern __shared__ float4 s_known[];      // min(m, kNnTile) records: small enough to co-reside with the MLP chains
   const int b = blockIdx.y;
   const int j = blockIdx.x * kNnThreads + threadIdx.x;
   const float *kn = known + static_cast<size_t>(b) * m * 3;
@@ -184,7 +184,8 @@ extern "C" int cpfn_three_nn(const float *unknown, const float *known, int B, in
   if (B == 0 || n == 0) return CPFN_OK;
   if (!unknown || !dist2 || !idx || (m > 0 && !known) || B > 65535) return CPFN_EINVAL;
   dim3 grid((n + kNnThreads - 1) / kNnThreads, B);
-  three_nn_kernel<<<grid, kNnThreads, 0, as_stream(stream)>>>(unknown, known, n, m, dist2, idx);
+  const size_t smem = sizeof(float4) * static_cast<size_t>(m < kNnTile ? (m > 0 ? m : 1) : kNnTile);
+  three_nn_kernel<<<grid, kNnThreads, smem, as_stream(stream)>>>(unknown, known, n, m, dist2, idx);
   return check_launch();
 }
 
