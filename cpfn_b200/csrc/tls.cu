@@ -60,7 +60,7 @@ TlsGeom tls_geom(int B, int N, int K, int sms) {
   g.G = imax(1, kTlsThreads / K);
   long long want = (static_cast<long long>(B) * N + 2LL * sms * g.G - 1) / (2LL * sms * g.G);
   g.ppt = static_cast<int>(want < 8 ? 8 : (want > kPPT ? kPPT : want));
-  g.ppt = imin(g.ppt, imax(1, kMaxCP / g.G));
+  g.ppt = imin((g.ppt + 7) & ~7, imax(8, (kMaxCP / g.G) & ~7));   // a multiple of 8 (uniform 8-point blocks)
   g.CP = g.G * g.ppt;
   const int SC = (N + g.CP - 1) / g.CP;
   const int cap = imax(1, (4 * sms + B - 1) / B);
@@ -118,13 +118,15 @@ tls_pass_kernel(const float *__restrict__ P, const float *__restrict__ X,
       }
     }
     __syncthreads();
-    for (int i = t; i < cn; i += kTlsThreads) {
-      const float *p = Pb + static_cast<size_t>(n0 + i) * 3;
-      const float px = __ldg(p), py = __ldg(p + 1), pz = __ldg(p + 2);
-      float xx = 0.f, xy = 0.f, xz = 0.f;
-      if (Xb) {
-        const float *x = Xb + static_cast<size_t>(n0 + i) * 3;
-        xx = __ldg(x); xy = __ldg(x + 1); xz = __ldg(x + 2);
+    for (int i = t; i < CP; i += kTlsThreads) {          // entries past the end of the cloud are zeros
+      float px = 0.f, py = 0.f, pz = 0.f, xx = 0.f, xy = 0.f, xz = 0.f;
+      if (i < cn) {
+        const float *p = Pb + static_cast<size_t>(n0 + i) * 3;
+        px = __ldg(p); py = __ldg(p + 1); pz = __ldg(p + 2);
+        if (Xb) {
+          const float *x = Xb + static_cast<size_t>(n0 + i) * 3;
+          xx = __ldg(x); xy = __ldg(x + 1); xz = __ldg(x + 2);
+        }
       }
       sp[i] = make_float4(px, py, pz, px * px + py * py + pz * pz);
       sx[i] = make_float4(xx, xy, xz, px * xx + py * xy + pz * xz);
@@ -133,15 +135,19 @@ tls_pass_kernel(const float *__restrict__ P, const float *__restrict__ X,
     float acc[F];
 #pragma unroll
     for (int f = 0; f < F; ++f) acc[f] = 0.f;
+    // this thread's valid points in the sub-chunk: j = g + i*G < cn  <=>  i < lim.  Blocks of 8 points are
+    // skipped uniformly (ppt is a multiple of 8); inside a block invalid pairs carry w = w' = 0.
+    const int lim = active ? imax(0, (cn - g + G - 1) / G) : 0;
+    const float4 *pp = sp + g, *xp = sx + g;
 #pragma unroll
     for (int i = 0; i < kPPT; ++i) {
-      const int j = g + i * G;
-      if (i >= ppt || j >= cn) continue;
+      if ((i & 7) == 0 && i >= ppt) break;
+      const bool ok = i < lim;
       const float w = wv[i];
-      const float4 p = sp[j];
+      const float4 p = pp[i * G];
       if (PASS == 1) {
-        const float4 x = sx[j];
-        const float wc = fmaxf(w, 1e-10f);
+        const float4 x = xp[i * G];
+        const float wc = ok ? fmaxf(w, 1e-10f) : 0.f;
         acc[0] += w;
         acc[1] = fmaf(w, p.x, acc[1]); acc[2] = fmaf(w, p.y, acc[2]); acc[3] = fmaf(w, p.z, acc[3]);
         acc[4] = fmaf(w, p.w, acc[4]);
@@ -154,8 +160,8 @@ tls_pass_kernel(const float *__restrict__ P, const float *__restrict__ X,
         acc[17] = fmaf(vy, x.y, acc[17]); acc[18] = fmaf(vy, x.z, acc[18]); acc[19] = fmaf(vz, x.z, acc[19]);
         acc[20] = fmaf(vx, x.w, acc[20]); acc[21] = fmaf(vy, x.w, acc[21]); acc[22] = fmaf(vz, x.w, acc[22]);
       } else if (PASS == 2) {
-        const float4 x = sx[j];
-        const float wc = fmaxf(w, 1e-10f);
+        const float4 x = xp[i * G];
+        const float wc = ok ? fmaxf(w, 1e-10f) : 0.f;
         const float dx = p.x - c0, dy = p.y - c1, dz = p.z - c2;
         const float wx = w * dx, wy = w * dy, wz = w * dz;
         acc[0] = fmaf(wx, dx, acc[0]); acc[1] = fmaf(wx, dy, acc[1]); acc[2] = fmaf(wx, dz, acc[2]);
@@ -174,7 +180,7 @@ tls_pass_kernel(const float *__restrict__ P, const float *__restrict__ X,
         acc[28] = fmaf(qy, ay, acc[28]); acc[29] = fmaf(qy, az, acc[29]); acc[30] = fmaf(qz, az, acc[30]);
       } else if (PASS == 4) {
         // raw moments  sum w * [1, p, p p^T, p p p, x, x x^T, x (p.x)]  (feature order of cpfn_weighted_moments)
-        const float4 x = sx[j];
+        const float4 x = xp[i * G];
         const float wx = w * p.x, wy = w * p.y, wz = w * p.z;
         acc[0] += w; acc[1] += wx; acc[2] += wy; acc[3] += wz;
         const float uxx = wx * p.x, uxy = wx * p.y, uxz = wx * p.z, uyy = wy * p.y, uyz = wy * p.z, uzz = wz * p.z;
