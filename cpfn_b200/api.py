@@ -17,6 +17,7 @@ class GlobalSPFN:
     def __init__(self, output_sizes=(3, 4, 28), device="cuda:0", classes=('plane', 'sphere', 'cylinder', 'cone')):
         self.device = torch.device(device)
         self.classes = list(classes)
+        self.output_sizes = list(output_sizes)
         self.model = PointNet2(dim_input=3, dim_pos=3, output_sizes=list(output_sizes)).to(self.device).eval()
         for p in self.model.parameters():
             p.requires_grad_(False)
@@ -76,35 +77,59 @@ class GlobalSPFN:
             out["parameters"] = L.compute_parameters(P, out["W"], out["X"], self.classes)
         return out
 
+    def _capture(self, fn):
+        """Warm ``fn`` up on a side stream (packs weights, sizes workspaces, sets kernel attributes),
+        then capture it.  Returns (graph, fn's result, launches of this library inside the graph)."""
+        cur = torch.cuda.current_stream(self.device)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                fn()
+        cur.wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        n0 = cuda_ops.LAUNCHES
+        with torch.cuda.graph(graph):
+            out = fn()
+        return graph, out, cuda_ops.LAUNCHES - n0
+
     @torch.no_grad()
     def forward_graphed(self, P, dropout=True, fit=True):
         """``forward`` replayed from a CUDA graph (captured once per input shape): the ~50 kernel
-        launches of a step become one graph launch.  The returned tensors are STATIC buffers that
+        launches of a step become one graph launch.  ``P`` may be a device tensor or a pinned host
+        tensor (copied straight into the graph's input).  The returned tensors are STATIC buffers that
         the next call overwrites; the always-on dropout still draws a fresh mask per call (torch's
         graph-safe generator)."""
         key = (tuple(P.shape), bool(dropout), bool(fit))
         entry = self._graphs.get(key)
         if entry is None:
-            static_in = P.clone()
-            cur = torch.cuda.current_stream(self.device)
-            side = torch.cuda.Stream(device=self.device)
-            side.wait_stream(cur)
-            with torch.cuda.stream(side):
-                for _ in range(2):                       # warm-up: packs weights, sizes workspaces, sets kernel attributes
-                    self.forward(static_in, dropout=dropout, fit=fit)
-            cur.wait_stream(side)
-            torch.cuda.synchronize(self.device)
-            graph = torch.cuda.CUDAGraph()
-            n0 = cuda_ops.LAUNCHES
-            with torch.cuda.graph(graph):
-                out = self.forward(static_in, dropout=dropout, fit=fit)
-            entry = (graph, static_in, out, cuda_ops.LAUNCHES - n0)
+            static_in = torch.empty(tuple(P.shape), dtype=torch.float32, device=self.device)
+            static_in.copy_(P)
+            graph, out, n = self._capture(lambda: self.forward(static_in, dropout=dropout, fit=fit))
+            entry = (graph, static_in, out, n)
             self._graphs[key] = entry
         graph, static_in, out, n_launch = entry
         static_in.copy_(P, non_blocking=True)
         graph.replay()
         cuda_ops.count_launches(n_launch)
         return out
+
+    @torch.no_grad()
+    def _fit_graphed(self, static_in, net_out):
+        """The four fitters on the network graph's static outputs, as a second graph: run_host starts the
+        device->host copies of the per-point results between the two, so they overlap the fitters."""
+        key = ("fit", static_in.data_ptr(), net_out["W"].data_ptr())
+        entry = self._graphs.get(key)
+        if entry is None:
+            graph, res, n = self._capture(
+                lambda: L.compute_parameters_packed(static_in, net_out["W"], net_out["X"], self.classes))
+            entry = (graph, res, n)
+            self._graphs[key] = entry
+        graph, res, n_launch = entry
+        graph.replay()
+        cuda_ops.count_launches(n_launch)
+        return res
 
     def _pinned(self, name, shape, dtype):
         t = self._pin.get(name)
@@ -114,20 +139,48 @@ class GlobalSPFN:
         return t
 
     @torch.no_grad()
-    def run_host(self, P_host, dropout=True, graphed=False):
+    def run_host(self, P_host, dropout=True, graphed=False, overlap_d2h=True):
         """P_host: CPU float32 [B,N,3] (pinned or pageable).  Copies it to the device, runs
         forward + fitters, and returns HOST tensors: the parameter dictionary, per-point
         instance labels (int32 [B,N], argmax of W), per-point type labels and unit normals --
         what evaluation_globalSPFN.py:97-110 of the reference saves per shape.
         Returns (results, h2d_bytes, d2h_bytes)."""
         B, N, _ = P_host.shape
+        if graphed and overlap_d2h and self.classes == ['plane', 'sphere', 'cylinder', 'cone']:
+            src = P_host if P_host.is_pinned() else self._pinned("P", P_host.shape, torch.float32).copy_(P_host)
+            out = self.forward_graphed(src, dropout=dropout, fit=False)
+            if "instance" in out:
+                main = torch.cuda.current_stream(self.device)
+                from . import fused
+                copier = fused._side_stream(self.device)
+                ready = torch.cuda.Event()
+                ready.record(main)
+                res = {}
+                with torch.cuda.stream(copier):          # per-point results go home while the fitters run
+                    copier.wait_event(ready)
+                    for k, v in (("normals", out["X"]), ("instance", out["instance"]), ("type", out["type"])):
+                        res[k] = self._pinned("out_" + k, v.shape, v.dtype)
+                        res[k].copy_(v, non_blocking=True)
+                params, packed = self._fit_graphed(self._graphs[(tuple(P_host.shape), bool(dropout), False)][1], out)
+                hp = self._pinned("out_params", packed.shape, packed.dtype)
+                hp.copy_(packed, non_blocking=True)
+                o = 0
+                for k, v in params.items():
+                    res[k] = hp[o:o + v.numel()].view(v.shape)
+                    o += v.numel()
+                d2h = packed.numel() * 4 + sum(res[k].numel() * res[k].element_size() for k in ("normals", "instance", "type"))
+                main.synchronize()
+                copier.synchronize()
+                return res, P_host.numel() * 4, d2h
         if P_host.is_pinned():
             stage = P_host
         else:
             stage = self._pinned("P", P_host.shape, torch.float32)
             stage.copy_(P_host)
-        P = stage.to(self.device, non_blocking=True)
-        out = self.forward_graphed(P, dropout=dropout) if graphed else self.forward(P, dropout=dropout)
+        if graphed:
+            out = self.forward_graphed(stage, dropout=dropout)           # H2D straight into the graph's input
+        else:
+            out = self.forward(stage.to(self.device, non_blocking=True), dropout=dropout)
         params = out["parameters"]
         res_dev = {"instance": out["instance"] if "instance" in out else torch.argmax(out["W"], dim=2).to(torch.int32),
                    "type": out["type"] if "type" in out else torch.argmax(out["T"], dim=2).to(torch.int32),
