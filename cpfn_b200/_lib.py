@@ -58,6 +58,9 @@ SIGNATURES = {
     "cpfn_gather_xyz": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "cpfn_spfn_post": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_void_p]),
+    "cpfn_extract_patches_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "cpfn_extract_patches": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_size_t, c_void_p]),
     "cpfn_mlp_packed_bytes": (c_size_t, [c_int, c_int]),
     "cpfn_mlp_pack_weights_host": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "cpfn_mlp_chain": (c_int, [c_void_p, c_void_p]),

@@ -10,7 +10,8 @@ Two levels:
                 reference's own Python modules run on top of libcpfn_b200.so.  Needs the reference
                 tree on sys.path.
   level="full"  the module API (B2) and the fitter API (B3) are replaced as well; the reference tree
-                is not needed for the hot path.
+                is not needed for the hot path.  ``Utils.sampling_utils`` (patch extraction, row f2) is
+                replaced too; the rest of the reference's ``Utils`` package is left alone.
 """
 import sys
 import types
@@ -50,11 +51,17 @@ def install(level="full"):
         "SPFN.differentiable_tls": spfn.differentiable_tls, "SPFN.geometry_utils": spfn.geometry_utils,
     }
     sys.modules.update(table)
+    # Patch extraction: only the one module of the reference's ``Utils`` package is
+    # replaced -- the package itself (config loader, dataset utilities, ...) stays the reference's.
+    from . import sampling_utils
+    sys.modules["Utils.sampling_utils"] = sampling_utils
+    if "Utils" in sys.modules:
+        sys.modules["Utils"].sampling_utils = sampling_utils
 
 
 def uninstall():
     for name in [n for n in sys.modules if n == "PointNet2" or n.startswith("PointNet2.") or n == "SPFN"
-                 or n.startswith("SPFN.")]:
+                 or n.startswith("SPFN.") or n == "Utils.sampling_utils"]:
         mod = sys.modules[name]
         if getattr(mod, "__name__", "").startswith("cpfn_b200") or name == "PointNet2":
             del sys.modules[name]

@@ -233,6 +233,23 @@ CPFN_API int cpfn_spfn_post(const float *heads, long long rows, int ld, int x_of
                             int w_off, int K, float *X, float *W, int32_t *inst, int32_t *type,
                             cpfn_stream_t stream);
 
+/* ---------------------------------------------------------------------------
+ * Patch extraction: the k nearest high-resolution points of every seed.
+ * Replaces, per seed, the numpy block of Utils/sampling_utils.py:9-13 and
+ * Preprocessing/preprocessing_sampling_patch.py:36-40:
+ *     distances = np.linalg.norm(seed - gt_points_hr, axis=1)
+ *     patch_indices = np.argsort(distances)[:k]; patch_distances = np.sort(distances)[:k]
+ * hr_xyz [N,3], seeds_xyz [S,3] (device) -> out_idx int32 [S,k] ordered by (distance, index)
+ * -- the stable argsort order; numpy's default sort leaves ties unordered --, out_dist f32 [S,k]
+ * (np.sort(distances)[:k], bit-identical; NULL to skip), out_radius f32 [S] = out_dist[:,k-1]
+ * (np.max(patch_distances), the pool-pruning radius of :16; NULL to skip).  1 <= k <= min(N, 16384).
+ * Exact radix select, no full sort; all S seeds share the launches.
+ * ------------------------------------------------------------------------- */
+CPFN_API size_t cpfn_extract_patches_workspace_bytes(int N, int S, int k);
+CPFN_API int cpfn_extract_patches(const float *hr_xyz, int N, const float *seeds_xyz, int S, int k,
+                                  int32_t *out_idx, float *out_dist, float *out_radius, void *workspace,
+                                  size_t workspace_bytes, cpfn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

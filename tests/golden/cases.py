@@ -167,3 +167,36 @@ def fitter_loss(params, W_np, torch):
             m = mask if v.dim() == 2 else mask.unsqueeze(-1)
             total = total + (m * G * v).sum()
     return total
+
+
+def patch_cases():
+    """name -> (points_lr [n_lr,3], points_hr [N,3], pool_indices, pool_labels, k, max_patches, np.random seed).
+    Low-res = a strided subset of the high-res shape cloud (as the reference's low-res files are a
+    sub-sampling of the high-res ones); fp32 distances of distinct points do tie now and then, see assert_patches_equivalent."""
+    out = {}
+    for name, N, n_lr, k, mp, seed in (("small", 4096, 512, 256, 8, 3), ("odd_k", 5000, 400, 300, 6, 4),
+                                       ("mid", 20000, 1024, 2048, 40, 5)):
+        hr = synth.shape_cloud(N, 900 + seed)[0].astype(np.float32)
+        lr = np.ascontiguousarray(hr[:: N // n_lr][:n_lr])
+        rng = np.random.RandomState(seed)
+        pool = np.sort(rng.choice(n_lr, size=n_lr // 2, replace=False))
+        labels = rng.randint(0, 5, size=len(pool))
+        out[name] = (lr, hr, pool, labels, k, mp, 100 + seed)
+    return out
+
+
+def assert_patches_equivalent(got, ref, hr):
+    """Patch index rows are equal up to the order of EQUAL distances (the reference's introsort does not
+    define it): same shape, every row holds the same points, and position by position the distance to the
+    row's seed (= its first, zero-distance entry: the low-res points are a subset of the high-res ones) is
+    bit-identical."""
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    for r in range(ref.shape[0]):
+        if np.array_equal(got[r], ref[r]):
+            continue
+        assert got[r, 0] == ref[r, 0]
+        seed = hr[ref[r, 0]]
+        dg = np.linalg.norm(seed[None] - hr[got[r]], axis=1)
+        dr = np.linalg.norm(seed[None] - hr[ref[r]], axis=1)
+        assert np.array_equal(dg, dr), r
+        assert np.array_equal(np.sort(got[r]), np.sort(ref[r])), r

@@ -24,6 +24,11 @@ def test_full_install_maps_reference_names(built_lib):
         fitter_factory.register_primitives(["sphere", "plane", "cylinder", "cone"])
         assert fitter_factory.primitive_name_to_id("plane") == 1 and fitter_factory.get_n_registered_primitives() == 4
         assert callable(cone_fitter.compute_parameters) and callable(losses_implementation.compute_parameters)
+        import inspect
+        su = sys.modules["Utils.sampling_utils"]                # evaluation_PatchSelection.py:14,87
+        assert su is cpfn_b200.sampling_utils
+        assert list(inspect.signature(su.sample).parameters)[:5] == ["gt_points_lr", "gt_points_hr", "pool_indices",
+                                                                     "num_points_patch", "max_number_patches"]
     finally:
         dropin.uninstall()
         sys.modules.update(saved)
