@@ -61,6 +61,18 @@ SIGNATURES = {
     "cpfn_extract_patches_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "cpfn_extract_patches": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_size_t, c_void_p]),
+    "cpfn_merge_inverse_bytes": (c_size_t, [c_int, c_int]),
+    "cpfn_merge_inverse_index": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "cpfn_merge_similarity_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "cpfn_merge_similarity": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                      c_void_p, c_void_p, c_size_t, c_void_p]),
+    "cpfn_heuristic_merging_host": (c_int, [c_void_p, c_void_p, ctypes.c_int64, c_void_p, ctypes.c_int64, c_void_p]),
+    "cpfn_merge_solve_host": (c_int, [c_void_p, ctypes.c_int64, ctypes.c_double, c_void_p, c_void_p]),
+    "cpfn_merge_point_labels": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                        c_int, c_int, c_void_p, c_void_p]),
+    "cpfn_merge_dense_labels": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "cpfn_merge_normals_types": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                         c_int, c_void_p, c_void_p, c_void_p]),
     "cpfn_mlp_packed_bytes": (c_size_t, [c_int, c_int]),
     "cpfn_mlp_pack_weights_host": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "cpfn_mlp_chain": (c_int, [c_void_p, c_void_p]),

@@ -10,8 +10,9 @@ Two levels:
                 reference's own Python modules run on top of libcpfn_b200.so.  Needs the reference
                 tree on sys.path.
   level="full"  the module API (B2) and the fitter API (B3) are replaced as well; the reference tree
-                is not needed for the hot path.  ``Utils.sampling_utils`` (patch extraction, row f2) is
-                replaced too; the rest of the reference's ``Utils`` package is left alone.
+                is not needed for the hot path.  ``Utils.sampling_utils`` (patch extraction, row f2) and
+                ``Utils.merging_utils`` (patch -> object merging, row f1) are replaced too; the rest of the
+                reference's ``Utils`` package is left alone.
 """
 import sys
 import types
@@ -53,15 +54,17 @@ def install(level="full"):
     sys.modules.update(table)
     # Patch extraction: only the one module of the reference's ``Utils`` package is
     # replaced -- the package itself (config loader, dataset utilities, ...) stays the reference's.
-    from . import sampling_utils
+    from . import merging_utils, sampling_utils
     sys.modules["Utils.sampling_utils"] = sampling_utils
+    sys.modules["Utils.merging_utils"] = merging_utils              # patch -> object merging, row f1
     if "Utils" in sys.modules:
         sys.modules["Utils"].sampling_utils = sampling_utils
+        sys.modules["Utils"].merging_utils = merging_utils
 
 
 def uninstall():
     for name in [n for n in sys.modules if n == "PointNet2" or n.startswith("PointNet2.") or n == "SPFN"
-                 or n.startswith("SPFN.") or n == "Utils.sampling_utils"]:
+                 or n.startswith("SPFN.") or n in ("Utils.sampling_utils", "Utils.merging_utils")]:
         mod = sys.modules[name]
         if getattr(mod, "__name__", "").startswith("cpfn_b200") or name == "PointNet2":
             del sys.modules[name]

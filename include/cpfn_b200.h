@@ -250,6 +250,52 @@ CPFN_API int cpfn_extract_patches(const float *hr_xyz, int N, const float *seeds
                                   int32_t *out_idx, float *out_dist, float *out_radius, void *workspace,
                                   size_t workspace_bytes, cpfn_stream_t stream);
 
+/* ---------------------------------------------------------------------------
+ * Patch -> object merging: Utils/merging_utils.py and the fusion block of
+ * evaluation_localSPFN.py:99-130, without the dense [N_global, nb*Kl+Kg] matrix.
+ * W [nb,Np,Kl] patch memberships, patch_idx int32 [nb,Np] global index of every patch point (unique inside
+ * a patch), S [Ng,Kg] object-level labels as float, M = nb*Kl + Kg.
+ * ------------------------------------------------------------------------- */
+
+/* inv int32 [nb,Ng]: inv[b,p] = position of global point p in patch b, or -1. */
+CPFN_API size_t cpfn_merge_inverse_bytes(int nb, int Ng);
+CPFN_API int cpfn_merge_inverse_index(const int32_t *patch_idx, int nb, int Np, int Ng, int32_t *inv,
+                                      cpfn_stream_t stream);
+
+/* similarity_soft (merging_utils.py:6-15): out [M,M] = A^T A, fp64 accumulation; Kl, Kg <= 32. */
+CPFN_API size_t cpfn_merge_similarity_workspace_bytes(int nb, int Kl, int Kg);
+CPFN_API int cpfn_merge_similarity(const float *W, const int32_t *patch_idx, const float *S, const int32_t *inv,
+                                   int nb, int Np, int Kl, int Ng, int Kg, float *out, void *workspace,
+                                   size_t workspace_bytes, cpfn_stream_t stream);
+
+/* heuristic_merging (merging_utils.py:17-33), HOST arrays: pairs int64 [P,2], penalty f64 [P],
+ * patch_id int64 [n_nodes] -> segment_id int64 [n_nodes].  Same result as the reference's
+ * repeated-argmax loop in one pass over the stably sorted pairs. */
+CPFN_API int cpfn_heuristic_merging_host(const int64_t *pairs, const double *penalty, int64_t n_pairs,
+                                         const int64_t *patch_id, int64_t n_nodes, int64_t *segment_id);
+
+/* The pair list of run_heuristic_solver (merging_utils.py:37-39: similarity > threshold, i < j, np.where order)
+ * taken straight from the HOST matrix similarity f64 [n_nodes,n_nodes], then the same greedy merge. */
+CPFN_API int cpfn_merge_solve_host(const double *similarity, int64_t n_nodes, double threshold,
+                                   const int64_t *patch_id, int64_t *segment_id);
+
+/* Fused evaluation_localSPFN.py:103-111 + get_point_final (merging_utils.py:46-50): labels int32 [M] in
+ * [0,L), label_weight f32 [L] = 1/(members+1e-10); out [Ng,L].  Points inside a patch drop the object block. */
+CPFN_API int cpfn_merge_point_labels(const float *W, const float *S, const int32_t *inv, const int32_t *labels,
+                                     const float *label_weight, int nb, int Np, int Kl, int Ng, int Kg, int L,
+                                     float *out, cpfn_stream_t stream);
+
+/* get_point_final on a dense A [Ng,M] (the reference's own call signature). */
+CPFN_API int cpfn_merge_dense_labels(const float *A, const int32_t *labels, const float *label_weight, int Ng, int M,
+                                     int L, float *out, cpfn_stream_t stream);
+
+/* Merged normals / types (evaluation_localSPFN.py:113-130): X [nb,Np,3], T [nb,Np,n_types] summed over the
+ * patches containing a point (ascending patch order), uncovered points take obj_normals [Ng,3] /
+ * obj_types [Ng,n_types]; normals re-normalised, types averaged.  n_types <= 8. */
+CPFN_API int cpfn_merge_normals_types(const float *X, const float *T, const int32_t *inv, const float *obj_normals,
+                                      const float *obj_types, int nb, int Np, int Ng, int n_types, float *out_normals,
+                                      float *out_types, cpfn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

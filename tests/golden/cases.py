@@ -200,3 +200,32 @@ def assert_patches_equivalent(got, ref, hr):
         dr = np.linalg.norm(seed[None] - hr[ref[r]], axis=1)
         assert np.array_equal(dg, dr), r
         assert np.array_equal(np.sort(got[r]), np.sort(ref[r])), r
+
+
+def merging_cases():
+    """name -> dict(W [nb,Np,Kl] soft-maxed memberships, X [nb,Np,3], T [nb,Np,4], idx int64 [nb,Np] (unique per
+    patch), S int64 one-hot [Ng,Kg] object labels, obj_normals, obj_types).  Patches are spatial neighbourhoods of
+    a shape cloud whose memberships follow the cloud's ground-truth primitives (+ noise), so patches overlap,
+    share primitives and leave part of the cloud uncovered -- the situation the merge is built for."""
+    out = {}
+    for name, Ng, nb, Np, Kl, Kg, seed in (("small", 3000, 5, 512, 6, 7, 11), ("wide", 6000, 9, 700, 21, 28, 12),
+                                           ("one_patch", 1500, 1, 256, 4, 5, 13)):
+        rng = np.random.RandomState(seed)
+        P, Xn, _, I = synth.shape_batch(1, Ng, seed=seed)
+        P, Xn, I = P[0], Xn[0], I[0]
+        idx = np.empty((nb, Np), np.int64)
+        W = np.empty((nb, Np, Kl), np.float32)
+        for b in range(nb):
+            c = P[rng.randint(Ng)]
+            idx[b] = np.argsort(np.linalg.norm(P - c[None], axis=1), kind="stable")[:Np]
+            local = I[idx[b]] % Kl                                   # local slot of the point's primitive
+            logits = 6.0 * np.eye(Kl, dtype=np.float32)[local] + rng.randn(Np, Kl).astype(np.float32)
+            e = np.exp(logits - logits.max(1, keepdims=True))
+            W[b] = e / e.sum(1, keepdims=True)
+        Xp = Xn[idx] + 0.05 * rng.randn(nb, Np, 3).astype(np.float32)
+        Xp /= np.linalg.norm(Xp, axis=2, keepdims=True)
+        T = rng.randn(nb, Np, 4).astype(np.float32)
+        S = np.eye(Kg, dtype=np.int64)[I % Kg]
+        out[name] = dict(W=W, X=Xp.astype(np.float32), T=T, idx=idx, S=S, obj_normals=Xn.astype(np.float32),
+                         obj_types=rng.randn(Ng, 4).astype(np.float32))
+    return out

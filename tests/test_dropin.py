@@ -25,6 +25,14 @@ def test_full_install_maps_reference_names(built_lib):
         assert fitter_factory.primitive_name_to_id("plane") == 1 and fitter_factory.get_n_registered_primitives() == 4
         assert callable(cone_fitter.compute_parameters) and callable(losses_implementation.compute_parameters)
         import inspect
+        mu = sys.modules["Utils.merging_utils"]                 # evaluation_localSPFN.py:101-102,111
+        assert mu is cpfn_b200.merging_utils
+        for fn, args in (("similarity_soft", ["spfn_labels", "predicted_labels", "point_indices"]),
+                         ("heuristic_merging", ["pairs_id", "patch_id", "penalty_value"]),
+                         ("run_heuristic_solver", ["similarity_matrix", "nb_patches", "max_label_per_object",
+                                                   "max_label_per_patch", "threshold"]),
+                         ("get_point_final", ["point2primitive_prediction", "output_labels_heuristic"])):
+            assert list(inspect.signature(getattr(mu, fn)).parameters)[:len(args)] == args, fn
         su = sys.modules["Utils.sampling_utils"]                # evaluation_PatchSelection.py:14,87
         assert su is cpfn_b200.sampling_utils
         assert list(inspect.signature(su.sample).parameters)[:5] == ["gt_points_lr", "gt_points_hr", "pool_indices",
