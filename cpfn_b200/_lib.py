@@ -73,6 +73,10 @@ SIGNATURES = {
     "cpfn_merge_dense_labels": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "cpfn_merge_normals_types": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                          c_int, c_void_p, c_void_p, c_void_p]),
+    "cpfn_primitive_residues": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_longlong, ctypes.c_longlong, c_int, c_int,
+                                        c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "cpfn_p_coverage": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,
+                                c_void_p, c_void_p]),
     "cpfn_mlp_packed_bytes": (c_size_t, [c_int, c_int]),
     "cpfn_mlp_pack_weights_host": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "cpfn_mlp_chain": (c_int, [c_void_p, c_void_p]),

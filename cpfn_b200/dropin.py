@@ -50,6 +50,7 @@ def install(level="full"):
         "SPFN.cylinder_fitter": cylinder_fitter, "SPFN.cone_fitter": cone_fitter,
         "SPFN.fitter_factory": fitter_factory, "SPFN.losses_implementation": losses_implementation,
         "SPFN.differentiable_tls": spfn.differentiable_tls, "SPFN.geometry_utils": spfn.geometry_utils,
+        "SPFN.metric_implementation": spfn.metric_implementation,
     }
     sys.modules.update(table)
     # Patch extraction: only the one module of the reference's ``Utils`` package is

@@ -296,6 +296,34 @@ CPFN_API int cpfn_merge_normals_types(const float *X, const float *T, const int3
                                       const float *obj_types, int nb, int Np, int Ng, int n_types, float *out_normals,
                                       float *out_types, cpfn_stream_t stream);
 
+/* ---------------------------------------------------------------------------
+ * Point-to-primitive residues (SURVEY 8a row a14 + the residue part of 8f row f3).
+ * Parameter tensors as in the dictionary of compute_parameters: [B,Kp,3] / [B,Kp], contiguous; a NULL
+ * pointer is allowed for a type that is not requested.  Class ids: 0 plane, 1 sphere, 2 cylinder, 3 cone.
+ * ------------------------------------------------------------------------- */
+typedef struct cpfn_primitive_params {
+  const float *plane_normal, *plane_center;
+  const float *sphere_center, *sphere_radius_squared;
+  const float *cylinder_axis, *cylinder_center, *cylinder_radius_squared;
+  const float *cone_apex, *cone_axis, *cone_half_angle;
+} cpfn_primitive_params_t;
+
+/* compute_residue_loss (SPFN/losses_implementation.py:351-387) with *_fitter.compute_residue_single:
+ * matching int32 [B,K] selects the parameter slot of every primitive; points: the primitive's n_pts points at
+ * points + b*stride_b + k*stride_k (floats; stride_k = 0 shares one cloud between all primitives, as
+ * compute_P_coverage does); class_ids[T] = the requested types in output order (T <= 4).
+ * per_point [B,K,n_pts,T] (NULL to skip), mean [B,K,T] = torch.mean(residue_per_point, dim=2) (NULL to skip). */
+CPFN_API int cpfn_primitive_residues(const cpfn_primitive_params_t *params, const int32_t *matching, const float *points,
+                                     long long stride_b, long long stride_k, int B, int Kp, int K, int n_pts,
+                                     const int *class_ids, int T, float *per_point, float *mean, cpfn_stream_t stream);
+
+/* compute_P_coverage (SPFN/metric_implementation.py:409-415) without the [B,K,N,T] intermediate:
+ * count[b,e] = #points of P [B,N,3] whose smallest sqrt_safe(residue) over the K primitives (each with its own
+ * class prim_class int32 [B,K]) is below epsilons_host[e] (HOST array, n_eps <= 4).  Coverage = count / N. */
+CPFN_API int cpfn_p_coverage(const cpfn_primitive_params_t *params, const int32_t *matching, const int32_t *prim_class,
+                             const float *P, int B, int Kp, int K, int N, const float *epsilons_host, int n_eps,
+                             float *count, cpfn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

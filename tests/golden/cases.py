@@ -229,3 +229,27 @@ def merging_cases():
         out[name] = dict(W=W, X=Xp.astype(np.float32), T=T, idx=idx, S=S, obj_normals=Xn.astype(np.float32),
                          obj_types=rng.randn(Ng, 4).astype(np.float32))
     return out
+
+
+def residue_case(seed=21, B=2, K=6, Kp=6, n_pts=96, N=700):
+    """Seeded inputs of compute_residue_loss / compute_P_coverage: plausible primitive parameters (unit normals and
+    axes, positive radii, half angles inside the clamp), a permutation-like matching with repeats, points around the
+    unit ball, one primitive with a point exactly on the cone apex (the F.normalize eps branch)."""
+    rng = np.random.RandomState(seed)
+    unit = lambda a: (a / np.linalg.norm(a, axis=-1, keepdims=True)).astype(np.float32)
+    params = {
+        "plane_normal": unit(rng.randn(B, Kp, 3)), "plane_center": rng.randn(B, Kp).astype(np.float32) * 0.3,
+        "sphere_center": rng.randn(B, Kp, 3).astype(np.float32) * 0.3,
+        "sphere_radius_squared": (rng.rand(B, Kp).astype(np.float32) * 0.5 + 0.01),
+        "cylinder_axis": unit(rng.randn(B, Kp, 3)), "cylinder_center": rng.randn(B, Kp, 3).astype(np.float32) * 0.3,
+        "cylinder_radius_squared": (rng.rand(B, Kp).astype(np.float32) * 0.3 + 0.01),
+        "cone_apex": rng.randn(B, Kp, 3).astype(np.float32) * 0.5, "cone_axis": unit(rng.randn(B, Kp, 3)),
+        "cone_half_angle": (rng.rand(B, Kp).astype(np.float32) * 1.2 + 0.1),
+    }
+    params["sphere_radius_squared"][0, 0] = -0.04              # sqrt_safe takes |x|
+    matching = rng.randint(0, Kp, (B, K)).astype(np.int64)
+    points = (rng.randn(B, K, n_pts, 3) * 0.5).astype(np.float32)
+    points[0, 1, 0] = params["cone_apex"][0, matching[0, 1]]   # v = 0
+    T_gt = rng.randint(0, 4, (B, K)).astype(np.int64)
+    P = (rng.randn(B, N, 3) * 0.5).astype(np.float32)
+    return params, matching, points, T_gt, P
