@@ -25,8 +25,7 @@ def load(name, overrides):
     if name in _loaded:
         return _loaded[name]
     path = find(name)
-    if path is None:
-        _loaded[name] = None
+    if path is None:                      # not cached: the checkout may be put on sys.path later
         return None
     spec = importlib.util.spec_from_file_location("cpfn_b200.spfn._ref_" + name, path)
     mod = importlib.util.module_from_spec(spec)
