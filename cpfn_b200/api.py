@@ -206,3 +206,51 @@ class GlobalSPFN:
             d2h += v.numel() * v.element_size()
         torch.cuda.current_stream(self.device).synchronize()
         return res, P_host.numel() * 4, d2h
+
+
+class LocalSPFN:
+    """One shape through the LocalSPFN inference path of evaluation_localSPFN.py: patches of the high-resolution
+    cloud (the k nearest points of every seed, Utils/sampling_utils.py) -> per-patch normalisation
+    (Dataset/dataloaders.py:249-253) -> the PointNet2 backbone with K = n_max_local_instances slots on the patches
+    as the batch dimension (:95-97) -> patch-to-object merging with the object-level prediction
+    (:99-130, Utils/merging_utils.py).  Everything between the seeds and the merged result stays on the device;
+    the greedy label merge is the one host step (as in the reference)."""
+
+    def __init__(self, n_max_local_instances=21, n_types=4, device="cuda:0", num_points_patch=8192):
+        self.engine = GlobalSPFN(output_sizes=(3, n_types, n_max_local_instances), device=device)
+        self.device = self.engine.device
+        self.num_points_patch = int(num_points_patch)
+
+    def load_state_dict(self, sd, strict=True):
+        return self.engine.load_state_dict(sd, strict=strict)
+
+    @staticmethod
+    def normalise_patches(P_global, patch_indices):
+        """dataloaders.py:249-253: centre every patch on its mean and scale it into the unit ball."""
+        P = P_global[patch_indices.long()]
+        P = P - P.mean(dim=1, keepdim=True)
+        return P / P.norm(dim=2, keepdim=True).amax(dim=1, keepdim=True)
+
+    @torch.no_grad()
+    def run_shape(self, P_global, spfn_labels, spfn_normals, spfn_type, seeds=None, patch_indices=None, dropout=True,
+                  graphed=False, threshold=0):
+        """P_global [Ng,3]; object-level prediction spfn_labels [Ng,Kg], spfn_normals [Ng,3], spfn_type [Ng,n_types];
+        either ``seeds`` [S,3] (patches are extracted here) or ``patch_indices`` int [nb,Np].  Returns a dict with
+        W_fusion [Ng,L], X_global [Ng,3], T_global [Ng,n_types], labels (numpy int64) and patch_indices."""
+        from . import merging_utils, sampling_utils
+        P_global = P_global.to(self.device, torch.float32).contiguous()
+        if patch_indices is None:
+            if seeds is None:
+                raise ValueError("run_shape needs seeds or patch_indices")
+            patch_indices = sampling_utils.extract_patches(P_global, seeds.to(self.device, torch.float32),
+                                                           self.num_points_patch)
+        patch_indices = patch_indices.to(self.device)
+        if patch_indices.shape[0] == 0:                       # evaluation_localSPFN.py:131-135: nothing to merge
+            raise ValueError("run_shape needs at least one patch (the reference falls back to the object-level labels)")
+        P = self.normalise_patches(P_global, patch_indices)
+        out = (self.engine.forward_graphed if graphed else self.engine.forward)(P, dropout=dropout, fit=False)
+        W_fusion, X_global, T_global, labels = merging_utils.merge_shape(
+            out["W"], out["X"], out["T"], patch_indices, spfn_labels.to(self.device), spfn_normals.to(self.device),
+            spfn_type.to(self.device), threshold=threshold)
+        return {"W_fusion": W_fusion, "X_global": X_global, "T_global": T_global, "labels": labels,
+                "patch_indices": patch_indices, "W": out["W"], "X": out["X"], "T": out["T"]}

@@ -155,3 +155,42 @@ def test_ragged_point_counts(engine, cuda_dev, n_points):
     d = eng.forward(torch.from_numpy(P).to(cuda_dev), dropout=True)
     kept = d["output_feat"] != 0
     assert torch.allclose(d["output_feat"][kept], 2 * out["output_feat"][kept], rtol=1e-5, atol=1e-6)   # mask is 0 or 2
+
+
+def test_localspfn_shape_pipeline(cuda_dev):
+    """Seeds -> patches -> normalisation -> LocalSPFN -> merge for one shape (api.LocalSPFN.run_shape): the glue is
+    checked against the numpy oracle of every step, fed with the engine's own per-patch predictions."""
+    from cpfn_b200 import synth
+    from oracle import merging as omerge, patches as opatch
+    Ng, nb, Np, Kl, Kg = 6000, 4, 1024, 21, 28
+    P, Xn, _, I = synth.shape_batch(1, Ng, seed=77)
+    P, Xn, I = P[0].astype(np.float32), Xn[0].astype(np.float32), I[0]
+    rng = np.random.RandomState(5)
+    seeds = P[rng.choice(Ng, nb, replace=False)]
+    S = np.eye(Kg, dtype=np.int64)[I % Kg]
+    obj_types = rng.randn(Ng, 4).astype(np.float32)
+    loc = api.LocalSPFN(n_max_local_instances=Kl, device=cuda_dev, num_points_patch=Np)
+    t = lambda a: torch.from_numpy(a).to(cuda_dev)
+    res = loc.run_shape(t(P), t(S), t(Xn), t(obj_types), seeds=t(seeds), dropout=False)
+    idx = res["patch_indices"].cpu().numpy()
+    assert idx.shape == (nb, Np)
+    for b in range(nb):
+        assert np.array_equal(idx[b], opatch.nearest(seeds[b], P, Np)[0])
+    Pn = P[idx] - P[idx].mean(axis=1, keepdims=True)                        # dataloaders.py:249-253
+    Pn = Pn / np.linalg.norm(Pn, axis=2, keepdims=True).max(axis=1, keepdims=True)
+    got = api.LocalSPFN.normalise_patches(t(P), res["patch_indices"]).cpu().numpy()
+    assert np.abs(got - Pn).max() < 1e-5                                     # fp32 means, different summation order
+    W, X, T = (res[k].cpu().numpy() for k in ("W", "X", "T"))
+    assert W.shape == (nb, Np, Kl) and np.allclose(W.sum(2), 1.0, atol=1e-5)
+    from cpfn_b200 import merging_utils
+    sim = merging_utils.similarity_soft(t(S), res["W"], res["patch_indices"]).cpu().numpy()
+    exact = omerge.similarity_soft(S, W, idx.astype(np.int64), dtype=np.float64)
+    assert np.abs(sim - exact).max() <= 1e-6 * np.abs(exact).max()
+    labels = omerge.run_heuristic_solver(sim, nb, Kg, Kl)     # the literal greedy loop on the same matrix
+    assert np.array_equal(res["labels"], labels)
+    fused = omerge.fuse_patches(S, W, idx.astype(np.int64), labels)
+    assert res["W_fusion"].shape == fused.shape and np.abs(res["W_fusion"].cpu().numpy() - fused).max() <= 1e-6
+    Xo, To = omerge.merge_normals_types(X, T, idx.astype(np.int64), Xn, obj_types)
+    assert np.array_equal(res["X_global"].cpu().numpy(), Xo) and np.array_equal(res["T_global"].cpu().numpy(), To)
+    res_g = loc.run_shape(t(P), t(S), t(Xn), t(obj_types), patch_indices=res["patch_indices"], dropout=False, graphed=True)
+    assert np.array_equal(res_g["labels"], labels) and torch.equal(res_g["X_global"], res["X_global"])
