@@ -324,6 +324,22 @@ CPFN_API int cpfn_p_coverage(const cpfn_primitive_params_t *params, const int32_
                              const float *P, int B, int Kp, int K, int N, const float *epsilons_host, int n_eps,
                              float *count, cpfn_stream_t stream);
 
+/* ---------------------------------------------------------------------------
+ * Farthest point sampling of ONE large cloud with the semantics of the reference's preprocessing
+ * (Preprocessing/preprocessing_sampling_lowres.py:14-42) -- not those of the pointnet2 op:
+ * true distances, first-index tie-break, seeds / labels.
+ *   labels == NULL : furthest_point_sampling(points, seeds, n_out): the seeds (int32 [n_seeds], may be NULL) only
+ *                    start with distance 0; out = the n_out successive arg-max indices.
+ *   labels != NULL : furthest_point_sampling_per_label(points, labels): out[0] = start_index (the reference draws it
+ *                    with np.random.randint), after every pick the points of the picked label drop out; n_out = the
+ *                    number of distinct labels.
+ * points f32 [N,3], N <= 8 * 1024 * SM count; cooperative launch over the whole GPU.
+ * ------------------------------------------------------------------------- */
+CPFN_API size_t cpfn_fps_dense_workspace_bytes(void);
+CPFN_API int cpfn_fps_dense(const float *points, int N, const int32_t *labels, const int32_t *seeds, int n_seeds,
+                            int start_index, int n_out, int32_t *out, void *workspace, size_t workspace_bytes,
+                            cpfn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -253,3 +253,17 @@ def residue_case(seed=21, B=2, K=6, Kp=6, n_pts=96, N=700):
     T_gt = rng.randint(0, 4, (B, K)).astype(np.int64)
     P = (rng.randn(B, N, 3) * 0.5).astype(np.float32)
     return params, matching, points, T_gt, P
+
+
+def lowres_cases():
+    """name -> (points float32 [N,3], labels int32 [N], nb_query_points, np.random seed).  Shape clouds with their
+    ground-truth primitive labels; 'lattice' has many exactly equal distances (first-maximum tie-break) and
+    duplicated points."""
+    out = {}
+    for name, N, m, seed in (("small", 3000, 200, 31), ("mid", 20000, 512, 32)):
+        P, _, _, I = synth.shape_batch(1, N, seed=seed)
+        out[name] = (P[0].astype(np.float32), I[0].astype(np.int32), m, 200 + seed)
+    lat = synth.lattice_cloud(1, 2048, seed=9)[0].astype(np.float32)
+    lat = np.concatenate([lat, lat[:100]])
+    out["lattice"] = (lat, (np.arange(len(lat)) % 7).astype(np.int32), 150, 233)
+    return out
