@@ -212,8 +212,8 @@ def run_ours(args):
     barrier()
     t0 = time.perf_counter()
     h2d = d2h = 0
+    torch.manual_seed(2000)
     for i in range(args.steps):
-        torch.manual_seed(2000 + i)
         _, h2d, d2h = eng.run_host(host_inputs[i % n_in], graphed=use_graph)
     barrier()
     e2e_s = time.perf_counter() - t0

@@ -72,6 +72,7 @@ struct ChainP {
   const float *b_src; int b_ch, b_rows; const float *nn_w;
   int out_mode; float *out; int ldo, pool_g;
   const float *l0_w, *l0_b; int l0_cout;   // GROUP mode without features: first layer (3 -> l0_cout) on CUDA cores
+  const float *in_bias;                    // INTERP mode: relu(interpolated + in_bias) enters layer 0
   int act_bytes0, act_bytes1, nstage, tmem_cols;
 };
 
@@ -300,6 +301,11 @@ __device__ void load_tile(const ChainP &p, uint32_t buf, long long col0, int w8,
           o.y = __fmaf_rn(f[u][2].y, w[u][2], __fmaf_rn(f[u][0].y, w[u][0], __fmul_rn(f[u][1].y, w[u][1])));
           o.z = __fmaf_rn(f[u][2].z, w[u][2], __fmaf_rn(f[u][0].z, w[u][0], __fmul_rn(f[u][1].z, w[u][1])));
           o.w = __fmaf_rn(f[u][2].w, w[u][2], __fmaf_rn(f[u][0].w, w[u][0], __fmul_rn(f[u][1].w, w[u][1])));
+          if (p.in_bias != nullptr) {      // the layer in front of the interpolation: its bias and ReLU
+            const float4 bb = __ldg(reinterpret_cast<const float4 *>(p.in_bias) + c4);
+            o.x = ok[u] ? fmaxf(o.x + bb.x, 0.f) : 0.f; o.y = ok[u] ? fmaxf(o.y + bb.y, 0.f) : 0.f;
+            o.z = ok[u] ? fmaxf(o.z + bb.z, 0.f) : 0.f; o.w = ok[u] ? fmaxf(o.w + bb.w, 0.f) : 0.f;
+          }
           store_quad<NT>(buf, r, a4 + c4, o);
         }
       }
@@ -994,6 +1000,8 @@ int launch_chain(const cpfn_mlp_chain_t *c, cudaStream_t st) {
   if (c->in_mode == CPFN_MLP_IN_GROUP) width += 3;
   else if (c->in_mode == CPFN_MLP_IN_INTERP) width += c->b_ch;
   p.l0_w = c->l0_w; p.l0_b = c->l0_b; p.l0_cout = c->l0_cout;
+  p.in_bias = c->in_bias;
+  if (c->in_bias != nullptr && c->in_mode != CPFN_MLP_IN_INTERP) return CPFN_EINVAL;
   if (c->l0_w != nullptr) {
     if (c->in_mode != CPFN_MLP_IN_GROUP || c->a_ch != 0 || !c->l0_b || c->l0_cout <= 0 || (c->l0_cout & 3)) return CPFN_EINVAL;
     width = c->l0_cout;

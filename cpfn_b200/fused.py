@@ -39,7 +39,8 @@ class _Chain(ctypes.Structure):
                 ("nn_w", ctypes.c_void_p),
                 ("out_mode", ctypes.c_int32), ("out", ctypes.c_void_p), ("ldo", ctypes.c_int32),
                 ("pool_g", ctypes.c_int32), ("split_cout", ctypes.c_int32),
-                ("l0_w", ctypes.c_void_p), ("l0_b", ctypes.c_void_p), ("l0_cout", ctypes.c_int32)]
+                ("l0_w", ctypes.c_void_p), ("l0_b", ctypes.c_void_p), ("l0_cout", ctypes.c_int32),
+                ("in_bias", ctypes.c_void_p)]
 
 
 def available():
@@ -102,7 +103,7 @@ class PackedChain:
 def run_chain(pc, B, cols_per_cloud, out, ldo, tile_cols=128, in_mode=IN_DENSE, a_src=None, a_ch=0, a_rows=0,
               idx=None, xyz=None, centers=None, group_k=0, b_src=None, b_ch=0, b_rows=0, nn_w=None,
               out_mode=OUT_ROWS, pool_g=0, biases=None, bias_per_cloud=(), masks=None, out_cm=None, split_cout=False,
-              l0=None):
+              l0=None, in_bias=None):
     """Enqueue one fused chain on torch's current stream."""
     c = _Chain()
     c.n_layers = len(pc.dims)
@@ -125,6 +126,8 @@ def run_chain(pc, B, cols_per_cloud, out, ldo, tile_cols=128, in_mode=IN_DENSE, 
     c.split_cout = int(split_cout)
     if l0 is not None:
         c.l0_w, c.l0_b, c.l0_cout = l0[0].data_ptr(), l0[1].data_ptr(), l0[0].shape[0]
+    if in_bias is not None:
+        c.in_bias = in_bias.data_ptr()
     with torch.cuda.device(out.device):
         _lib.check(_lib.lib().cpfn_mlp_chain(ctypes.byref(c), torch.cuda.current_stream(out.device).cuda_stream),
                    "mlp_chain")
@@ -321,10 +324,12 @@ def sa_forward_pm(module, xyz, feats_pm, indices=None):
     return new_xyz, out
 
 
-def _fp_chain(module, device, split=None):
+def _fp_chain(module, device, split=None, tail=None):
     """split = number of leading input channels of layer 0 that are a per-cloud constant
-    (FP1: the broadcast global feature) -> returns (chain without them, const-part weight)."""
-    key = _CACHE_ATTR + ("_s%d_%d" % split if split else "")
+    (FP1: the broadcast global feature) -> returns (chain without them, const-part weight).
+    tail = (W [cout,cin] numpy, tag): one more layer without bias / ReLU appended to the chain -- the linear part
+    of the NEXT module's first layer, applied here once per source row (see pointnet2_forward)."""
+    key = _CACHE_ATTR + ("_s%d_%d" % split if split else "") + ("_t" + tail[1] if tail else "")
     pc = getattr(module, key, None)
     if pc is None or pc[0].weights.device != device:
         layers, wconst = [], None
@@ -336,12 +341,14 @@ def _fp_chain(module, device, split=None):
                           torch.from_numpy(np.ascontiguousarray(b)).to(device))
                 w = np.concatenate([w[:, :split[0]], w[:, split[1]:]], axis=1)
             layers.append((w, b, True))
+        if tail is not None:
+            layers.append((np.ascontiguousarray(tail[0], dtype=np.float32), np.zeros(tail[0].shape[0], np.float32), False))
         pc = (PackedChain(layers, device), wconst)
         setattr(module, key, pc)
     return pc
 
 
-def fp_forward_pm(module, xyz1, xyz2, feats1_pm, feats2_pm, nn=None):
+def fp_forward_pm(module, xyz1, xyz2, feats1_pm, feats2_pm, nn=None, tail=None):
     """Point-major feature propagation.  xyz1 [B,N,3], xyz2 [B,S,3] | None, feats1_pm [B,N,D1] | None,
     feats2_pm [B,S,D2] -> [B,N,D']."""
     B, N, _ = xyz1.shape
@@ -364,7 +371,7 @@ def fp_forward_pm(module, xyz1, xyz2, feats1_pm, feats2_pm, nn=None):
             run_chain(pc, B, N, out, out.shape[2], tile_cols=tile, biases=[bias0] + [None] * (len(pc.dims) - 1),
                       bias_per_cloud=(0,), **first)
         return out
-    pc, _ = _fp_chain(module, dev)
+    pc, _ = _fp_chain(module, dev, tail=tail)
     w, idx = nn if nn is not None else three_nn_weights(xyz1, xyz2)
     out = torch.empty(B, N, pc.dims[-1][1], dtype=torch.float32, device=dev)
     run_chain(pc, B, N, out, out.shape[2], tile_cols=pick_tile(pc.dims, N), in_mode=IN_INTERP, a_src=feats1_pm, a_ch=D1, a_rows=N,
@@ -409,18 +416,26 @@ def feature_propagation_forward(module, pos1, pos2, feats1, feats2):
 
 
 def _head_chain(model, device):
+    """FP3 (from its second layer on) + fc1 + bn1 + ReLU + the heads as ONE chain.  FP3's input is the 3-NN
+    interpolation of l5 alone (pn2_network.py:58: feats1 is None), so its first layer commutes with the
+    interpolation: W1 (sum_j w_j f_j) = sum_j w_j (W1 f_j).  W1 (BatchNorm folded) is applied to the 512 rows of
+    l5 per cloud as one more layer of FP2's chain instead of to the 8192 interpolated rows; the bias and the ReLU
+    are applied where the rows are interpolated (``in_bias``).  Returns (chain, head sizes, W1, b1)."""
     pc = getattr(model, _CACHE_ATTR, None)
     if pc is None or pc[0].weights.device != device:
-        layers = []
-        for conv, bn in zip(model.sfp3.mlp_convs, model.sfp3.mlp_bns):
+        layers, first = [], None
+        for j, (conv, bn) in enumerate(zip(model.sfp3.mlp_convs, model.sfp3.mlp_bns)):
             w, b = fold_bn(conv.weight, conv.bias, bn)
-            layers.append((w, b, True))
+            if j == 0:
+                first = (w, torch.from_numpy(np.ascontiguousarray(b, dtype=np.float32)).to(device))
+            else:
+                layers.append((w, b, True))
         w, b = fold_bn(model.fc1.weight, model.fc1.bias, model.bn1)
         layers.append((w, b, True))
         hw = np.concatenate([fold_bn(fc.weight, fc.bias, None)[0] for fc in model.fc2], axis=0)
         hb = np.concatenate([fold_bn(fc.weight, fc.bias, None)[1] for fc in model.fc2], axis=0)
         layers.append((hw, hb, False))
-        pc = (PackedChain(layers, device), [fc.out_channels for fc in model.fc2])
+        pc = (PackedChain(layers, device), [fc.out_channels for fc in model.fc2], first[0], first[1])
         setattr(model, _CACHE_ATTR, pc)
     return pc
 
@@ -459,8 +474,8 @@ def pointnet2_forward(model, P, dropout=True):
     l2_xyz, l2 = sa_forward_pm(model.sa2, l1_xyz, l1, indices=idx2)
     _, l3 = sa_forward_pm(model.sa3, l2_xyz, l2)
     l4 = fp_forward_pm(model.sfp1, l2_xyz, None, l2, l3)
-    l5 = fp_forward_pm(model.sfp2, l1_xyz, l2_xyz, l1, l4, nn=nn2)
-    pc, head_sizes = _head_chain(model, dev)
+    pc, head_sizes, w_fp3, b_fp3 = _head_chain(model, dev)
+    l5 = fp_forward_pm(model.sfp2, l1_xyz, l2_xyz, l1, l4, nn=nn2, tail=(w_fp3, "fp3"))      # = W1_fp3 @ (FP2 output)
     n_out = sum(head_sizes)
     w, idx = nn3
     heads = torch.empty(B, N, n_out, dtype=torch.float32, device=dev)
@@ -468,7 +483,8 @@ def pointnet2_forward(model, P, dropout=True):
     fc1_layer = len(pc.dims) - 2
     masks = {fc1_layer: mask} if mask is not None else None
     run_chain(pc, B, N, heads, n_out, tile_cols=pick_tile(pc.dims, N, need_cloud_aligned=True, name='HEAD'), in_mode=IN_INTERP, a_src=None, a_ch=0, a_rows=N, idx=idx,
-              b_src=l5, b_ch=l5.shape[2], b_rows=l5.shape[1], nn_w=w, masks=masks, out_cm={fc1_layer: output_feat})
+              b_src=l5, b_ch=l5.shape[2], b_rows=l5.shape[1], nn_w=w, masks=masks, out_cm={fc1_layer: output_feat},
+              in_bias=b_fp3)
     outs, o = [], 0
     for n in head_sizes:
         outs.append(heads[:, :, o:o + n])

@@ -196,6 +196,11 @@ typedef struct {
    * relu(l0_w [l0_cout,3] * (xyz[idx] - centre) + l0_b) evaluated on the CUDA cores while the tile is
    * built; layers[0].cin must then equal l0_cout. */
   const float *l0_w; const float *l0_b; int32_t l0_cout;
+  /* INTERP mode: when non-NULL, relu(interpolated + in_bias[b_ch]) is what enters layer 0.  A layer in front
+   * of the interpolation is linear in the rows it interpolates, W (sum_j w_j f_j) = sum_j w_j (W f_j): the caller
+   * applies that layer's W once per SOURCE row and its bias + ReLU here, per interpolated row
+   * (pointset_feature_propagation.py:36-51 for FP3, whose input is the interpolation alone). */
+  const float *in_bias;
 } cpfn_mlp_chain_t;
 
 /* Replaces the conv+BN+ReLU(+max) chains of pointset_abstraction.py:61-74,
