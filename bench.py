@@ -206,23 +206,37 @@ def run_ours(args):
     t_wall = time.perf_counter() - t_wall0
     launches = cuda_ops.LAUNCHES - launches0
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-    # end-to-end through the public host-buffer API (H2D + forward + fit + D2H every step)
+    # end-to-end through the public host-buffer API (H2D + forward + fit + D2H every step).  Two numbers:
+    # the latency of one synchronous call (run_host) and the throughput of the streaming call (stream_host:
+    # the same work per step with two batches in flight, the next batch's H2D under the current batch's compute)
     for i in range(max(5, args.warmup)):     # first replays of a fresh graph include its upload
         eng.run_host(host_inputs[i % n_in], graphed=use_graph)
     barrier()
+    torch.manual_seed(2000)
     t0 = time.perf_counter()
     h2d = d2h = 0
-    torch.manual_seed(2000)
     for i in range(args.steps):
         _, h2d, d2h = eng.run_host(host_inputs[i % n_in], graphed=use_graph)
     barrier()
-    e2e_s = time.perf_counter() - t0
+    lat_s = time.perf_counter() - t0
+    e2e_s, pipelined = lat_s, False
+    if use_graph:
+        for _ in eng.stream_host(host_inputs[i % n_in] for i in range(max(5, args.warmup))):
+            pass
+        barrier()
+        t0 = time.perf_counter()
+        n_done = 0
+        for _, h2d, d2h in eng.stream_host(host_inputs[i % n_in] for i in range(args.steps)):
+            n_done += 1
+        barrier()
+        e2e_s, pipelined = time.perf_counter() - t0, True
+        assert n_done == args.steps
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    t = torch.tensor([dev_ms, e2e_s * 1e3, lat_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         import torch.distributed as dist
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    dev_ms, e2e_ms, lat_ms = float(t[0]), float(t[1]), float(t[2])
 
     if rank != 0:
         if world > 1:
@@ -292,7 +306,10 @@ def run_ours(args):
                    "sharding": "clouds sharded across ranks, no data-path collective", "fused_mlp": bool(fused.available()),
                    "cuda_graph": bool(use_graph)},
         "e2e": {"value": total_points / (e2e_ms * 1e-3 / args.steps), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
+                "api": "GlobalSPFN.stream_host (two batches in flight; every step does its full H2D, forward, fit, D2H)"
+                       if pipelined else "GlobalSPFN.run_host",
+                "single_call_latency_ms": lat_ms / args.steps},
         "gpu_launches": launches, "wall_ms_per_step_incl_flush": t_wall * 1e3 / args.steps,
         "fits_per_s": 4 * world * B_PER_GPU * K_SLOTS / (ms_per_step * 1e-3),
         "breakdown_us": breakdown, "roofline": roofline,

@@ -101,7 +101,16 @@ class GlobalSPFN:
         tensor (copied straight into the graph's input).  The returned tensors are STATIC buffers that
         the next call overwrites; the always-on dropout still draws a fresh mask per call (torch's
         graph-safe generator)."""
-        key = (tuple(P.shape), bool(dropout), bool(fit))
+        graph, static_in, out, n_launch = self._net_graph(P, dropout, fit, 0)
+        static_in.copy_(P, non_blocking=True)
+        graph.replay()
+        cuda_ops.count_launches(n_launch)
+        return out
+
+    def _net_graph(self, P, dropout, fit, slot):
+        """(graph, its static input, its static outputs, launches) for inputs shaped like P; ``slot`` selects one
+        of several independent copies (own input / output buffers) so that consecutive batches can overlap."""
+        key = (tuple(P.shape), bool(dropout), bool(fit)) + ((slot,) if slot else ())
         entry = self._graphs.get(key)
         if entry is None:
             static_in = torch.empty(tuple(P.shape), dtype=torch.float32, device=self.device)
@@ -109,11 +118,7 @@ class GlobalSPFN:
             graph, out, n = self._capture(lambda: self.forward(static_in, dropout=dropout, fit=fit))
             entry = (graph, static_in, out, n)
             self._graphs[key] = entry
-        graph, static_in, out, n_launch = entry
-        static_in.copy_(P, non_blocking=True)
-        graph.replay()
-        cuda_ops.count_launches(n_launch)
-        return out
+        return entry
 
     @torch.no_grad()
     def _fit_graphed(self, static_in, net_out):
@@ -130,6 +135,67 @@ class GlobalSPFN:
         graph.replay()
         cuda_ops.count_launches(n_launch)
         return res
+
+    @torch.no_grad()
+    def stream_host(self, batches, dropout=True):
+        """``run_host`` over a sequence of pinned host batches of ONE shape, two batches in flight: while batch i
+        is on the SMs, batch i+1's clouds are already crossing PCIe into a second set of graph buffers, and batch
+        i's per-point results travel back under its own fitters.  Every batch still does its full H2D, forward,
+        fit and D2H; only their overlap changes.  Yields (results, h2d_bytes, d2h_bytes) in order; the result
+        tensors of a batch are pinned buffers that are reused two batches later."""
+        from . import fused
+        main = torch.cuda.current_stream(self.device)
+        copy_in = self.__dict__.setdefault("_copy_in", torch.cuda.Stream(device=self.device))
+        copier = fused._side_stream(self.device)
+        free = [None, None]                                   # slot's input may be overwritten after this event
+        sent = [None, None]                                   # slot's per-point outputs have left the device
+        pending = None
+        for i, P_host in enumerate(batches):
+            if not P_host.is_pinned():
+                raise RuntimeError("stream_host needs pinned host tensors (torch.Tensor.pin_memory())")
+            slot = i & 1
+            graph, static_in, out, n_launch = self._net_graph(P_host, dropout, False, slot)
+            if "instance" not in out or self.classes != ['plane', 'sphere', 'cylinder', 'cone']:
+                raise RuntimeError("stream_host supports the SPFN head layout [3, n_types, K <= 64] with all four fitters")
+            with torch.cuda.stream(copy_in):                  # H2D on its own stream, as early as the slot allows
+                if free[slot] is not None:
+                    copy_in.wait_event(free[slot])
+                static_in.copy_(P_host, non_blocking=True)
+                arrived = torch.cuda.Event()
+                arrived.record(copy_in)
+            main.wait_event(arrived)
+            if sent[slot] is not None:
+                main.wait_event(sent[slot])                   # the graph overwrites what that copy reads
+            graph.replay()
+            cuda_ops.count_launches(n_launch)
+            ready = torch.cuda.Event()
+            ready.record(main)
+            res, tag = {}, "s%d_" % slot
+            with torch.cuda.stream(copier):                   # per-point results go home while the fitters run
+                copier.wait_event(ready)
+                for k, v in (("normals", out["X"]), ("instance", out["instance"]), ("type", out["type"])):
+                    res[k] = self._pinned(tag + k, v.shape, v.dtype)
+                    res[k].copy_(v, non_blocking=True)
+                copied = torch.cuda.Event()
+                copied.record(copier)
+            params, packed = self._fit_graphed(static_in, out)
+            hp = self._pinned(tag + "params", packed.shape, packed.dtype)
+            hp.copy_(packed, non_blocking=True)
+            o = 0
+            for k, v in params.items():
+                res[k] = hp[o:o + v.numel()].view(v.shape)
+                o += v.numel()
+            done = torch.cuda.Event()
+            done.record(main)
+            free[slot], sent[slot] = done, copied             # the fitters were the last readers of static_in
+            d2h = packed.numel() * 4 + sum(res[k].numel() * res[k].element_size() for k in ("normals", "instance", "type"))
+            if pending is not None:                           # hand out the previous batch while this one runs
+                pending[1].synchronize(); pending[2].synchronize()
+                yield pending[0], pending[3], pending[4]
+            pending = (res, done, copied, P_host.numel() * 4, d2h)
+        if pending is not None:
+            pending[1].synchronize(); pending[2].synchronize()
+            yield pending[0], pending[3], pending[4]
 
     def _pinned(self, name, shape, dtype):
         t = self._pin.get(name)

@@ -194,3 +194,23 @@ def test_localspfn_shape_pipeline(cuda_dev):
     assert np.array_equal(res["X_global"].cpu().numpy(), Xo) and np.array_equal(res["T_global"].cpu().numpy(), To)
     res_g = loc.run_shape(t(P), t(S), t(Xn), t(obj_types), patch_indices=res["patch_indices"], dropout=False, graphed=True)
     assert np.array_equal(res_g["labels"], labels) and torch.equal(res_g["X_global"], res["X_global"])
+
+
+def test_stream_host_equals_run_host(engine, cuda_dev):
+    """The pipelined host API returns, batch by batch, what the synchronous call returns (dropout off), for more
+    batches than there are buffer slots, and refuses pageable memory."""
+    eng, sd = engine
+    batches = [torch.from_numpy(cases.network_input(seed=60 + i)).pin_memory() for i in range(5)]
+    want = []
+    for P in batches:
+        res, h2d, d2h = eng.run_host(P, dropout=False, graphed=True)
+        want.append({k: v.clone() for k, v in res.items()})
+    n = 0
+    for i, (res, h2d, d2h) in enumerate(eng.stream_host(iter(batches), dropout=False)):
+        assert h2d == batches[i].numel() * 4 and d2h > 0 and set(res) == set(want[i])
+        for k, v in want[i].items():
+            assert torch.equal(res[k], v), (i, k)
+        n += 1
+    assert n == len(batches)
+    with pytest.raises(RuntimeError):
+        list(eng.stream_host([torch.from_numpy(cases.network_input())], dropout=False))
