@@ -206,6 +206,33 @@ def run_ours(args):
     t_wall = time.perf_counter() - t_wall0
     launches = cuda_ops.LAUNCHES - launches0
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    per_op, step_us, clocks = {}, float("nan"), None
+    if rank == 0:
+        # ---- profiling pass (rank 0): per-op device times, dominant kernel, roofline ----
+        timer = OpTimer()
+        originals = [(cuda_ops, n, timer.wrap(cuda_ops, n)) for n in
+                     ("farthest_point_sampling", "ball_query", "three_nn", "three_weighted_sum", "group_points", "gather_points")]
+        originals.append((fitmod, "fit_primitives_packed", timer.wrap(fitmod, "fit_primitives_packed", "fit_primitives")))
+        if fused.available():
+            originals.append((fused, "run_chain", timer.wrap(fused, "run_chain", "mlp_chain")))
+        fused.USE_SIDE_STREAM = False          # serialise the step so that per-op event times are meaningful
+        tot = []
+        for i in range(args.steps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            step(i, graphed=False)
+            b.record()
+            tot.append((a, b))
+        per_op = timer.summary()
+        fused.USE_SIDE_STREAM = True
+        clocks = sampler.stop()
+        step_us = float(np.mean([a.elapsed_time(b) * 1e3 for a, b in tot]))
+        for mod, n, fn in originals:
+            setattr(mod, n, fn)
+        breakdown = {k: round(float(np.sum(v)) / args.steps, 2) for k, v in per_op.items()}
+        breakdown["step_total_serialised_ungraphed"] = round(step_us, 2)
+    barrier()
     # end-to-end through the public host-buffer API (H2D + forward + fit + D2H every step).  Two numbers:
     # the latency of one synchronous call (run_host) and the throughput of the streaming call (stream_host:
     # the same work per step with two batches in flight, the next batch's H2D under the current batch's compute)
@@ -245,30 +272,6 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # ---- profiling pass (rank 0): per-op device times, dominant kernel, roofline ----
-    timer = OpTimer()
-    originals = [(cuda_ops, n, timer.wrap(cuda_ops, n)) for n in
-                 ("farthest_point_sampling", "ball_query", "three_nn", "three_weighted_sum", "group_points", "gather_points")]
-    originals.append((fitmod, "fit_primitives_packed", timer.wrap(fitmod, "fit_primitives_packed", "fit_primitives")))
-    if fused.available():
-        originals.append((fused, "run_chain", timer.wrap(fused, "run_chain", "mlp_chain")))
-    fused.USE_SIDE_STREAM = False          # serialise the step so that per-op event times are meaningful
-    tot = []
-    for i in range(args.steps):
-        flush.zero_()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        step(i, graphed=False)
-        b.record()
-        tot.append((a, b))
-    per_op = timer.summary()
-    fused.USE_SIDE_STREAM = True
-    clocks = sampler.stop()
-    step_us = float(np.mean([a.elapsed_time(b) * 1e3 for a, b in tot]))
-    for mod, n, fn in originals:
-        setattr(mod, n, fn)
-    breakdown = {k: round(float(np.sum(v)) / args.steps, 2) for k, v in per_op.items()}
-    breakdown["step_total_serialised_ungraphed"] = round(step_us, 2)
     # Dominant kernel of ours: SA1 furthest point sampling (one launch per step at N=8192, m=512).
     fps_us = [t_ for t_ in per_op.get("farthest_point_sampling", [])]
     fps_big = fps_us[0::2] if len(fps_us) >= 2 else fps_us       # calls alternate SA1 (8192->512), SA2 (512->128)

@@ -327,24 +327,49 @@ extern "C" size_t cpfn_ball_query_grid_workspace_bytes(int B, int N) {
          static_cast<size_t>(B) * N * sizeof(float4) + 256;
 }
 
-extern "C" int cpfn_ball_query_grid(const float *new_xyz, const float *xyz, int B, int N, int S, float radius,
-                                    int nsample, int32_t *idx, void *workspace, size_t workspace_bytes,
-                                    cpfn_stream_t stream) {
+namespace cpfn {
+namespace {
+struct GridWs { float4 *sorted; GridHeader *hdr; int *cell_start; };
+GridWs grid_ws(void *workspace, int B, int N) {
+  unsigned char *w = static_cast<unsigned char *>(workspace);
+  GridWs g;
+  g.sorted = reinterpret_cast<float4 *>(w);
+  w += static_cast<size_t>(B) * N * sizeof(float4);
+  g.hdr = reinterpret_cast<GridHeader *>(w);
+  w += static_cast<size_t>(B) * sizeof(GridHeader);
+  g.cell_start = reinterpret_cast<int *>(w);
+  return g;
+}
+bool grid_applies(int B, int N, float radius) { return N >= 2048 && N <= kGridMaxN && radius > 0.f && B <= 65535; }
+}  // namespace
+}  // namespace cpfn
+
+// The grid depends on the cloud and the radius only -- not on the queries -- so a caller can build it while
+// the queries are still being produced (the SA layer's farthest point sampling) and query it afterwards.
+extern "C" int cpfn_ball_query_grid_build(const float *xyz, int B, int N, float radius, void *workspace,
+                                          size_t workspace_bytes, cpfn_stream_t stream) {
+  using namespace cpfn;
+  if (B < 0 || N < 0) return CPFN_EINVAL;
+  if (B == 0 || !grid_applies(B, N, radius)) return CPFN_OK;                 // the query will use the scan kernel
+  if (!xyz) return CPFN_EINVAL;
+  if (!workspace || workspace_bytes < cpfn_ball_query_grid_workspace_bytes(B, N)) return CPFN_EWORKSPACE;
+  const GridWs g = grid_ws(workspace, B, N);
+  bq_grid_build_kernel<<<B, kGridBuildThreads, 0, as_stream(stream)>>>(xyz, N, radius, g.hdr, g.cell_start, g.sorted);
+  return check_launch();
+}
+
+extern "C" int cpfn_ball_query_grid_query(const float *new_xyz, const float *xyz, int B, int N, int S, float radius,
+                                          int nsample, int32_t *idx, void *workspace, size_t workspace_bytes,
+                                          cpfn_stream_t stream) {
   using namespace cpfn;
   if (B < 0 || N < 0 || S < 0 || nsample < 0) return CPFN_EINVAL;
   if (B == 0 || S == 0 || nsample == 0) return CPFN_OK;
-  if (N < 2048 || N > kGridMaxN || !(radius > 0.f) || B > 65535)    // small / huge clouds: the scan kernel
+  if (!grid_applies(B, N, radius))                                           // small / huge clouds: the scan kernel
     return cpfn_ball_query(new_xyz, xyz, B, N, S, radius, nsample, idx, stream);
-  if (!new_xyz || !xyz || !idx) return CPFN_EINVAL;
+  if (!new_xyz || !idx) return CPFN_EINVAL;
   if (!workspace || workspace_bytes < cpfn_ball_query_grid_workspace_bytes(B, N)) return CPFN_EWORKSPACE;
   cudaStream_t st = as_stream(stream);
-  unsigned char *w = static_cast<unsigned char *>(workspace);
-  float4 *sorted = reinterpret_cast<float4 *>(w);
-  w += static_cast<size_t>(B) * N * sizeof(float4);
-  GridHeader *hdr = reinterpret_cast<GridHeader *>(w);
-  w += static_cast<size_t>(B) * sizeof(GridHeader);
-  int *cell_start = reinterpret_cast<int *>(w);
-  bq_grid_build_kernel<<<B, kGridBuildThreads, 0, st>>>(xyz, N, radius, hdr, cell_start, sorted);
+  const GridWs g = grid_ws(workspace, B, N);
   const size_t smem = sizeof(unsigned int) * kGridQueryWarps * static_cast<size_t>((N + 31) >> 5);
   if (smem > 48 * 1024)
     CPFN_CUDA_TRY(cudaFuncSetAttribute(bq_grid_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -353,7 +378,17 @@ extern "C" int cpfn_ball_query_grid(const float *new_xyz, const float *xyz, int 
   int gx = (S + kGridQueryWarps - 1) / kGridQueryWarps;
   const int cap = (4 * sms + B - 1) / B;
   if (gx > cap) gx = cap < 1 ? 1 : cap;
-  bq_grid_query_kernel<<<dim3(gx, B), kGridQueryWarps * 32, smem, st>>>(new_xyz, N, S, radius, nsample, hdr, cell_start,
-                                                                        sorted, idx);
+  bq_grid_query_kernel<<<dim3(gx, B), kGridQueryWarps * 32, smem, st>>>(new_xyz, N, S, radius, nsample, g.hdr,
+                                                                        g.cell_start, g.sorted, idx);
   return check_launch();
+}
+
+extern "C" int cpfn_ball_query_grid(const float *new_xyz, const float *xyz, int B, int N, int S, float radius,
+                                    int nsample, int32_t *idx, void *workspace, size_t workspace_bytes,
+                                    cpfn_stream_t stream) {
+  if (B < 0 || N < 0 || S < 0 || nsample < 0) return CPFN_EINVAL;
+  if (B == 0 || S == 0 || nsample == 0) return CPFN_OK;
+  const int rc = cpfn_ball_query_grid_build(xyz, B, N, radius, workspace, workspace_bytes, stream);
+  if (rc != CPFN_OK) return rc;
+  return cpfn_ball_query_grid_query(new_xyz, xyz, B, N, S, radius, nsample, idx, workspace, workspace_bytes, stream);
 }

@@ -9,6 +9,7 @@ reference's channel-major [B, C, N] tensors are produced only where the referenc
 returns them (``l3_feats``, ``output_feat``, the module-level SA / FP forwards).
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -137,7 +138,6 @@ def run_chain(pc, B, cols_per_cloud, out, ldo, tile_cols=128, in_mode=IN_DENSE, 
 
 def pick_tile(dims, cols_per_cloud, need_cloud_aligned=False, prefer=128, name=None):
     """Tile choice; CPFN_TILE_<SA1|SA2|HEAD>=128|64|32 overrides it (tuning experiments)."""
-    import os
     if name and os.environ.get("CPFN_TILE_" + name):
         return int(os.environ["CPFN_TILE_" + name])
     return _pick_tile(dims, cols_per_cloud, need_cloud_aligned, prefer)
@@ -292,6 +292,40 @@ def sa_indices(module, xyz):
     fps_idx = cuda_ops.farthest_point_sampling(xyz, module.num_points)
     new_xyz = gather_xyz(xyz, fps_idx)
     return new_xyz, cuda_ops.ball_query(new_xyz, xyz, module.radius_list[0], module.num_samples_list[0])
+
+
+def sa_indices_overlapped(module, xyz, side):
+    """``sa_indices`` with the ball query's uniform grid -- which depends on the cloud and the radius, not on the
+    centroids -- built on ``side`` while farthest point sampling runs on the current stream (FPS leaves more than
+    half of the SMs idle).  Same result as ``sa_indices``."""
+    B, N, _ = xyz.shape
+    dev = xyz.device
+    radius, K = float(module.radius_list[0]), int(module.num_samples_list[0])
+    L = _lib.lib()
+    if side is None or not (2048 <= N <= 32768) or radius <= 0 or os.environ.get("CPFN_BQ_NO_GRID"):
+        return sa_indices(module, xyz)
+    main = torch.cuda.current_stream(dev)
+    nbytes = L.cpfn_ball_query_grid_workspace_bytes(B, N)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    fork = torch.cuda.Event()
+    fork.record(main)
+    with torch.cuda.stream(side), torch.cuda.device(dev):
+        side.wait_event(fork)
+        _lib.check(L.cpfn_ball_query_grid_build(xyz.data_ptr(), B, N, radius, ws.data_ptr(), nbytes, side.cuda_stream),
+                   "ball_query_grid_build")
+        built = torch.cuda.Event()
+        built.record(side)
+    ws.record_stream(side)
+    fps_idx = cuda_ops.farthest_point_sampling(xyz, module.num_points)
+    new_xyz = gather_xyz(xyz, fps_idx)
+    S = new_xyz.shape[1]
+    idx = torch.empty(B, S, K, dtype=torch.int32, device=dev)
+    main.wait_event(built)
+    with torch.cuda.device(dev):
+        _lib.check(L.cpfn_ball_query_grid_query(new_xyz.data_ptr(), xyz.data_ptr(), B, N, S, radius, K, idx.data_ptr(),
+                                                ws.data_ptr(), nbytes, main.cuda_stream), "ball_query_grid_query")
+    cuda_ops.count_launches(2)
+    return new_xyz, idx
 
 
 def sa_forward_pm(module, xyz, feats_pm, indices=None):
@@ -453,7 +487,7 @@ def pointnet2_forward(model, P, dropout=True):
     # FP3) runs on a side stream, concurrently with SA1's ball query and MLP chain on the main stream.
     main = torch.cuda.current_stream(dev)
     side = _side_stream(dev) if USE_SIDE_STREAM else main
-    idx1 = sa_indices(model.sa1, P)
+    idx1 = sa_indices_overlapped(model.sa1, P, side if side is not main else None)
     l1_xyz = idx1[0]
     fork = torch.cuda.Event()
     fork.record(main)

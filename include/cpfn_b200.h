@@ -81,6 +81,15 @@ CPFN_API size_t cpfn_ball_query_grid_workspace_bytes(int B, int N);
 CPFN_API int cpfn_ball_query_grid(const float *new_xyz, const float *xyz, int B, int N, int S,
                                   float radius, int nsample, int32_t *idx, void *workspace,
                                   size_t workspace_bytes, cpfn_stream_t stream);
+/* The two halves of cpfn_ball_query_grid: the grid depends on (xyz, radius) only, so it can be built on another
+ * stream while the queries (the SA layer's FPS centroids) are still being computed; the query half then needs
+ * the same workspace.  Outside the grid kernel's range (N < 2048, N > 32768) build is a no-op and query
+ * falls back to cpfn_ball_query. */
+CPFN_API int cpfn_ball_query_grid_build(const float *xyz, int B, int N, float radius, void *workspace,
+                                        size_t workspace_bytes, cpfn_stream_t stream);
+CPFN_API int cpfn_ball_query_grid_query(const float *new_xyz, const float *xyz, int B, int N, int S, float radius,
+                                        int nsample, int32_t *idx, void *workspace, size_t workspace_bytes,
+                                        cpfn_stream_t stream);
 
 /* Gather / group (+ gradients).  Replace gather_points(_grad)
  * (src/sampling.cpp:15-64, src/sampling_gpu.cu:8-53) and group_points(_grad)
