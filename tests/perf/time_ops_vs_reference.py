@@ -1,6 +1,7 @@
 """Per-op device timings at GlobalSPFN sizes (B=16, N=8192): this library vs the
 reference kernels (oracle/_ref) on the same GPU.  CUDA events, L2 flushed between
-iterations.  Diagnostic tool, not the bench contract (see bench.py)."""
+iterations.  Diagnostic tool, not the bench contract (see bench.py); lives under tests/ because it
+loads the reference extension through oracle/ (test infrastructure)."""
 import json
 import os
 import sys
@@ -8,7 +9,7 @@ import sys
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from cpfn_b200 import cuda_ops, synth  # noqa: E402
 from oracle import build_ref  # noqa: E402
