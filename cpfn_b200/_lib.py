@@ -83,6 +83,8 @@ SIGNATURES = {
     "cpfn_ball_query_grid_build": (c_int, [c_void_p, c_int, c_int, c_float, c_void_p, c_size_t, c_void_p]),
     "cpfn_ball_query_grid_query": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p,
                                            c_size_t, c_void_p]),
+    "cpfn_furthest_point_sampling_xyz": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
+                                                 c_void_p]),
     "cpfn_mlp_packed_bytes": (c_size_t, [c_int, c_int]),
     "cpfn_mlp_pack_weights_host": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "cpfn_mlp_chain": (c_int, [c_void_p, c_void_p]),

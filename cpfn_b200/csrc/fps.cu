@@ -79,7 +79,7 @@ __device__ __forceinline__ void stage_soa(const float *__restrict__ p, int N, in
 // in increasing reference rank and the strict '>' keeps the right one on ties.
 template <int PPT, bool COORDS_IN_REGS>
 __global__ void __launch_bounds__(1024, 1)
-fps_cta_kernel(const float *__restrict__ xyz, int N, int m, int log2T,
+fps_cta_kernel(const float *__restrict__ xyz, float *__restrict__ new_xyz, int N, int m, int log2T,
                int32_t *__restrict__ idx) {
   extern __shared__ float s_xyz[];
   __shared__ unsigned long long slot[2][32];
@@ -109,6 +109,8 @@ fps_cta_kernel(const float *__restrict__ xyz, int N, int m, int log2T,
 
   if (t == 0) out[0] = 0;
   float cx = sx[0], cy = sy[0], cz = sz[0];
+  float *nx = new_xyz ? new_xyz + static_cast<size_t>(blockIdx.x) * m * 3 : nullptr;   // the centroids themselves
+  if (nx && t == 0) { nx[0] = cx; nx[1] = cy; nx[2] = cz; }
   for (int j = 1; j < m; ++j) {
     float best = -1.0f;
     int bi = 0;
@@ -130,6 +132,7 @@ fps_cta_kernel(const float *__restrict__ xyz, int N, int m, int log2T,
     const int old = L ? static_cast<int>(fps_unrank(~L, log2T)) : 0;
     if (t == 0) out[j] = old;
     cx = sx[old]; cy = sy[old]; cz = sz[old];
+    if (nx && t == 0) { nx[3 * j] = cx; nx[3 * j + 1] = cy; nx[3 * j + 2] = cz; }
   }
 }
 
@@ -195,7 +198,7 @@ constexpr int kFpsClusterWarps = kFpsClusterThreads / 32;
 // in increasing reference rank and the strict '>' keeps the right one on ties.
 template <int PPT>
 __global__ void __launch_bounds__(kFpsClusterThreads, 1)
-fps_cluster_kernel(const float *__restrict__ xyz, int N, int m, int log2T, int Nc,
+fps_cluster_kernel(const float *__restrict__ xyz, float *__restrict__ new_xyz, int N, int m, int log2T, int Nc,
                    int32_t *__restrict__ idx) {
   extern __shared__ float s_xyz[];
   __shared__ __align__(8) unsigned long long xslot[2][8 * kFpsClusterWarps];   // [parity][sender CTA * 8 + sender warp]
@@ -245,6 +248,8 @@ fps_cluster_kernel(const float *__restrict__ xyz, int N, int m, int log2T, int N
 
   if (r == 0 && t == 0) out[0] = 0;
   float cx = sx[0], cy = sy[0], cz = sz[0];
+  float *nx = (new_xyz && r == 0 && t == 0) ? new_xyz + static_cast<size_t>(cloud) * m * 3 : nullptr;
+  if (nx) { nx[0] = cx; nx[1] = cy; nx[2] = cz; }
   for (int j = 1; j < m; ++j) {
     float best = -1.0f;
     int bi = 0;
@@ -278,12 +283,13 @@ fps_cluster_kernel(const float *__restrict__ xyz, int N, int m, int log2T, int N
     const int old = L ? static_cast<int>(fps_unrank(~L, log2T)) : 0;
     if (r == 0 && t == 0) out[j] = old;
     cx = sx[old]; cy = sy[old]; cz = sz[old];
+    if (nx) { nx[3 * j] = cx; nx[3 * j + 1] = cy; nx[3 * j + 2] = cz; }
   }
   cluster_sync_all();                    // nobody leaves while a peer may still write into its shared memory
 }
 
 template <int PPT>
-int launch_cluster(const float *xyz, int B, int N, int m, int log2T, int C, int Nc, int32_t *idx,
+int launch_cluster(const float *xyz, float *new_xyz, int B, int N, int m, int log2T, int C, int Nc, int32_t *idx,
                    cudaStream_t st) {
   const size_t smem = 3u * static_cast<size_t>((N + 31) & ~31) * sizeof(float);
   auto kern = fps_cluster_kernel<PPT>;
@@ -300,14 +306,14 @@ int launch_cluster(const float *xyz, int B, int N, int m, int log2T, int C, int 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CPFN_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, xyz, N, m, log2T, Nc, idx));
+  CPFN_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, xyz, new_xyz, N, m, log2T, Nc, idx));
   return check_launch();
 }
 
 // Any N: running minimum in a global workspace [B,N], coordinates re-read
 // through L1/L2 every round.  Only used beyond kMaxSmemN points per cloud.
 __global__ void __launch_bounds__(1024, 1)
-fps_stream_kernel(const float *__restrict__ xyz, int N, int m, int log2T,
+fps_stream_kernel(const float *__restrict__ xyz, float *__restrict__ new_xyz, int N, int m, int log2T,
                   float *__restrict__ temp, int32_t *__restrict__ idx) {
   __shared__ unsigned long long slot[2][32];
   const int NT = blockDim.x, t = threadIdx.x, nwarps = NT >> 5;
@@ -320,6 +326,8 @@ fps_stream_kernel(const float *__restrict__ xyz, int N, int m, int log2T,
   }
   if (t == 0) out[0] = 0;
   float cx = p[0], cy = p[1], cz = p[2];
+  float *nx = (new_xyz && t == 0) ? new_xyz + static_cast<size_t>(blockIdx.x) * m * 3 : nullptr;
+  if (nx) { nx[0] = cx; nx[1] = cy; nx[2] = cz; }
   for (int j = 1; j < m; ++j) {
     float best = -1.0f;
     int bk = 0;
@@ -337,6 +345,7 @@ fps_stream_kernel(const float *__restrict__ xyz, int N, int m, int log2T,
     const int old = L ? static_cast<int>(fps_unrank(~L, log2T)) : 0;
     if (t == 0) out[j] = old;
     cx = p[3 * old]; cy = p[3 * old + 1]; cz = p[3 * old + 2];
+    if (nx) { nx[3 * j] = cx; nx[3 * j + 1] = cy; nx[3 * j + 2] = cz; }
   }
 }
 
@@ -350,14 +359,14 @@ int ref_log2_threads(int n) {
 }
 
 template <int PPT, bool REGS>
-int launch_cta(const float *xyz, int B, int N, int m, int log2T, int NT, int32_t *idx,
+int launch_cta(const float *xyz, float *new_xyz, int B, int N, int m, int log2T, int NT, int32_t *idx,
                cudaStream_t st) {
   const size_t smem = 3u * static_cast<size_t>((N + 31) & ~31) * sizeof(float);
   auto kern = fps_cta_kernel<PPT, REGS>;
   if (smem + 1024 > 48 * 1024)  // static shared memory counts against the 48 KB default
     CPFN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem)));
-  kern<<<B, NT, smem, st>>>(xyz, N, m, log2T, idx);
+  kern<<<B, NT, smem, st>>>(xyz, new_xyz, N, m, log2T, idx);
   return check_launch();
 }
 
@@ -372,6 +381,12 @@ extern "C" size_t cpfn_fps_workspace_bytes(int B, int N) {
 extern "C" int cpfn_furthest_point_sampling(const float *xyz, int B, int N, int nsamples,
                                             int32_t *idx, void *workspace,
                                             size_t workspace_bytes, cpfn_stream_t stream) {
+  return cpfn_furthest_point_sampling_xyz(xyz, B, N, nsamples, idx, nullptr, workspace, workspace_bytes, stream);
+}
+
+extern "C" int cpfn_furthest_point_sampling_xyz(const float *xyz, int B, int N, int nsamples, int32_t *idx,
+                                                float *new_xyz, void *workspace, size_t workspace_bytes,
+                                                cpfn_stream_t stream) {
   using namespace cpfn;
   if (B < 0 || N < 0 || nsamples < 0) return CPFN_EINVAL;
   if (B == 0 || nsamples == 0) return CPFN_OK;
@@ -383,7 +398,7 @@ extern "C" int cpfn_furthest_point_sampling(const float *xyz, int B, int N, int 
   if (N > kMaxSmemN) {
     const size_t need = cpfn_fps_workspace_bytes(B, N);
     if (!workspace || workspace_bytes < need) return CPFN_EWORKSPACE;
-    fps_stream_kernel<<<B, 1024, 0, st>>>(xyz, N, nsamples, log2T,
+    fps_stream_kernel<<<B, 1024, 0, st>>>(xyz, new_xyz, N, nsamples, log2T,
                                           static_cast<float *>(workspace), idx);
     return check_launch();
   }
@@ -399,18 +414,18 @@ extern "C" int cpfn_furthest_point_sampling(const float *xyz, int B, int N, int 
     if (C > 1) {
       const int Nc = ((N + C - 1) / C + 511) / 512 * 512;
       const int ppt = Nc / 256;
-      if (ppt <= 2) return launch_cluster<2>(xyz, B, N, nsamples, log2T, C, Nc, idx, st);
-      if (ppt <= 4) return launch_cluster<4>(xyz, B, N, nsamples, log2T, C, Nc, idx, st);
-      if (ppt <= 8) return launch_cluster<8>(xyz, B, N, nsamples, log2T, C, Nc, idx, st);
-      if (ppt <= 16) return launch_cluster<16>(xyz, B, N, nsamples, log2T, C, Nc, idx, st);
+      if (ppt <= 2) return launch_cluster<2>(xyz, new_xyz, B, N, nsamples, log2T, C, Nc, idx, st);
+      if (ppt <= 4) return launch_cluster<4>(xyz, new_xyz, B, N, nsamples, log2T, C, Nc, idx, st);
+      if (ppt <= 8) return launch_cluster<8>(xyz, new_xyz, B, N, nsamples, log2T, C, Nc, idx, st);
+      if (ppt <= 16) return launch_cluster<16>(xyz, new_xyz, B, N, nsamples, log2T, C, Nc, idx, st);
     }
   }
   // Block size: a multiple of T (>= one warp); N >= 1024 always uses 1024.
   const int NT = N >= 1024 ? 1024 : (T < 32 ? 32 : T);
   const int ppt = (N + NT - 1) / NT;
-  if (ppt <= 1) return launch_cta<1, true>(xyz, B, N, nsamples, log2T, NT, idx, st);
-  if (ppt <= 2) return launch_cta<2, true>(xyz, B, N, nsamples, log2T, NT, idx, st);
-  if (ppt <= 4) return launch_cta<4, true>(xyz, B, N, nsamples, log2T, NT, idx, st);
-  if (ppt <= 8) return launch_cta<8, true>(xyz, B, N, nsamples, log2T, NT, idx, st);
-  return launch_cta<16, false>(xyz, B, N, nsamples, log2T, NT, idx, st);
+  if (ppt <= 1) return launch_cta<1, true>(xyz, new_xyz, B, N, nsamples, log2T, NT, idx, st);
+  if (ppt <= 2) return launch_cta<2, true>(xyz, new_xyz, B, N, nsamples, log2T, NT, idx, st);
+  if (ppt <= 4) return launch_cta<4, true>(xyz, new_xyz, B, N, nsamples, log2T, NT, idx, st);
+  if (ppt <= 8) return launch_cta<8, true>(xyz, new_xyz, B, N, nsamples, log2T, NT, idx, st);
+  return launch_cta<16, false>(xyz, new_xyz, B, N, nsamples, log2T, NT, idx, st);
 }

@@ -1067,7 +1067,7 @@ int launch_chain(const cpfn_mlp_chain_t *c, cudaStream_t st) {
   const int units = (NT == 128 && two_sub) ? (p.n_tiles + 1) / 2 : p.n_tiles;   // the ping-pong kernel takes tile pairs
   const int grid = units < per_sm * sms ? units : per_sm * sms;
   if (grid <= 0) return CPFN_OK;
-  if (atomic_pool)
+  if (atomic_pool && !c->out_prezeroed)
     CPFN_CUDA_TRY(cudaMemsetAsync(c->out, 0, sizeof(float) * static_cast<size_t>(p.cols / c->pool_g) * c->ldo, st));
   const dim3 grid2(grid, p.split_cout ? p.L[0].cout_chunks : 1);
   kern<<<grid2, kChainThreads, smem, st>>>(p);

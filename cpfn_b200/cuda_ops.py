@@ -73,21 +73,24 @@ def _check(code, what, launches=1):
     count_launches(launches)
 
 
-def farthest_point_sampling(points, nsamples):
-    """points f32 [B,N,3] -> i32 [B,nsamples] (sampling.cpp:65-86)."""
+def farthest_point_sampling(points, nsamples, return_centroids=False):
+    """points f32 [B,N,3] -> i32 [B,nsamples] (sampling.cpp:65-86).  ``return_centroids`` (an extension, off by
+    default) also returns the sampled points f32 [B,nsamples,3], written by the same kernel."""
     _check_contiguous(points, "points")
     _check_float(points, "points")
     _need_cuda(points)
     B, N = points.size(0), points.size(1)
     out = torch.empty((B, nsamples), dtype=torch.int32, device=points.device)
+    cen = torch.empty((B, nsamples, 3), dtype=torch.float32, device=points.device) if return_centroids else None
     L = _lib.lib()
     ws_bytes = L.cpfn_fps_workspace_bytes(B, N)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=points.device) if ws_bytes else None
     with torch.cuda.device(points.device):
-        _check(L.cpfn_furthest_point_sampling(_p(points), B, N, int(nsamples), _p(out),
+        _check(L.cpfn_furthest_point_sampling_xyz(_p(points), B, N, int(nsamples), _p(out),
+                                                  _p(cen) if cen is not None else None,
                                                   _p(ws) if ws is not None else None, ws_bytes,
                                                   _stream(points)), "farthest_point_sampling")
-    return out
+    return (out, cen) if return_centroids else out
 
 
 def ball_query(new_xyz, xyz, radius, nsample):

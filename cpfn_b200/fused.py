@@ -41,7 +41,7 @@ class _Chain(ctypes.Structure):
                 ("out_mode", ctypes.c_int32), ("out", ctypes.c_void_p), ("ldo", ctypes.c_int32),
                 ("pool_g", ctypes.c_int32), ("split_cout", ctypes.c_int32),
                 ("l0_w", ctypes.c_void_p), ("l0_b", ctypes.c_void_p), ("l0_cout", ctypes.c_int32),
-                ("in_bias", ctypes.c_void_p)]
+                ("in_bias", ctypes.c_void_p), ("out_prezeroed", ctypes.c_int32)]
 
 
 def available():
@@ -104,7 +104,7 @@ class PackedChain:
 def run_chain(pc, B, cols_per_cloud, out, ldo, tile_cols=128, in_mode=IN_DENSE, a_src=None, a_ch=0, a_rows=0,
               idx=None, xyz=None, centers=None, group_k=0, b_src=None, b_ch=0, b_rows=0, nn_w=None,
               out_mode=OUT_ROWS, pool_g=0, biases=None, bias_per_cloud=(), masks=None, out_cm=None, split_cout=False,
-              l0=None, in_bias=None):
+              l0=None, in_bias=None, out_prezeroed=False):
     """Enqueue one fused chain on torch's current stream."""
     c = _Chain()
     c.n_layers = len(pc.dims)
@@ -129,6 +129,7 @@ def run_chain(pc, B, cols_per_cloud, out, ldo, tile_cols=128, in_mode=IN_DENSE, 
         c.l0_w, c.l0_b, c.l0_cout = l0[0].data_ptr(), l0[1].data_ptr(), l0[0].shape[0]
     if in_bias is not None:
         c.in_bias = in_bias.data_ptr()
+    c.out_prezeroed = int(bool(out_prezeroed))
     with torch.cuda.device(out.device):
         _lib.check(_lib.lib().cpfn_mlp_chain(ctypes.byref(c), torch.cuda.current_stream(out.device).cuda_stream),
                    "mlp_chain")
@@ -164,7 +165,7 @@ def _pick_tile(dims, cols_per_cloud, need_cloud_aligned=False, prefer=128):
     raise RuntimeError("cpfn_b200.fused: chain does not fit shared memory: %r" % (dims,))
 
 
-def run_layerwise(pc, B, cols_per_cloud, out, first, out_mode=OUT_ROWS, pool_g=0, bias0=None):
+def run_layerwise(pc, B, cols_per_cloud, out, first, out_mode=OUT_ROWS, pool_g=0, bias0=None, out_prezeroed=False):
     """Few columns, wide layers: run the chain one layer per launch with one CTA per (64-column tile,
     128-channel chunk) so that the weight stream is spread over many SMs; activations between the
     layers are point-major fp32 rows in HBM (a few MB, L2 resident).  `first` = kwargs of the input
@@ -183,7 +184,8 @@ def run_layerwise(pc, B, cols_per_cloud, out, first, out_mode=OUT_ROWS, pool_g=0
         if (c.dims[0][0] + 63) // 64 * 2 * tile * 128 + 5120 + 3 * 16384 > 227 * 1024:
             tile = 32
         run_chain(c, B, cols_per_cloud, dst, cout, tile_cols=tile, split_cout=True,
-                  out_mode=(out_mode if last else OUT_ROWS), pool_g=(pool_g if last else 0), **x_kwargs, **extra)
+                  out_mode=(out_mode if last else OUT_ROWS), pool_g=(pool_g if last else 0),
+                  out_prezeroed=(out_prezeroed and last), **x_kwargs, **extra)
         x_kwargs = dict(in_mode=IN_DENSE, a_src=dst, a_ch=cout, a_rows=cols_per_cloud)
     return out
 
@@ -289,8 +291,7 @@ def _sa_chain(module, device):
 def sa_indices(module, xyz):
     """FPS -> centroid gather -> ball query of a (non group_all) SA layer: (new_xyz [B,S,3], group_idx
     int32 [B,S,K]).  Depends on positions only, so it can run ahead of the previous layer's MLP."""
-    fps_idx = cuda_ops.farthest_point_sampling(xyz, module.num_points)
-    new_xyz = gather_xyz(xyz, fps_idx)
+    _, new_xyz = cuda_ops.farthest_point_sampling(xyz, module.num_points, return_centroids=True)
     return new_xyz, cuda_ops.ball_query(new_xyz, xyz, module.radius_list[0], module.num_samples_list[0])
 
 
@@ -316,8 +317,7 @@ def sa_indices_overlapped(module, xyz, side):
         built = torch.cuda.Event()
         built.record(side)
     ws.record_stream(side)
-    fps_idx = cuda_ops.farthest_point_sampling(xyz, module.num_points)
-    new_xyz = gather_xyz(xyz, fps_idx)
+    _, new_xyz = cuda_ops.farthest_point_sampling(xyz, module.num_points, return_centroids=True)   # centroids from the kernel
     S = new_xyz.shape[1]
     idx = torch.empty(B, S, K, dtype=torch.int32, device=dev)
     main.wait_event(built)
@@ -328,9 +328,10 @@ def sa_indices_overlapped(module, xyz, side):
     return new_xyz, idx
 
 
-def sa_forward_pm(module, xyz, feats_pm, indices=None):
+def sa_forward_pm(module, xyz, feats_pm, indices=None, out=None):
     """Point-major set abstraction.  xyz [B,N,3], feats_pm [B,N,D] | None ->
-    (new_xyz [B,S,3] | None, new_feats_pm [B,S,D'])."""
+    (new_xyz [B,S,3] | None, new_feats_pm [B,S,D']).  ``out``: a ZERO-FILLED [B,S,D'] buffer for the pooled
+    features (the caller filled it off the critical path; the chain then skips its own memset)."""
     assert len(module.radius_list) == 1, "multi-scale grouping: use the per-op path"
     B, N, _ = xyz.shape
     dev = xyz.device
@@ -338,23 +339,27 @@ def sa_forward_pm(module, xyz, feats_pm, indices=None):
     cout = pc.dims[-1][1]
     D = 0 if feats_pm is None else feats_pm.shape[2]
     if module.group_all:
-        idx = torch.arange(N, dtype=torch.int32, device=dev).repeat(B)
-        centers = torch.zeros(B, 3, dtype=torch.float32, device=dev)
-        out = torch.empty(B, 1, cout, dtype=torch.float32, device=dev)
+        idx, centers = _group_all_constants(B, N, dev)        # every point of the cloud, centre at the origin
+        pre = out is not None
+        if not pre:
+            out = torch.empty(B, 1, cout, dtype=torch.float32, device=dev)
         first = dict(in_mode=IN_GROUP, a_src=feats_pm, a_ch=D, a_rows=N, idx=idx, xyz=xyz, centers=centers, group_k=N)
         if N % 32 == 0 and B * N <= 16384:
-            run_layerwise(pc, B, N, out, first, out_mode=OUT_POOL, pool_g=N)
+            run_layerwise(pc, B, N, out, first, out_mode=OUT_POOL, pool_g=N, out_prezeroed=pre)
         else:
             tile = pick_tile(pc.dims, N, need_cloud_aligned=True, prefer=32 if cout > 512 else 128)
-            run_chain(pc, B, N, out, cout, tile_cols=tile, out_mode=OUT_POOL, pool_g=N, **first)
+            run_chain(pc, B, N, out, cout, tile_cols=tile, out_mode=OUT_POOL, pool_g=N, out_prezeroed=pre, **first)
         return None, out
     S, K = module.num_points, module.num_samples_list[0]
     if indices is None:
         indices = sa_indices(module, xyz)
     new_xyz, group_idx = indices
-    out = torch.empty(B, S, cout, dtype=torch.float32, device=dev)
+    pre = out is not None
+    if not pre:
+        out = torch.empty(B, S, cout, dtype=torch.float32, device=dev)
     run_chain(pc, B, S * K, out, cout, tile_cols=pick_tile(pc.dims, S * K, name=('SA1' if D == 0 else 'SA2'), prefer=(128 if D == 0 else 64)), in_mode=IN_GROUP, a_src=feats_pm, a_ch=D, a_rows=N,
-              idx=group_idx, xyz=xyz, centers=new_xyz, group_k=K, out_mode=OUT_POOL, pool_g=K, l0=getattr(pc, "l0", None))
+              idx=group_idx, xyz=xyz, centers=new_xyz, group_k=K, out_mode=OUT_POOL, pool_g=K, l0=getattr(pc, "l0", None),
+              out_prezeroed=pre)
     return new_xyz, out
 
 
@@ -394,7 +399,11 @@ def fp_forward_pm(module, xyz1, xyz2, feats1_pm, feats2_pm, nn=None, tail=None):
         D2 = feats2_pm.shape[2]
         pc, wconst = _fp_chain(module, dev, split=(D1, D1 + D2))
         g = feats2_pm.reshape(B, D2).contiguous()
-        bias0 = torch.zeros(B, pc.biases[0].numel(), dtype=torch.float32, device=dev)
+        # per-cloud bias rows: linear_rows rewrites the cout valid entries every call, the padding stays zero
+        bias0 = getattr(module, _CACHE_ATTR + "_bias0", None)
+        if bias0 is None or bias0.shape[0] != B or bias0.device != dev:
+            bias0 = torch.zeros(B, pc.biases[0].numel(), dtype=torch.float32, device=dev)
+            setattr(module, _CACHE_ATTR + "_bias0", bias0)
         linear_rows(g, wconst[0], wconst[1], bias0)          # fp32: W_global @ g + b, one vector per cloud
         out = torch.empty(B, N, pc.dims[-1][1], dtype=torch.float32, device=dev)
         first = dict(in_mode=IN_DENSE, a_src=feats1_pm, a_ch=D1, a_rows=N)
@@ -414,6 +423,18 @@ def fp_forward_pm(module, xyz1, xyz2, feats1_pm, feats2_pm, nn=None, tail=None):
 
 
 _ones_cache = {}
+_group_all_cache = {}
+
+
+def _group_all_constants(B, N, dev):
+    """(group index 0..N-1 per cloud int32 [B*N], zero centres [B,3]) of a group_all SA layer -- constants,
+    built once per shape instead of three tiny kernels on the critical path of every step."""
+    key = (B, N, dev)
+    c = _group_all_cache.get(key)
+    if c is None:
+        c = _group_all_cache[key] = (torch.arange(N, dtype=torch.int32, device=dev).repeat(B),
+                                     torch.zeros(B, 3, dtype=torch.float32, device=dev))
+    return c
 _side_streams = {}
 USE_SIDE_STREAM = True      # bench.py's per-op profiling pass serialises everything on one stream
 

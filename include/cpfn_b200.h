@@ -64,6 +64,11 @@ CPFN_API size_t cpfn_fps_workspace_bytes(int B, int N);
 CPFN_API int cpfn_furthest_point_sampling(const float *xyz, int B, int N, int nsamples,
                                  int32_t *idx, void *workspace,
                                  size_t workspace_bytes, cpfn_stream_t stream);
+/* The same sampling that also writes the sampled centroids new_xyz f32 [B,nsamples,3] = xyz[b, idx[b,s], :]
+ * (the select_point_subset that follows FPS in pointset_abstraction.py:49-50) from inside the kernel; NULL = skip. */
+CPFN_API int cpfn_furthest_point_sampling_xyz(const float *xyz, int B, int N, int nsamples, int32_t *idx,
+                                              float *new_xyz, void *workspace, size_t workspace_bytes,
+                                              cpfn_stream_t stream);
 
 /* Ball query.  Replaces ball_query (src/ball_query.cpp:8-32, kernel
  * src/ball_query_gpu.cu:9-44).  new_xyz [B,S,3], xyz [B,N,3] -> idx
@@ -210,6 +215,9 @@ typedef struct {
    * applies that layer's W once per SOURCE row and its bias + ReLU here, per interpolated row
    * (pointset_feature_propagation.py:36-51 for FP3, whose input is the interpolation alone). */
   const float *in_bias;
+  /* OUT_POOL with atomic merging needs the pooled output zero-filled; non-zero = the caller has already done
+   * that (e.g. off the critical path, on another stream), the library skips its own cudaMemsetAsync. */
+  int32_t out_prezeroed;
 } cpfn_mlp_chain_t;
 
 /* Replaces the conv+BN+ReLU(+max) chains of pointset_abstraction.py:61-74,

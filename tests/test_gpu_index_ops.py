@@ -234,3 +234,15 @@ def test_ball_query_grid_equals_scan_kernel(cuda_dev, oracle_ops, monkeypatch):
         b = cuda_ops.ball_query(_t(q, cuda_dev), _t(xyz, cuda_dev), r, K).cpu().numpy()
         np.testing.assert_array_equal(a, b, err_msg=name)
         np.testing.assert_array_equal(a, oracle_ops.ball_query(q, xyz, r, K), err_msg=name)
+
+
+@pytest.mark.parametrize("B,N,m", [(16, 8192, 512), (2, 8192, 300), (3, 1000, 64), (40, 2048, 128), (2, 20000, 96)])
+def test_fps_writes_the_centroids(B, N, m, cuda_dev):
+    """return_centroids: the sampling kernels (cluster, single-CTA and streaming variants) write xyz[idx] themselves;
+    same indices as the plain call, coordinates bit-identical to a gather."""
+    P = _t(synth.uniform_cloud(B, N, seed=N + m), cuda_dev)
+    idx = cuda_ops.farthest_point_sampling(P, m)
+    idx2, cen = cuda_ops.farthest_point_sampling(P, m, return_centroids=True)
+    assert torch.equal(idx, idx2) and cen.shape == (B, m, 3)
+    want = torch.gather(P, 1, idx.long().unsqueeze(2).expand(B, m, 3))
+    assert torch.equal(cen, want)
