@@ -162,6 +162,8 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"       # NCCL prints its version banner on STDOUT; keep stdout = the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     from cpfn_b200 import api, cuda_ops, fused
     from cpfn_b200.spfn import fit as fitmod
