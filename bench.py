@@ -122,7 +122,7 @@ def run_reference(args):
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -162,8 +162,6 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"       # NCCL prints its version banner on STDOUT; keep stdout = the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     from cpfn_b200 import api, cuda_ops, fused
     from cpfn_b200.spfn import fit as fitmod
@@ -321,14 +319,35 @@ def run_ours(args):
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "clocks": clocks,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
         dist.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def _claim_stdout():
+    """Libraries (NCCL's version banner, for one) write to file descriptor 1.  The contract is ONE JSON line on
+    stdout: keep a private duplicate of the real stdout for that line and point fd 1 at stderr for everything else."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
