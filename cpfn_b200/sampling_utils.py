@@ -87,6 +87,14 @@ class _Extractor:
         return idx[0], radius_host
 
 
+def _check_lr(gt_points_lr):
+    """numpy would compute ``seed - gt_points_hr`` in the wider of the two dtypes: with a float64 low-res cloud the
+    reference's distances are float64 arithmetic, which the float32 kernel does not reproduce."""
+    if gt_points_lr.dtype != np.float32:
+        raise TypeError("gt_points_lr must be float32 (as the reference's preprocessing writes it), got %s"
+                        % gt_points_lr.dtype)
+
+
 def _prune(gt_points_lr, i, pool_indices, radius):
     distances = np.linalg.norm(np.expand_dims(gt_points_lr[i], axis=0) - gt_points_lr[pool_indices], axis=1)
     return np.where(distances <= radius)[0]
@@ -95,6 +103,7 @@ def _prune(gt_points_lr, i, pool_indices, radius):
 def sample(gt_points_lr, gt_points_hr, pool_indices, num_points_patch=8192, max_number_patches=32, device="cuda:0"):
     """Utils/sampling_utils.py:4-19.  Returns int64 [n_patches, num_points_patch]."""
     gt_points_lr = np.asarray(gt_points_lr)
+    _check_lr(gt_points_lr)
     pool_indices = np.asarray(pool_indices)
     extractor = _Extractor(gt_points_hr, num_points_patch, device)
     patches = []
@@ -111,6 +120,7 @@ def sample_per_label(gt_points_lr, gt_points_hr, pool_indices, pool_labels, num_
     """``sample`` of Preprocessing/preprocessing_sampling_patch.py:22-47: round-robin over the labels that
     still have pool points, one seed per label and round."""
     gt_points_lr = np.asarray(gt_points_lr)
+    _check_lr(gt_points_lr)
     pool_indices, pool_labels = np.asarray(pool_indices), np.asarray(pool_labels)
     extractor = _Extractor(gt_points_hr, num_points_patch, device)
     patches = []

@@ -40,3 +40,14 @@ def test_ties_are_ordered_by_index():
     hr[:, 0] = np.repeat(np.arange(8), 8)            # eight groups of eight identical points
     idx, dist = opatch.nearest(np.zeros(3, np.float32), hr, 12)
     assert idx.tolist() == list(range(12)) and dist.tolist() == [0.0] * 8 + [1.0] * 4
+
+
+def test_host_mirror_rejects_float64_clouds(built_lib):
+    """numpy computes the reference's distances in the wider dtype of the two clouds; only the float32 arithmetic
+    is implemented, so float64 inputs are refused before any GPU work (no silent down-cast)."""
+    from cpfn_b200 import sampling_utils
+    pts = np.random.RandomState(0).randn(50, 3)
+    with pytest.raises(TypeError):
+        sampling_utils.sample(pts, pts.astype(np.float32), np.arange(10), 16, 2)
+    with pytest.raises(TypeError):
+        sampling_utils.sample_per_label(pts, pts.astype(np.float32), np.arange(10), np.zeros(10, int), 16, 2)
