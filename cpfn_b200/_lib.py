@@ -68,6 +68,7 @@ SIGNATURES = {
                                       c_void_p, c_void_p, c_size_t, c_void_p]),
     "cpfn_heuristic_merging_host": (c_int, [c_void_p, c_void_p, ctypes.c_int64, c_void_p, ctypes.c_int64, c_void_p]),
     "cpfn_merge_solve_host": (c_int, [c_void_p, ctypes.c_int64, ctypes.c_double, c_void_p, c_void_p]),
+    "cpfn_merge_solve_host_f32": (c_int, [c_void_p, ctypes.c_int64, c_float, c_void_p, c_void_p]),
     "cpfn_merge_point_labels": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                         c_int, c_int, c_void_p, c_void_p]),
     "cpfn_merge_dense_labels": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),

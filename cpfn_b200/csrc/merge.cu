@@ -397,79 +397,129 @@ extern "C" int cpfn_merge_normals_types(const float *X, const float *T, const in
 // The reference repeatedly takes the arg-max pair, merges the two segments, ORs their patch sets and drops
 // every pair whose segments now share a patch.  Patch sets only grow, so a dropped pair stays dropped: the
 // same result comes from ONE pass over the pairs in stable descending order of the penalty, merging a pair
-// iff its segments' patch sets are disjoint when it is reached -- except the very first pair, which the
-// reference merges before any filtering.
+// iff its segments' patch sets are disjoint when it is reached -- except the very first pair (the first
+// maximum in the reference's pair order), which the reference merges before any filtering.  Pairs inside one
+// patch can therefore only ever merge as that first pair and are not even sorted.
 namespace {
 
-// Order-preserving key of a double, inverted: ascending keys == descending values.
+struct PairRec {
+  uint64_t key;       // order-preserving bits of the penalty, inverted: ascending keys == descending penalties
+  int32_t a, b;
+};
+
 inline uint64_t descending_key(double v) {
   uint64_t k;
   memcpy(&k, &v, sizeof(k));
   k = (k >> 63) ? ~k : (k | (1ull << 63));
   return ~k;
 }
+inline uint64_t descending_key(float v) {           // 32 significant bits: three radix passes instead of six
+  uint32_t k;
+  memcpy(&k, &v, sizeof(k));
+  k = (k >> 31) ? ~k : (k | (1u << 31));
+  return static_cast<uint32_t>(~k);
+}
 
-// Stable LSD radix sort of (key, position) records by key; passes whose digit is constant are skipped
-// (penalties that were float32 have 29 zero low bits).
-void radix_sort_records(std::vector<std::pair<uint64_t, int64_t>> &rec) {
-  std::vector<std::pair<uint64_t, int64_t>> tmp(rec.size());
-  for (int shift = 0; shift < 64; shift += 11) {
-    size_t count[2049] = {0};
-    for (const auto &r : rec) ++count[((r.first >> shift) & 2047) + 1];
+// Stable LSD radix sort by key over `bits` key bits, 8 bits per pass (256 output streams stay in L1; 2048 of
+// them did not and made the scatter the slowest part of the solve); passes whose digit is constant are skipped.
+// Scratch vectors live per host thread: a solve needs ~2 MB of them, and fresh allocations of that size are
+// mapped and page-faulted on every call (measured: most of the solve's time in a container).
+std::vector<PairRec> &scratch(int which) {
+  static thread_local std::vector<PairRec> v[2];
+  return v[which];
+}
+
+void radix_sort_records(std::vector<PairRec> &rec, int bits) {
+  std::vector<PairRec> &tmp = scratch(1);
+  tmp.resize(rec.size());
+  size_t count[257];
+  for (int shift = 0; shift < bits; shift += 8) {
+    std::fill(count, count + 257, 0);
+    for (const PairRec &r : rec) ++count[((r.key >> shift) & 255) + 1];
     bool single = false;
-    for (int d = 1; d <= 2048; ++d) single = single || count[d] == rec.size();
+    for (int d = 1; d <= 256 && !single; ++d) single = count[d] == rec.size();
     if (single) continue;
-    for (int d = 1; d <= 2048; ++d) count[d] += count[d - 1];
-    for (const auto &r : rec) tmp[count[(r.first >> shift) & 2047]++] = r;
+    for (int d = 1; d <= 256; ++d) count[d] += count[d - 1];
+    for (const PairRec &r : rec) tmp[count[(r.key >> shift) & 255]++] = r;
     rec.swap(tmp);
   }
 }
 
-// The greedy merge itself; pairs / penalty in the reference's order (np.where order, i < j).
-int greedy_merge(const int64_t *pairs, const double *penalty, int64_t n_pairs, const int64_t *patch_id,
-                 int64_t n_nodes, int64_t *segment_id) {
-  int64_t n_patch = 0;
-  for (int64_t i = 0; i < n_nodes; ++i) {
-    if (patch_id[i] < 0) return CPFN_EINVAL;
-    n_patch = std::max(n_patch, patch_id[i] + 1);
+class Segments {                                       // segment labels + the patch set of every label
+ public:
+  Segments(const int64_t *patch_id, int64_t n_nodes, int64_t *segment_id) : n_(n_nodes), seg_(segment_id) {
+    int64_t n_patch = 0;
+    for (int64_t i = 0; i < n_; ++i) n_patch = std::max(n_patch, patch_id[i] + 1);
+    words_ = static_cast<size_t>((n_patch + 63) / 64);
+    mask_.assign(static_cast<size_t>(n_) * words_, 0);
+    for (int64_t i = 0; i < n_; ++i) {
+      seg_[i] = i;
+      mask_[static_cast<size_t>(i) * words_ + static_cast<size_t>(patch_id[i] / 64)] |= 1ull << (patch_id[i] % 64);
+    }
   }
-  const size_t words = static_cast<size_t>((n_patch + 63) / 64);
-  std::vector<uint64_t> mask(static_cast<size_t>(n_nodes) * words, 0);      // patch set of segment label l
-  for (int64_t i = 0; i < n_nodes; ++i) {
-    segment_id[i] = i;
-    mask[static_cast<size_t>(i) * words + static_cast<size_t>(patch_id[i] / 64)] |= 1ull << (patch_id[i] % 64);
+  // merges the segment of b into the segment of a (as :24-27 do); `unconditional` skips the patch-set test
+  void offer(int64_t a, int64_t b, bool unconditional) {
+    const int64_t la = seg_[a], lb = seg_[b];
+    uint64_t *ma = mask_.data() + static_cast<size_t>(la) * words_, *mb = mask_.data() + static_cast<size_t>(lb) * words_;
+    if (!unconditional)
+      for (size_t w = 0; w < words_; ++w)
+        if (ma[w] & mb[w]) return;
+    if (la == lb) return;
+    for (int64_t i = 0; i < n_; ++i)
+      if (seg_[i] == lb) seg_[i] = la;
+    for (size_t w = 0; w < words_; ++w) ma[w] |= mb[w];
   }
-  // Pairs inside one patch can only ever merge as the very first pair (their patch sets always clash), so
-  // apart from the overall first maximum they are dropped before the sort.
-  int64_t first_pair = -1;
-  for (int64_t i = 0; i < n_pairs; ++i)
-    if (first_pair < 0 || penalty[i] > penalty[first_pair]) first_pair = i;
-  std::vector<std::pair<uint64_t, int64_t>> order;
-  order.reserve(static_cast<size_t>(n_pairs));
-  for (int64_t i = 0; i < n_pairs; ++i) {
-    const int64_t a = pairs[2 * i], b = pairs[2 * i + 1];
-    if (a < 0 || b < 0 || a >= n_nodes || b >= n_nodes) return CPFN_EINVAL;
-    if (i == first_pair || patch_id[a] != patch_id[b]) order.emplace_back(descending_key(penalty[i]), i);
-  }
-  radix_sort_records(order);                                                  // stable: ties keep the reference's order
+
+ private:
+  int64_t n_;
+  int64_t *seg_;
+  size_t words_ = 1;
+  std::vector<uint64_t> mask_;
+};
+
+// `rec`: the cross-patch pairs in the reference's pair order; (fa, fb): the first maximum over ALL pairs when it
+// is a pair inside one patch (else fa < 0: the first maximum is then simply the first record after the sort).
+void greedy_merge(std::vector<PairRec> &rec, int key_bits, int64_t fa, int64_t fb, Segments &segs) {
+  radix_sort_records(rec, key_bits);                   // stable: ties keep the reference's order
   bool first = true;
-  for (const auto &rec : order) {
-    const int64_t o = rec.second;
-    const int64_t a = pairs[2 * o], b = pairs[2 * o + 1];
-    const int64_t la = segment_id[a], lb = segment_id[b];
-    uint64_t *ma = mask.data() + static_cast<size_t>(la) * words, *mb = mask.data() + static_cast<size_t>(lb) * words;
-    if (!first) {
-      bool clash = false;
-      for (size_t w = 0; w < words && !clash; ++w) clash = (ma[w] & mb[w]) != 0;
-      if (clash) continue;
-    }
+  if (fa >= 0) { segs.offer(fa, fb, true); first = false; }
+  for (const PairRec &r : rec) {
+    segs.offer(r.a, r.b, first);
     first = false;
-    if (la != lb) {
-      for (int64_t i = 0; i < n_nodes; ++i)
-        if (segment_id[i] == lb) segment_id[i] = la;
-      for (size_t w = 0; w < words; ++w) ma[w] |= mb[w];
+  }
+}
+
+bool valid_patch_ids(const int64_t *patch_id, int64_t n_nodes) {
+  for (int64_t i = 0; i < n_nodes; ++i)
+    if (patch_id[i] < 0) return false;
+  return true;
+}
+
+// The pair list of run_heuristic_solver (:37-39: similarity > threshold, i < j, np.where order) straight from
+// the matrix, then the greedy merge.
+template <typename T>
+int solve_from_matrix(const T *similarity, int64_t n_nodes, T threshold, const int64_t *patch_id, int64_t *segment_id) {
+  if (n_nodes <= 0 || n_nodes > 0x7fffffff || !similarity || !patch_id || !segment_id || !valid_patch_ids(patch_id, n_nodes))
+    return CPFN_EINVAL;
+  std::vector<PairRec> &rec = scratch(0);
+  rec.clear();
+  bool have_best = false, best_same_patch = false;
+  T best = 0;
+  int64_t fa = -1, fb = -1;
+  for (int64_t i = 0; i < n_nodes; ++i) {
+    const T *row = similarity + i * n_nodes;
+    const int64_t pi = patch_id[i];
+    for (int64_t j = i + 1; j < n_nodes; ++j) {
+      const T v = row[j];
+      if (!(v > threshold)) continue;
+      const bool same = patch_id[j] == pi;
+      if (!have_best || v > best) { have_best = true; best = v; best_same_patch = same; fa = i; fb = j; }
+      if (!same) rec.push_back(PairRec{descending_key(v), static_cast<int32_t>(i), static_cast<int32_t>(j)});
     }
   }
+  Segments segs(patch_id, n_nodes, segment_id);
+  if (!best_same_patch) fa = fb = -1;
+  greedy_merge(rec, sizeof(T) == 4 ? 32 : 64, fa, fb, segs);
   return CPFN_OK;
 }
 
@@ -477,19 +527,34 @@ int greedy_merge(const int64_t *pairs, const double *penalty, int64_t n_pairs, c
 
 extern "C" int cpfn_heuristic_merging_host(const int64_t *pairs, const double *penalty, int64_t n_pairs,
                                            const int64_t *patch_id, int64_t n_nodes, int64_t *segment_id) {
-  if (n_nodes <= 0 || !patch_id || !segment_id || n_pairs < 0 || (n_pairs > 0 && (!pairs || !penalty))) return CPFN_EINVAL;
-  return greedy_merge(pairs, penalty, n_pairs, patch_id, n_nodes, segment_id);
+  if (n_nodes <= 0 || n_nodes > 0x7fffffff || !patch_id || !segment_id || n_pairs < 0 || (n_pairs > 0 && (!pairs || !penalty)) ||
+      !valid_patch_ids(patch_id, n_nodes))
+    return CPFN_EINVAL;
+  std::vector<PairRec> &rec = scratch(0);
+  rec.clear();
+  int64_t first_pair = -1;
+  for (int64_t i = 0; i < n_pairs; ++i) {
+    const int64_t a = pairs[2 * i], b = pairs[2 * i + 1];
+    if (a < 0 || b < 0 || a >= n_nodes || b >= n_nodes) return CPFN_EINVAL;
+    if (first_pair < 0 || penalty[i] > penalty[first_pair]) first_pair = i;
+  }
+  int64_t fa = -1, fb = -1;
+  for (int64_t i = 0; i < n_pairs; ++i) {
+    const int64_t a = pairs[2 * i], b = pairs[2 * i + 1];
+    if (patch_id[a] != patch_id[b]) rec.push_back(PairRec{descending_key(penalty[i]), static_cast<int32_t>(a), static_cast<int32_t>(b)});
+    else if (i == first_pair) { fa = a; fb = b; }
+  }
+  Segments segs(patch_id, n_nodes, segment_id);
+  greedy_merge(rec, 64, fa, fb, segs);
+  return CPFN_OK;
 }
 
 extern "C" int cpfn_merge_solve_host(const double *similarity, int64_t n_nodes, double threshold,
                                      const int64_t *patch_id, int64_t *segment_id) {
-  if (n_nodes <= 0 || !similarity || !patch_id || !segment_id) return CPFN_EINVAL;
-  std::vector<int64_t> pairs;
-  std::vector<double> penalty;
-  for (int64_t i = 0; i < n_nodes; ++i)                                       // np.where order, kept where i < j
-    for (int64_t j = i + 1; j < n_nodes; ++j) {
-      const double v = similarity[i * n_nodes + j];
-      if (v > threshold) { pairs.push_back(i); pairs.push_back(j); penalty.push_back(v); }
-    }
-  return greedy_merge(pairs.data(), penalty.data(), static_cast<int64_t>(penalty.size()), patch_id, n_nodes, segment_id);
+  return solve_from_matrix<double>(similarity, n_nodes, threshold, patch_id, segment_id);
+}
+
+extern "C" int cpfn_merge_solve_host_f32(const float *similarity, int64_t n_nodes, float threshold,
+                                         const int64_t *patch_id, int64_t *segment_id) {
+  return solve_from_matrix<float>(similarity, n_nodes, threshold, patch_id, segment_id);
 }

@@ -88,13 +88,19 @@ def run_heuristic_solver(similarity_matrix, nb_patches, max_label_per_object, ma
     similarity_matrix = np.asarray(similarity_matrix)
     patch_id = np.concatenate((np.repeat(np.arange(nb_patches), repeats=max_label_per_patch, axis=0),
                                nb_patches * np.ones([max_label_per_object], dtype=int)), axis=0).astype(np.int64)
-    sim64 = np.ascontiguousarray(similarity_matrix, dtype=np.float64)      # exact for the float32 the reference passes
-    if sim64.ndim != 2 or sim64.shape[0] != sim64.shape[1] or sim64.shape[0] != len(patch_id):
+    if similarity_matrix.ndim != 2 or similarity_matrix.shape[0] != similarity_matrix.shape[1] or \
+            similarity_matrix.shape[0] != len(patch_id):
         raise ValueError("similarity_matrix must be [nb*Kl+Kg, nb*Kl+Kg]")
     labels = np.empty(len(patch_id), dtype=np.int64)
     as_p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
-    _lib.check(_lib.lib().cpfn_merge_solve_host(as_p(sim64), len(patch_id), float(threshold), as_p(patch_id), as_p(labels)),
-               "merge_solve")
+    if similarity_matrix.dtype == np.float32:
+        # numpy compares a float32 array with a Python scalar in float32 (the scalar is cast first)
+        sim = np.ascontiguousarray(similarity_matrix)
+        rc = _lib.lib().cpfn_merge_solve_host_f32(as_p(sim), len(patch_id), float(np.float32(threshold)), as_p(patch_id), as_p(labels))
+    else:
+        sim = np.ascontiguousarray(similarity_matrix, dtype=np.float64)
+        rc = _lib.lib().cpfn_merge_solve_host(as_p(sim), len(patch_id), float(threshold), as_p(patch_id), as_p(labels))
+    _lib.check(rc, "merge_solve")
     flag = np.diag(similarity_matrix)
     replacement_values = np.concatenate((np.tile(np.arange(-max_label_per_patch, 0), nb_patches),
                                          np.arange(-max_label_per_object, 0)), axis=0)

@@ -300,6 +300,9 @@ CPFN_API int cpfn_heuristic_merging_host(const int64_t *pairs, const double *pen
  * taken straight from the HOST matrix similarity f64 [n_nodes,n_nodes], then the same greedy merge. */
 CPFN_API int cpfn_merge_solve_host(const double *similarity, int64_t n_nodes, double threshold,
                                    const int64_t *patch_id, int64_t *segment_id);
+/* The same for the float32 matrix similarity_soft returns (what the reference passes): no conversion, 32-bit sort keys. */
+CPFN_API int cpfn_merge_solve_host_f32(const float *similarity, int64_t n_nodes, float threshold,
+                                       const int64_t *patch_id, int64_t *segment_id);
 
 /* Fused evaluation_localSPFN.py:103-111 + get_point_final (merging_utils.py:46-50): labels int32 [M] in
  * [0,L), label_weight f32 [L] = 1/(members+1e-10); out [Ng,L].  Points inside a patch drop the object block. */
