@@ -73,3 +73,29 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
         _lib.lib()
+
+
+def test_argument_validation_needs_no_gpu(built_lib):
+    """Every entry point checks its arguments before it touches CUDA: invalid calls return CPFN_EINVAL (-1) /
+    CPFN_EWORKSPACE (-3) on a machine without a GPU, and the workspace-size helpers are pure host arithmetic."""
+    L = _lib.lib()
+    null = None
+    one = ctypes.c_void_p(16)                       # a non-null, never dereferenced pointer
+    assert L.cpfn_furthest_point_sampling(null, 2, 100, 10, one, null, 0, null) == -1
+    assert L.cpfn_ball_query(null, null, 2, 100, 10, 0.2, 4, null, null) == -1
+    assert L.cpfn_extract_patches(one, 100, one, 1, 200, one, null, null, one, 1 << 30, null) == -1       # k > N
+    assert L.cpfn_extract_patches(one, 100000, one, 1, 20000, one, null, null, one, 1 << 30, null) == -1  # k > 16384
+    assert L.cpfn_extract_patches(one, 100, one, 1, 10, one, null, null, null, 0, null) == -3             # no workspace
+    assert L.cpfn_extract_patches_workspace_bytes(131072, 32, 8192) >= 32 * (131072 * 4 + 8192 * 8)
+    assert L.cpfn_merge_inverse_bytes(32, 131072) == 32 * 131072 * 4
+    assert L.cpfn_merge_similarity_workspace_bytes(32, 21, 28) == 700 * 700 * 8
+    assert L.cpfn_merge_similarity(one, one, one, one, 2, 64, 40, 1000, 28, one, one, 1 << 30, null) == -1  # Kl > 32
+    assert L.cpfn_merge_point_labels(one, one, one, one, one, 2, 64, 21, 1000, 28, 5000, one, null) == -1   # L too large
+    assert L.cpfn_merge_normals_types(one, one, one, one, one, 2, 64, 1000, 9, one, one, null) == -1        # n_types > 8
+    assert L.cpfn_primitive_residues(one, one, one, 0, 0, 1, 4, 4, 16, null, 4, one, one, null) == -1       # no class list
+    assert L.cpfn_p_coverage(one, one, one, one, 1, 4, 4, 100, one, 5, one, null) == -1                      # > 4 thresholds
+    assert L.cpfn_fps_dense(one, 100, null, null, 0, 100, 10, one, one, 1 << 20, null) == -1                 # start outside the cloud
+    assert L.cpfn_fps_dense(one, 100, null, null, 0, 0, 10, one, null, 0, null) == -3
+    assert L.cpfn_fps_dense_workspace_bytes() > 0
+    assert L.cpfn_heuristic_merging_host(null, null, 0, null, 4, null) == -1
+    assert L.cpfn_merge_solve_host_f32(null, 4, 0.0, null, null) == -1
