@@ -72,8 +72,8 @@ def make_inputs(n_batches, batch, seed):
 
 
 def model_state(template):
-    from tests.golden import cases
-    return {k: torch.from_numpy(v) for k, v in cases.network_state(template, seed=1234).items()}
+    from cpfn_b200 import synth
+    return {k: torch.from_numpy(v) for k, v in synth.network_state(template, seed=1234).items()}
 
 
 # ----------------------------------------------------------------------------------------------

@@ -56,6 +56,8 @@ SIGNATURES = {
     "cpfn_three_nn_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "cpfn_linear_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "cpfn_gather_xyz": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "cpfn_rng_set": (c_int, [c_void_p, ctypes.c_ulonglong, ctypes.c_ulonglong, c_void_p]),
+    "cpfn_dropout_mask_bits": (c_int, [c_void_p, c_int, c_int, c_int, c_float, ctypes.c_longlong, c_void_p, c_void_p]),
     "cpfn_spfn_post": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_void_p]),
     "cpfn_extract_patches_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),

@@ -23,14 +23,34 @@ class GlobalSPFN:
             p.requires_grad_(False)
         self._pin = {}
         self._graphs = {}
+        self._sources = None
+        self._graph_sig = None
 
     def load_state_dict(self, sd, strict=True):
         """Reference-layout state dict (training_SPFN.py:72-74 loads with strict=True)."""
         out = self.model.load_state_dict(sd, strict=strict)
+        self.invalidate()
+        return out
+
+    def invalidate(self):
+        """Forget the captured graphs and the packed weights.  Weight changes are detected without this (every
+        replay compares the parameters' version counters with the ones the graphs were captured from); call it
+        after REPLACING parameter objects of ``self.model``."""
         from . import fused
         fused.invalidate(self.model)
         self._graphs.clear()
-        return out
+        self._sources = None
+
+    def _weights_changed(self):
+        """True when a parameter / BatchNorm statistic of the model was written since the graphs were captured
+        (their packed weight images are baked into the graphs)."""
+        from . import fused
+        if self._sources is None:
+            self._sources = fused.model_sources(self.model)
+        sig = fused.signature(self._sources)
+        changed = self._graph_sig is not None and sig != self._graph_sig
+        self._graph_sig = sig
+        return changed
 
     @torch.no_grad()
     def forward(self, P, dropout=True, fit=True):
@@ -40,10 +60,18 @@ class GlobalSPFN:
         ``dropout=False`` replaces the reference's always-on dropout by the identity (parity runs)."""
         from . import fused
         if fused.available():
+            if not P.is_cuda:
+                raise RuntimeError("CPU not supported")
             heads, l3_feats, feat, l1_xyz, l2_xyz, packed = fused.pointnet2_forward(self.model, P, dropout=dropout)
-            out = {"X_raw": heads[0], "T_raw": heads[1], "W_raw": heads[2], "l3_feats": l3_feats,
-                   "output_feat": feat, "l1_pos": l1_xyz.permute(0, 2, 1), "l2_pos": l2_xyz.permute(0, 2, 1)}
-            if len(heads) == 3 and heads[0].shape[2] == 3 and heads[2].shape[2] <= 64:
+            out = {"heads": list(heads), "l3_feats": l3_feats, "output_feat": feat,
+                   "l1_pos": l1_xyz.permute(0, 2, 1), "l2_pos": l2_xyz.permute(0, 2, 1)}
+            if len(heads) != 3:
+                # not the SPFN head layout (PatchSelection: one head of two logits, evaluation_PatchSelection.py:45):
+                # the raw heads are the result, there is nothing to fit
+                out["X_raw"] = heads[0]
+                return out
+            out.update({"X_raw": heads[0], "T_raw": heads[1], "W_raw": heads[2]})
+            if heads[0].shape[2] == 3 and heads[2].shape[2] <= 64:
                 # SPFN post-processing (Utils/training_utils.py:141-142) in one kernel
                 nt = heads[1].shape[2]
                 out["X"], out["W"], out["instance"], out["type"] = fused.spfn_post(packed, 0, 3 + nt, heads[2].shape[2],
@@ -55,27 +83,8 @@ class GlobalSPFN:
             if fit:
                 out["parameters"], out["parameters_packed"] = L.compute_parameters_packed(P, out["W"], out["X"], self.classes)
             return out
-        m = self.model
-        x = P.transpose(2, 1)
-        pos = x[:, :3, :]
-        l1_pos, l1_feats = m.sa1(pos, None)
-        l2_pos, l2_feats = m.sa2(l1_pos, l1_feats)
-        _, l3_feats = m.sa3(l2_pos, l2_feats)
-        l4 = m.sfp1(l2_pos, None, l2_feats, l3_feats)
-        l5 = m.sfp2(l1_pos, l2_pos, l1_feats, l4)
-        l6 = m.sfp3(pos, l1_pos, None, l5)
-        feat = torch.relu(m.bn1(m.fc1(l6)))
-        if dropout:
-            feat = torch.nn.functional.dropout(feat, p=0.5)
-        heads = [fc(feat).transpose(1, 2) for fc in m.fc2]
-        out = {"X_raw": heads[0], "T_raw": heads[1], "W_raw": heads[2], "l3_feats": l3_feats,
-               "output_feat": feat, "l1_pos": l1_pos, "l2_pos": l2_pos}
-        out["X"] = torch.nn.functional.normalize(heads[0], p=2, dim=2, eps=1e-12)
-        out["T"] = heads[1]
-        out["W"] = torch.softmax(heads[2], dim=2)
-        if fit:
-            out["parameters"] = L.compute_parameters(P, out["W"], out["X"], self.classes)
-        return out
+        raise RuntimeError("cpfn_b200: the fused CUDA path is unavailable (no CUDA device, or libcpfn_b200.so lacks "
+                           "cpfn_mlp_chain); there is no fallback")
 
     def _capture(self, fn):
         """Warm ``fn`` up on a side stream (packs weights, sizes workspaces, sets kernel attributes),
@@ -103,13 +112,23 @@ class GlobalSPFN:
         graph-safe generator)."""
         graph, static_in, out, n_launch = self._net_graph(P, dropout, fit, 0)
         static_in.copy_(P, non_blocking=True)
+        if dropout:
+            self._sync_rng(P.shape)
         graph.replay()
         cuda_ops.count_launches(n_launch)
         return out
 
+    def _sync_rng(self, shape):
+        """A captured forward draws its dropout mask from the device-side RNG state: refresh it from torch's
+        generator before every replay (fused.sync_rng)."""
+        from . import fused
+        fused.sync_rng(self.device, shape[0] * 128 * shape[1])
+
     def _net_graph(self, P, dropout, fit, slot):
         """(graph, its static input, its static outputs, launches) for inputs shaped like P; ``slot`` selects one
         of several independent copies (own input / output buffers) so that consecutive batches can overlap."""
+        if self._weights_changed():
+            self._graphs.clear()
         key = (tuple(P.shape), bool(dropout), bool(fit)) + ((slot,) if slot else ())
         entry = self._graphs.get(key)
         if entry is None:
@@ -166,6 +185,8 @@ class GlobalSPFN:
             main.wait_event(arrived)
             if sent[slot] is not None:
                 main.wait_event(sent[slot])                   # the graph overwrites what that copy reads
+            if dropout:
+                self._sync_rng(P_host.shape)
             graph.replay()
             cuda_ops.count_launches(n_launch)
             ready = torch.cuda.Event()

@@ -149,6 +149,89 @@ linear_rows_kernel(const float *__restrict__ x, const float *__restrict__ W, con
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if (lane == 0) out[static_cast<size_t>(r) * ldo + co] = acc + __ldg(bias + co);
+  if (co == 0)                                  // zero padding of the row (columns cout .. ldo-1)
+    for (int k = cout + lane; k < ldo; k += 32) out[static_cast<size_t>(r) * ldo + k] = 0.f;
+}
+
+// ---- dropout keep-mask as bits, drawn from torch's own Philox stream ----------------------------
+// Philox4x32-10 as curand implements it (curand_philox4x32_x.h; torch's fused_dropout_kernel_vec calls
+// curand_init(seed, thread, offset) + curand_uniform4 per 4 consecutive elements).
+__device__ __forceinline__ uint4 philox_round(uint4 c, uint2 k) {
+  const unsigned int hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+  const unsigned int hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+  return make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+}
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 9; ++r) {
+    c = philox_round(c, k);
+    k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+  }
+  return philox_round(c, k);
+}
+// curand_uniform: x * 2^-32 + 2^-33 in fp32, in (0, 1]
+__device__ __forceinline__ bool keep_bit(unsigned int x, float keep) {
+  return __fmaf_rn(__uint2float_rn(x), 2.3283064e-10f, 1.16415322e-10f) < keep;
+}
+
+__global__ void rng_set_kernel(unsigned long long *state, unsigned long long seed, unsigned long long offset) {
+  state[0] = seed;
+  state[1] = offset;
+}
+
+// One thread per (4 consecutive rows, 32-channel word).  Element (b, c, n) of the channel-major tensor has linear
+// index e = (b*C + c)*N + n; torch's thread (e/4) % T draws it in iteration (e/4) / T as component e % 4.
+__global__ void __launch_bounds__(kGlueThreads)
+dropout_bits_kernel(const unsigned long long *__restrict__ state, int C, int N, long long rows, float keep,
+                    unsigned int T, int words, uint32_t *__restrict__ bits) {
+  const long long t = static_cast<long long>(blockIdx.x) * kGlueThreads + threadIdx.x;
+  const long long quad = t / words;
+  const int cw = static_cast<int>(t - quad * words);
+  const long long r0 = quad * 4;
+  if (r0 >= rows) return;
+  const unsigned long long seed = state[0], off4 = state[1] >> 2;
+  const uint2 key = make_uint2(static_cast<unsigned int>(seed), static_cast<unsigned int>(seed >> 32));
+  unsigned long long base[4];
+  int nr = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long r = r0 + i;
+    if (r < rows) {
+      const long long b = r / N;
+      base[i] = static_cast<unsigned long long>(b) * C * N + static_cast<unsigned long long>(r - b * N);
+      nr = i + 1;
+    } else {
+      base[i] = 0;
+    }
+  }
+  uint32_t w[4] = {0u, 0u, 0u, 0u};
+  const int c_end = min(C, cw * 32 + 32);
+  for (int c = cw * 32; c < c_end; ++c) {
+    unsigned long long have = ~0ull;
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (i < nr) {
+        const unsigned long long e = base[i] + static_cast<unsigned long long>(c) * N;
+        const unsigned long long q = e >> 2;
+        if (q != have) {
+          unsigned long long k;
+          if ((q >> 32) == 0) k = static_cast<unsigned int>(q) / T;       // 32-bit division in the common case
+          else k = q / T;
+          const unsigned long long sub = q - k * T, ctr = off4 + k;
+          o = philox4x32_10(make_uint4(static_cast<unsigned int>(ctr), static_cast<unsigned int>(ctr >> 32),
+                                       static_cast<unsigned int>(sub), 0u), key);
+          have = q;
+        }
+        const int comp = static_cast<int>(e & 3);
+        const unsigned int x = comp == 0 ? o.x : (comp == 1 ? o.y : (comp == 2 ? o.z : o.w));
+        if (keep_bit(x, keep)) w[i] |= 1u << (c & 31);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (i < nr) bits[(r0 + i) * words + cw] = w[i];
 }
 
 }  // namespace
@@ -163,6 +246,30 @@ extern "C" int cpfn_linear_rows(const float *x, const float *W, const float *bia
   const long long warps = static_cast<long long>(rows) * cout;
   const unsigned grid = static_cast<unsigned>((warps * 32 + kGlueThreads - 1) / kGlueThreads);
   linear_rows_kernel<<<grid, kGlueThreads, 0, as_stream(stream)>>>(x, W, bias, rows, cin, cout, ldo, out);
+  return check_launch();
+}
+
+extern "C" int cpfn_rng_set(unsigned long long *rng_state, unsigned long long seed, unsigned long long offset,
+                            cpfn_stream_t stream) {
+  using namespace cpfn;
+  if (!rng_state) return CPFN_EINVAL;
+  rng_set_kernel<<<1, 1, 0, as_stream(stream)>>>(rng_state, seed, offset);
+  return check_launch();
+}
+
+extern "C" int cpfn_dropout_mask_bits(const unsigned long long *rng_state, int B, int C, int N, float keep_prob,
+                                      long long torch_threads, uint32_t *bits, cpfn_stream_t stream) {
+  using namespace cpfn;
+  if (B < 0 || C <= 0 || N < 0 || torch_threads <= 0 || torch_threads > 0xFFFFFFFFll) return CPFN_EINVAL;
+  if (B == 0 || N == 0) return CPFN_OK;
+  if (!rng_state || !bits) return CPFN_EINVAL;
+  const int words = (C + 31) / 32;
+  const long long rows = static_cast<long long>(B) * N;
+  const long long threads = ((rows + 3) / 4) * words;
+  const long long grid = (threads + kGlueThreads - 1) / kGlueThreads;
+  if (grid > 0x7FFFFFFFll) return CPFN_EINVAL;
+  dropout_bits_kernel<<<static_cast<unsigned>(grid), kGlueThreads, 0, as_stream(stream)>>>(
+      rng_state, C, N, rows, keep_prob, static_cast<unsigned int>(torch_threads), words, bits);
   return check_launch();
 }
 

@@ -53,7 +53,9 @@ constexpr int kMiscBytes = 8192;     // barriers, TMEM slot, per-row loader scra
 struct LayerP {
   int cin_atoms, ksteps, cout_chunks, cout, relu, bias_per_cloud, next_k16;
   const float *bias;
-  const float *mask;
+  const uint32_t *mask_bits;   // dropout keep bits, [col][mask_words] (bit ch%32 of word ch/32)
+  float mask_scale;
+  int mask_words;
   float *out_cm;
 };
 
@@ -431,7 +433,7 @@ mlp_chain_kernel(const __grid_constant__ ChainP p) {
         const bool last = (l == p.n_layers - 1);
         const uint32_t out_buf = smem_u32(act0);
         const int cout_pad = L.cout_chunks * 128;
-        const bool slow = (L.mask != nullptr) || (L.out_cm != nullptr);
+        const bool slow = (L.mask_bits != nullptr) || (L.out_cm != nullptr);
         const int n_chunks = p.split_cout ? 1 : L.cout_chunks;
         const int chunk_base = p.split_cout ? static_cast<int>(blockIdx.y) : 0;
         for (int m0 = 0; m0 < n_chunks; m0 += wave_max) {
@@ -462,9 +464,11 @@ mlp_chain_kernel(const __grid_constant__ ChainP p) {
 #pragma unroll
                 for (int i4 = 0; i4 < 4; ++i4) {
                   if (col0 + c + i4 * 4 < p.cols) {    // tiles are cloud-aligned here: whole quads are valid
-                    if (L.mask != nullptr) {
-                      const float4 mk = __ldg(reinterpret_cast<const float4 *>(L.mask + cm_base + c) + i4);
-                      v[i4 * 4] *= mk.x; v[i4 * 4 + 1] *= mk.y; v[i4 * 4 + 2] *= mk.z; v[i4 * 4 + 3] *= mk.w;
+                    if (L.mask_bits != nullptr) {
+                      const uint32_t *mb = L.mask_bits + (col0 + c + i4 * 4) * L.mask_words + (ch >> 5);
+#pragma unroll
+                      for (int q = 0; q < 4; ++q)
+                        v[i4 * 4 + q] = ((__ldg(mb + q * L.mask_words) >> (ch & 31)) & 1u) ? v[i4 * 4 + q] * L.mask_scale : 0.f;
                     }
                     if (L.out_cm != nullptr)
                       reinterpret_cast<float4 *>(L.out_cm + cm_base + c)[i4] =
@@ -650,8 +654,16 @@ mlp_chain_pm1_kernel(const __grid_constant__ ChainP p) {
         const bool last = (l == p.n_layers - 1);
         const uint32_t out_buf = smem_u32(act0);
         const int cout_pad = L.cout_chunks * 128, cout16 = (L.cout + 15) & ~15;
-        const bool slow = (L.mask != nullptr) || (L.out_cm != nullptr);
+        const bool slow = (L.mask_bits != nullptr) || (L.out_cm != nullptr);
         const float *bias_base = L.bias + (L.bias_per_cloud ? cloud * cout_pad : 0);
+        uint4 mbits = make_uint4(~0u, ~0u, ~0u, ~0u);     // this point's keep bits (thread = point)
+        if (L.mask_bits != nullptr && row_ok) {
+          const uint32_t *mb = L.mask_bits + col * L.mask_words;
+          mbits.x = __ldg(mb);
+          if (L.mask_words > 1) mbits.y = __ldg(mb + 1);
+          if (L.mask_words > 2) mbits.z = __ldg(mb + 2);
+          if (L.mask_words > 3) mbits.w = __ldg(mb + 3);
+        }
         for (int m0 = 0; m0 < L.cout_chunks; m0 += wave_max) {
           const int mc = min(wave_max, L.cout_chunks - m0);
           mbar_wait(acc_full, acc_phase);
@@ -682,12 +694,11 @@ mlp_chain_pm1_kernel(const __grid_constant__ ChainP p) {
               if (slow && row_ok) {                    // dropout mask / channel-major copy: coalesced over the warp
                 const size_t o0 = (static_cast<size_t>(cloud) * L.cout + ch0) * p.cols_per_cloud + n_in_cloud + row;
                 const size_t cs = static_cast<size_t>(p.cols_per_cloud);
-                if (L.mask != nullptr) {
-                  float mk[16];
+                if (L.mask_bits != nullptr) {
+                  const int mw = ch0 >> 5;
+                  const uint32_t m16 = (mw == 0 ? mbits.x : (mw == 1 ? mbits.y : (mw == 2 ? mbits.z : mbits.w))) >> (ch0 & 31);
 #pragma unroll
-                  for (int i = 0; i < 16; ++i) mk[i] = (ch0 + i < L.cout) ? __ldg(L.mask + o0 + i * cs) : 1.f;
-#pragma unroll
-                  for (int i = 0; i < 16; ++i) v[i] *= mk[i];
+                  for (int i = 0; i < 16; ++i) v[i] = ((m16 >> i) & 1u) ? v[i] * L.mask_scale : 0.f;
                 }
                 if (L.out_cm != nullptr) {
 #pragma unroll
@@ -868,8 +879,16 @@ mlp_chain_pm_kernel(const __grid_constant__ ChainP p) {
         const LayerP &L = p.L[l];
         const bool last = (l == p.n_layers - 1);
         const int cout_pad = L.cout_chunks * 128, cout16 = (L.cout + 15) & ~15;
-        const bool slow = (L.mask != nullptr) || (L.out_cm != nullptr);
+        const bool slow = (L.mask_bits != nullptr) || (L.out_cm != nullptr);
         const float *bias_base = L.bias + (L.bias_per_cloud ? cloud * cout_pad : 0);
+        uint4 mbits = make_uint4(~0u, ~0u, ~0u, ~0u);     // this point's keep bits (thread = point)
+        if (L.mask_bits != nullptr && row_ok) {
+          const uint32_t *mb = L.mask_bits + col * L.mask_words;
+          mbits.x = __ldg(mb);
+          if (L.mask_words > 1) mbits.y = __ldg(mb + 1);
+          if (L.mask_words > 2) mbits.z = __ldg(mb + 2);
+          if (L.mask_words > 3) mbits.w = __ldg(mb + 3);
+        }
         mbar_wait(acc_full + g, acc_phase);
         acc_phase ^= 1;
         tc_fence_after();
@@ -893,12 +912,11 @@ mlp_chain_pm_kernel(const __grid_constant__ ChainP p) {
           if (slow && row_ok) {                    // dropout mask / channel-major copy: coalesced over the warp
             const size_t o0 = (static_cast<size_t>(cloud) * L.cout + ch0) * p.cols_per_cloud + n_in_cloud + row;
             const size_t cs = static_cast<size_t>(p.cols_per_cloud);
-            if (L.mask != nullptr) {
-              float mk[16];
+            if (L.mask_bits != nullptr) {
+              const int mw = ch0 >> 5;
+              const uint32_t m16 = (mw == 0 ? mbits.x : (mw == 1 ? mbits.y : (mw == 2 ? mbits.z : mbits.w))) >> (ch0 & 31);
 #pragma unroll
-              for (int i = 0; i < 16; ++i) mk[i] = (ch0 + i < L.cout) ? __ldg(L.mask + o0 + i * cs) : 1.f;
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] *= mk[i];
+              for (int i = 0; i < 16; ++i) v[i] = ((m16 >> i) & 1u) ? v[i] * L.mask_scale : 0.f;
             }
             if (L.out_cm != nullptr) {
 #pragma unroll
@@ -973,7 +991,9 @@ int launch_chain(const cpfn_mlp_chain_t *c, cudaStream_t st) {
     L.cout = s.cout;
     L.relu = s.relu;
     L.bias_per_cloud = s.bias_per_cloud;
-    L.bias = s.bias; L.mask = s.mask; L.out_cm = s.out_cm;
+    L.bias = s.bias; L.out_cm = s.out_cm;
+    L.mask_bits = s.mask_bits; L.mask_scale = s.mask_scale; L.mask_words = (s.cout + 31) / 32;
+    if (s.mask_bits != nullptr && s.cout > 128) return CPFN_EINVAL;
     L.next_k16 = 0;
     if (l > 0) {
       if (s.cin != c->layers[l - 1].cout) return CPFN_EINVAL;
@@ -983,7 +1003,7 @@ int launch_chain(const cpfn_mlp_chain_t *c, cudaStream_t st) {
     if (L.cout_chunks > max_chunks) max_chunks = L.cout_chunks;
     const size_t in_bytes = static_cast<size_t>(L.cin_atoms) * 2 * NT * 128;
     if (in_bytes > act_need[0]) act_need[0] = in_bytes;
-    if (NT != 128 && (s.bias_per_cloud || s.mask || s.out_cm) && (c->cols_per_cloud % NT) != 0) return CPFN_EINVAL;
+    if (NT != 128 && (s.bias_per_cloud || s.mask_bits || s.out_cm) && (c->cols_per_cloud % NT) != 0) return CPFN_EINVAL;
   }
   if (static_cast<size_t>(total_blocks) * kStageBytes != c->weight_bytes) return CPFN_EINVAL;
   p.weights = static_cast<const uint8_t *>(c->weights);

@@ -14,16 +14,10 @@ import torch
 
 from . import _lib
 
-_bq_ws = {}
-
-
 def _bq_workspace(nbytes, device):
-    key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
-    ws = _bq_ws.get(key)
-    if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
-        _bq_ws[key] = ws
-    return ws
+    """Grid workspace of the uniform-grid ball query: a fresh block from torch's caching allocator per call
+    (stream-safe; a captured CUDA graph keeps the block it was captured with alive)."""
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
 # Number of kernels this package enqueued (bench.py reports it as gpu_launches).
@@ -108,7 +102,7 @@ def ball_query(new_xyz, xyz, radius, nsample):
     L = _lib.lib()
     with torch.cuda.device(new_xyz.device):
         if 2048 <= N <= 32768 and float(radius) > 0 and not os.environ.get("CPFN_BQ_NO_GRID"):
-            # uniform-grid kernel (bit-identical result, ~10x fewer distance tests); workspace is cached
+            # uniform-grid kernel (bit-identical result, ~10x fewer distance tests)
             nbytes = L.cpfn_ball_query_grid_workspace_bytes(xyz.size(0), N)
             ws = _bq_workspace(nbytes, new_xyz.device)
             _check(L.cpfn_ball_query_grid(_p(new_xyz), _p(xyz), xyz.size(0), N, S, float(radius), int(nsample), _p(out),

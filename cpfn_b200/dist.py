@@ -21,42 +21,65 @@ def units_per_rank(n_units, world):
 
 def gather_patch_records(records, n_units, group=None):
     """All-gather the per-patch records of every rank; returns the list of `n_units` records in unit
-    order (unit i lives on rank i mod G) on every rank.  One collective for the payload."""
+    order (unit i lives on rank i mod G) on every rank.  A record is a dict with ``W`` f32 [n,K] memberships,
+    ``X`` f32 [n,3] normals, ``T`` f32 [n,n_types] type logits, ``patch_indices`` int64 [n] and ``parameters``
+    f32 [K,P] fitted parameters (P = 22 for the four primitive types; may be [K,0]).  Two collectives carry the
+    payload: one for the float fields (one flat buffer), one for the int64 indices.  Ranks without patches (more
+    ranks than patches) learn the record shape from an all-reduce."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
+    nccl = dist.get_backend(group) == "nccl"
     if records:
         dev = records[0]["W"].device
-    elif dist.get_backend(group) == "nccl":
+    elif nccl:
         dev = torch.device("cuda", torch.cuda.current_device())
     else:
         dev = torch.device("cpu")
     per = units_per_rank(n_units, world)
-    shapes = torch.zeros(2, dtype=torch.int64, device=dev)
+    if len(records) != len(shard_units(n_units, rank, world)):
+        raise ValueError("rank %d holds %d records, its share of %d units is %d" %
+                         (rank, len(records), n_units, len(shard_units(n_units, rank, world))))
+    shapes = torch.zeros(4, dtype=torch.int64, device=dev)
     if records:
-        shapes[0], shapes[1] = records[0]["W"].shape
-    dist.all_reduce(shapes, op=dist.ReduceOp.MAX, group=group)      # n, K (ranks without patches learn them)
-    n, K = int(shapes[0]), int(shapes[1])
-    rec_len = n * K + n * 3 + n * 4 + n * 2 + K * 22
+        r0 = records[0]
+        n, K = r0["W"].shape
+        shapes[0], shapes[1], shapes[2], shapes[3] = n, K, r0["T"].shape[-1], r0["parameters"].shape[-1]
+        for r in records:
+            if r["W"].dtype != torch.float32 or r["X"].dtype != torch.float32 or r["T"].dtype != torch.float32:
+                raise TypeError("gather_patch_records: W, X and T must be float32")
+            if (tuple(r["W"].shape) != (n, K) or tuple(r["X"].shape) != (n, 3) or r["T"].shape != r0["T"].shape
+                    or r["patch_indices"].numel() != n or r["parameters"].shape != r0["parameters"].shape):
+                raise ValueError("gather_patch_records: the records of one call must share their shapes")
+    mine = shapes.clone()
+    dist.all_reduce(shapes, op=dist.ReduceOp.MAX, group=group)      # ranks without patches learn the shapes
+    if records and not torch.equal(mine, shapes):
+        raise ValueError("gather_patch_records: ranks disagree on the record shape: %s vs %s" %
+                         (mine.tolist(), shapes.tolist()))
+    n, K, n_types, n_par = (int(v) for v in shapes.tolist())
+    fields = (("W", n * K, (n, K)), ("X", n * 3, (n, 3)), ("T", n * n_types, (n, n_types)),
+              ("parameters", K * n_par, (K, n_par)))
+    rec_len = sum(size for _, size, _ in fields)
     flat = torch.zeros(per, rec_len, dtype=torch.float32, device=dev)
+    flat_idx = torch.zeros(per, n, dtype=torch.int64, device=dev)
     for i, r in enumerate(records):
-        flat[i] = torch.cat([r["W"].reshape(-1), r["X"].reshape(-1), r["T"].reshape(-1),
-                             r["patch_indices"].to(torch.int64).contiguous().view(torch.float32).reshape(-1),
-                             r["parameters"].reshape(-1)])
+        flat[i] = torch.cat([r[name].reshape(-1).to(torch.float32) for name, _, _ in fields])
+        flat_idx[i] = r["patch_indices"].reshape(-1).to(torch.int64)
     out = torch.empty(world, per, rec_len, dtype=torch.float32, device=dev)
-    if dist.get_backend(group) == "nccl":
+    out_idx = torch.empty(world, per, n, dtype=torch.int64, device=dev)
+    if nccl:
         dist.all_gather_into_tensor(out.view(world * per, rec_len), flat, group=group)
+        dist.all_gather_into_tensor(out_idx.view(world * per, n), flat_idx, group=group)
     else:
         dist.all_gather(list(out.unbind(0)), flat, group=group)
+        dist.all_gather(list(out_idx.unbind(0)), flat_idx, group=group)
     result = []
     for u in range(n_units):
         row = out[u % world, u // world]
         o = 0
         rec = {}
-        for name, size, shape in (("W", n * K, (n, K)), ("X", n * 3, (n, 3)), ("T", n * 4, (n, 4))):
+        for name, size, shape in fields:
             rec[name] = row[o:o + size].view(shape)
             o += size
-        rec["patch_indices"] = row[o:o + 2 * n].contiguous().view(torch.int64)
-        o += 2 * n
-        rec["parameters"] = row[o:o + K * 22].view(K, 22)
+        rec["patch_indices"] = out_idx[u % world, u // world]
         result.append(rec)
     return result

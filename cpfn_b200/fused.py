@@ -24,8 +24,8 @@ TIMED_OPS = ("mlp_chain",)
 
 class _Layer(ctypes.Structure):
     _fields_ = [("cin", ctypes.c_int32), ("cout", ctypes.c_int32), ("relu", ctypes.c_int32),
-                ("bias_per_cloud", ctypes.c_int32), ("bias", ctypes.c_void_p), ("mask", ctypes.c_void_p),
-                ("out_cm", ctypes.c_void_p)]
+                ("bias_per_cloud", ctypes.c_int32), ("bias", ctypes.c_void_p), ("mask_bits", ctypes.c_void_p),
+                ("mask_scale", ctypes.c_float), ("out_cm", ctypes.c_void_p)]
 
 
 class _Chain(ctypes.Structure):
@@ -115,7 +115,8 @@ def run_chain(pc, B, cols_per_cloud, out, ldo, tile_cols=128, in_mode=IN_DENSE, 
         c.layers[l].cin, c.layers[l].cout, c.layers[l].relu = cin, cout, int(relu)
         c.layers[l].bias_per_cloud = int(l in bias_per_cloud)
         c.layers[l].bias = bias.data_ptr()
-        c.layers[l].mask = masks[l].data_ptr() if (masks and masks.get(l) is not None) else None
+        if masks and masks.get(l) is not None:          # (keep bits [cols, ceil(cout/32)] int32, scale of the kept values)
+            c.layers[l].mask_bits, c.layers[l].mask_scale = masks[l][0].data_ptr(), float(masks[l][1])
         c.layers[l].out_cm = out_cm[l].data_ptr() if (out_cm and out_cm.get(l) is not None) else None
     c.weights, c.weight_bytes = pc.weights.data_ptr(), pc.weights.numel()
     c.tile_cols, c.in_mode, c.B, c.cols_per_cloud = tile_cols, in_mode, B, cols_per_cloud
@@ -260,15 +261,58 @@ _CACHE_ATTR = "_cpfn_fused_cache"
 
 
 def invalidate(model):
-    """Drop the folded / packed weights cached on the modules (call after load_state_dict)."""
+    """Drop the folded / packed weights cached on the modules.  Not needed for correctness: every cache entry
+    carries the signature of the tensors it was built from and is rebuilt when one of them changed."""
     for m in model.modules():
         for k in [k for k in vars(m) if k.startswith(_CACHE_ATTR)]:
             delattr(m, k)
 
 
+def _conv_bn_sources(convs, bns):
+    out = []
+    for conv, bn in zip(convs, bns):
+        out += [conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var]
+    return out
+
+
+def signature(tensors):
+    """Changes whenever one of `tensors` is written in place (optimizer step, load_state_dict, BatchNorm's
+    running statistics in train mode), moved or replaced: (storage address, version counter) per tensor."""
+    return tuple((t.data_ptr(), t._version) for t in tensors)
+
+
+def model_sources(model):
+    """Every parameter / buffer the fused forward of a PointNet2 folds into its packed weights."""
+    out = []
+    for sa in (model.sa1, model.sa2, model.sa3):
+        out += _conv_bn_sources(sa.conv_blocks[0], sa.bn_blocks[0])
+    for fp in (model.sfp1, model.sfp2, model.sfp3):
+        out += _conv_bn_sources(fp.mlp_convs, fp.mlp_bns)
+    out += [model.fc1.weight, model.fc1.bias]
+    if not model.features_extractor:
+        out += [model.bn1.weight, model.bn1.bias, model.bn1.running_mean, model.bn1.running_var]
+        for fc in model.fc2:
+            out += [fc.weight, fc.bias]
+    return out
+
+
+def _cached(module, key, sources, device):
+    """The cache entry `key` of `module` if it was built from the current values of `sources` on `device`."""
+    entry = getattr(module, key, None)
+    if entry is not None and entry[1] == device and entry[2] == signature(sources):
+        return entry[0]
+    return None
+
+
+def _store(module, key, value, sources, device):
+    setattr(module, key, (value, device, signature(sources)))
+    return value
+
+
 def _sa_chain(module, device):
-    pc = getattr(module, _CACHE_ATTR, None)
-    if pc is None or pc.weights.device != device:
+    sources = _conv_bn_sources(module.conv_blocks[0], module.bn_blocks[0])
+    pc = _cached(module, _CACHE_ATTR, sources, device)
+    if pc is None:
         layers = []
         for j, (conv, bn) in enumerate(zip(module.conv_blocks[0], module.bn_blocks[0])):
             w, b = fold_bn(conv.weight, conv.bias, bn)
@@ -284,7 +328,7 @@ def _sa_chain(module, device):
             l0 = (torch.from_numpy(np.ascontiguousarray(w0)).to(device), torch.from_numpy(np.ascontiguousarray(b0)).to(device))
         pc = PackedChain(layers, device)
         pc.l0 = l0
-        setattr(module, _CACHE_ATTR, pc)
+        _store(module, _CACHE_ATTR, pc, sources, device)
     return pc
 
 
@@ -366,11 +410,12 @@ def sa_forward_pm(module, xyz, feats_pm, indices=None, out=None):
 def _fp_chain(module, device, split=None, tail=None):
     """split = number of leading input channels of layer 0 that are a per-cloud constant
     (FP1: the broadcast global feature) -> returns (chain without them, const-part weight).
-    tail = (W [cout,cin] numpy, tag): one more layer without bias / ReLU appended to the chain -- the linear part
+    tail = (W [cout,cin] numpy, tag, the tensors W was folded from): one more layer without bias / ReLU appended to the chain -- the linear part
     of the NEXT module's first layer, applied here once per source row (see pointnet2_forward)."""
     key = _CACHE_ATTR + ("_s%d_%d" % split if split else "") + ("_t" + tail[1] if tail else "")
-    pc = getattr(module, key, None)
-    if pc is None or pc[0].weights.device != device:
+    sources = _conv_bn_sources(module.mlp_convs, module.mlp_bns) + (list(tail[2]) if tail else [])
+    pc = _cached(module, key, sources, device)
+    if pc is None:
         layers, wconst = [], None
         for j, (conv, bn) in enumerate(zip(module.mlp_convs, module.mlp_bns)):
             w, b = fold_bn(conv.weight, conv.bias, bn)
@@ -382,8 +427,7 @@ def _fp_chain(module, device, split=None, tail=None):
             layers.append((w, b, True))
         if tail is not None:
             layers.append((np.ascontiguousarray(tail[0], dtype=np.float32), np.zeros(tail[0].shape[0], np.float32), False))
-        pc = (PackedChain(layers, device), wconst)
-        setattr(module, key, pc)
+        pc = _store(module, key, (PackedChain(layers, device), wconst), sources, device)
     return pc
 
 
@@ -399,11 +443,9 @@ def fp_forward_pm(module, xyz1, xyz2, feats1_pm, feats2_pm, nn=None, tail=None):
         D2 = feats2_pm.shape[2]
         pc, wconst = _fp_chain(module, dev, split=(D1, D1 + D2))
         g = feats2_pm.reshape(B, D2).contiguous()
-        # per-cloud bias rows: linear_rows rewrites the cout valid entries every call, the padding stays zero
-        bias0 = getattr(module, _CACHE_ATTR + "_bias0", None)
-        if bias0 is None or bias0.shape[0] != B or bias0.device != dev:
-            bias0 = torch.zeros(B, pc.biases[0].numel(), dtype=torch.float32, device=dev)
-            setattr(module, _CACHE_ATTR + "_bias0", bias0)
+        # per-cloud bias rows, allocated per call (a captured graph keeps its own copy alive): linear_rows writes the
+        # cout valid entries and the zero padding
+        bias0 = torch.empty(B, pc.biases[0].numel(), dtype=torch.float32, device=dev)
         linear_rows(g, wconst[0], wconst[1], bias0)          # fp32: W_global @ g + b, one vector per cloud
         out = torch.empty(B, N, pc.dims[-1][1], dtype=torch.float32, device=dev)
         first = dict(in_mode=IN_DENSE, a_src=feats1_pm, a_ch=D1, a_rows=N)
@@ -422,7 +464,6 @@ def fp_forward_pm(module, xyz1, xyz2, feats1_pm, feats2_pm, nn=None, tail=None):
     return out
 
 
-_ones_cache = {}
 _group_all_cache = {}
 
 
@@ -446,13 +487,59 @@ def _side_stream(dev):
     return _side_streams[key]
 
 
-def _ones(B, C, N, dev):
-    key = (B, C, N, dev)
-    t = _ones_cache.get(key)
+# ---- always-on dropout (pn2_network.py:63) as a bit mask drawn from torch's CUDA generator -----------------------
+
+_rng_state = {}
+
+
+def _rng_state_tensor(dev):
+    key = (dev.type, dev.index)
+    t = _rng_state.get(key)
     if t is None:
-        _ones_cache.clear()
-        t = _ones_cache[key] = torch.ones(B, C, N, device=dev)
+        t = _rng_state[key] = torch.zeros(2, dtype=torch.int64, device=dev)      # {seed, offset}, read by the mask kernel
     return t
+
+
+def dropout_plan(nelem, dev):
+    """(threads, generator advance) of the launch torch's F.dropout makes for `nelem` float32 elements on `dev`
+    (ATen native/cuda/Dropout.cu: 256-thread blocks, at most SMs x max-threads/256 of them, 4 elements per
+    thread and iteration; the generator moves on by 4 x iterations)."""
+    props = torch.cuda.get_device_properties(dev)
+    blocks = min(props.multi_processor_count * (props.max_threads_per_multi_processor // 256), (nelem + 255) // 256)
+    threads = max(1, blocks) * 256
+    return threads, ((max(nelem, 1) - 1) // (threads * 4) + 1) * 4
+
+
+def sync_rng(dev, nelem):
+    """Hand the current (seed, offset) of torch's CUDA generator to the device-side RNG state the mask kernel
+    reads, and advance the generator exactly as F.dropout on `nelem` elements would: torch.manual_seed governs the
+    masks, and they are the ones the reference's own F.dropout call draws on this GPU.  Stream-ordered (a one-thread
+    kernel); call it before every replay of a captured forward -- it cannot be part of the capture."""
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    gen = torch.cuda.default_generators[idx]
+    seed, offset = gen.initial_seed(), gen.get_offset()
+    gen.set_offset(offset + dropout_plan(nelem, dev)[1])
+    state = _rng_state_tensor(dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().cpfn_rng_set(state.data_ptr(), seed & 0xFFFFFFFFFFFFFFFF, offset,
+                                           torch.cuda.current_stream(dev).cuda_stream), "rng_set")
+    cuda_ops.count_launches(1)
+
+
+def dropout_bits(B, C, N, dev, p=0.5):
+    """Keep bits of F.dropout(x [B,C,N], p): (int32 [B*N, ceil(C/32)], scale of the kept values).  Outside a graph
+    capture the RNG state is taken from torch's generator here; a captured launch reads whatever ``sync_rng`` wrote
+    before the replay."""
+    if not torch.cuda.is_current_stream_capturing():
+        sync_rng(dev, B * C * N)
+    words = (C + 31) // 32
+    bits = torch.empty(B * N, words, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().cpfn_dropout_mask_bits(_rng_state_tensor(dev).data_ptr(), B, C, N, 1.0 - p,
+                                                     dropout_plan(B * C * N, dev)[0], bits.data_ptr(),
+                                                     torch.cuda.current_stream(dev).cuda_stream), "dropout_mask_bits")
+    cuda_ops.count_launches(1)
+    return bits, 1.0 / (1.0 - p)
 
 
 def _pm(t):
@@ -476,8 +563,11 @@ def _head_chain(model, device):
     interpolation: W1 (sum_j w_j f_j) = sum_j w_j (W1 f_j).  W1 (BatchNorm folded) is applied to the 512 rows of
     l5 per cloud as one more layer of FP2's chain instead of to the 8192 interpolated rows; the bias and the ReLU
     are applied where the rows are interpolated (``in_bias``).  Returns (chain, head sizes, W1, b1)."""
-    pc = getattr(model, _CACHE_ATTR, None)
-    if pc is None or pc[0].weights.device != device:
+    sources = (_conv_bn_sources(model.sfp3.mlp_convs, model.sfp3.mlp_bns)
+               + [model.fc1.weight, model.fc1.bias, model.bn1.weight, model.bn1.bias, model.bn1.running_mean,
+                  model.bn1.running_var] + [t for fc in model.fc2 for t in (fc.weight, fc.bias)])
+    pc = _cached(model, _CACHE_ATTR, sources, device)
+    if pc is None:
         layers, first = [], None
         for j, (conv, bn) in enumerate(zip(model.sfp3.mlp_convs, model.sfp3.mlp_bns)):
             w, b = fold_bn(conv.weight, conv.bias, bn)
@@ -490,8 +580,8 @@ def _head_chain(model, device):
         hw = np.concatenate([fold_bn(fc.weight, fc.bias, None)[0] for fc in model.fc2], axis=0)
         hb = np.concatenate([fold_bn(fc.weight, fc.bias, None)[1] for fc in model.fc2], axis=0)
         layers.append((hw, hb, False))
-        pc = (PackedChain(layers, device), [fc.out_channels for fc in model.fc2], first[0], first[1])
-        setattr(model, _CACHE_ATTR, pc)
+        pc = _store(model, _CACHE_ATTR, (PackedChain(layers, device), [fc.out_channels for fc in model.fc2], first[0],
+                                         first[1], sources[:6]), sources, device)
     return pc
 
 
@@ -517,20 +607,20 @@ def pointnet2_forward(model, P, dropout=True):
         idx2 = sa_indices(model.sa2, l1_xyz)
         nn3 = three_nn_weights(P, l1_xyz)
         nn2 = three_nn_weights(l1_xyz, idx2[0])
-        # the reference's always-on dropout (pn2_network.py:63): same generator, same shape, same mask
-        mask = torch.nn.functional.dropout(_ones(B, 128, N, dev), p=0.5) if dropout else None
+        # the reference's always-on dropout (pn2_network.py:63): same generator, same mask, as 1 bit per element
+        mask = dropout_bits(B, 128, N, dev, p=0.5) if dropout else None
         join = torch.cuda.Event()
         join.record(side)
     _, l1 = sa_forward_pm(model.sa1, P, None, indices=idx1)
     main.wait_event(join)
     if side is not main:
-        for t in (*idx2, *nn3, *nn2) + ((mask,) if mask is not None else ()):
+        for t in (*idx2, *nn3, *nn2) + ((mask[0],) if mask is not None else ()):
             t.record_stream(main)
     l2_xyz, l2 = sa_forward_pm(model.sa2, l1_xyz, l1, indices=idx2)
     _, l3 = sa_forward_pm(model.sa3, l2_xyz, l2)
     l4 = fp_forward_pm(model.sfp1, l2_xyz, None, l2, l3)
-    pc, head_sizes, w_fp3, b_fp3 = _head_chain(model, dev)
-    l5 = fp_forward_pm(model.sfp2, l1_xyz, l2_xyz, l1, l4, nn=nn2, tail=(w_fp3, "fp3"))      # = W1_fp3 @ (FP2 output)
+    pc, head_sizes, w_fp3, b_fp3, fp3_src = _head_chain(model, dev)
+    l5 = fp_forward_pm(model.sfp2, l1_xyz, l2_xyz, l1, l4, nn=nn2, tail=(w_fp3, "fp3", fp3_src))   # = W1_fp3 @ (FP2 output)
     n_out = sum(head_sizes)
     w, idx = nn3
     heads = torch.empty(B, N, n_out, dtype=torch.float32, device=dev)

@@ -52,9 +52,26 @@ class PointNet2(nn.Module):
             self.bn1 = nn.BatchNorm1d(HIDDEN)
             self.fc2 = nn.ModuleList([nn.Conv1d(HIDDEN, width, 1) for width in output_sizes])
 
+    def _whole_network_fused(self, x):
+        """Inference on bare positions without injected features: the whole forward is the fused pipeline of
+        cpfn_b200/fused.py (side-stream overlap, FP3 + fc1 + dropout + heads as one kernel) instead of one fused
+        call per module."""
+        from . import fused
+        if self.training or self.use_glob_features or self.use_loc_features or self.features_extractor:
+            return False
+        if self.dim_pos != 3 or x.dim() != 3 or x.shape[2] != 3 or not x.is_cuda or x.dtype != torch.float32:
+            return False
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            return False
+        return fused.available()
+
     def forward(self, x, glob_features=None, loc_features=None, fast=True):
         """x [B,N,dim_input] -> [head_0 [B,N,o0], ..., l3_feats [B,1024(+),1], output_feat [B,128,N]]
         (a features extractor returns ``(l3_feats, output_feat)`` with output_feat = fc1 output)."""
+        if fast and self._whole_network_fused(x):
+            from . import fused
+            heads, code, hidden = fused.pointnet2_forward(self, x, dropout=True)[:3]
+            return list(heads) + [code, hidden]
         channels_first = x.transpose(2, 1)
         xyz0 = channels_first[:, :self.dim_pos, :]
         f0 = channels_first[:, self.dim_pos:, :] if channels_first.shape[1] > self.dim_pos else None

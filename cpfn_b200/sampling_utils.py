@@ -15,16 +15,9 @@ import torch
 
 from . import _lib, cuda_ops
 
-_workspaces = {}
-
-
 def _workspace(dev, nbytes):
-    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
-    w = _workspaces.get(key)
-    if w is None or w.numel() < nbytes:
-        w = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        _workspaces[key] = w
-    return w
+    """Per-call scratch from torch's caching allocator (stream- and graph-safe)."""
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)
 
 
 def extract_patches(points_hr, seeds, num_points_patch=8192, return_distances=False):

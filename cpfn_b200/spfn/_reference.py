@@ -34,3 +34,17 @@ def load(name, overrides):
         setattr(mod, k, v)
     _loaded[name] = mod
     return mod
+
+
+def forwarder(module_globals, name, hot_names):
+    """PEP 562 ``__getattr__`` for the mirror module ``cpfn_b200.spfn.<name>``: names this package does not define
+    (``create_primitive_from_dict``, ``extract_parameter_data_as_dict``, ``compute_parameter_loss``, the TensorFlow
+    twins ...: host-side metadata and loss glue outside the hot path) are looked up in the reference's own
+    ``SPFN/<name>.py``, loaded privately with this package's ``hot_names`` patched into it."""
+    def __getattr__(attr):
+        ref = load(name, {k: module_globals[k] for k in hot_names})
+        if ref is not None and hasattr(ref, attr):
+            return getattr(ref, attr)
+        raise AttributeError("cpfn_b200.spfn.%s has no '%s' (not a hot-path function; put the reference checkout "
+                             "on sys.path to use the reference's own)" % (name, attr))
+    return __getattr__

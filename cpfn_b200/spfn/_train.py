@@ -30,16 +30,10 @@ _names = [(0, 0, 0), (0, 0, 1), (0, 0, 2), (0, 1, 1), (0, 1, 2), (0, 2, 2), (1, 
 for _i, _t in enumerate(_names):
     _T10[_t] = _i
 
-_ws_cache = {}
-
-
 def _workspace(nbytes, device):
-    key = (device.type, device.index)
-    ws = _ws_cache.get(key)
-    if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
-        _ws_cache[key] = ws
-    return ws
+    """Scratch for the partial sums: a fresh block from torch's caching allocator per call, so that concurrent
+    callers on different streams never share it and a captured CUDA graph owns the block it was captured with."""
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
 class _WeightedMoments(torch.autograd.Function):

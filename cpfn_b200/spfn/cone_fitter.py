@@ -4,7 +4,7 @@ import math
 
 import torch
 
-from . import fit
+from . import _reference, fit
 
 
 def acos_safe(x):
@@ -21,3 +21,6 @@ def compute_residue_single(apex, axis, half_angle, p):
     v_normalized = torch.nn.functional.normalize(v, p=2, dim=-1, eps=1e-12)
     alpha = acos_safe(torch.sum(v_normalized * axis, dim=-1))
     return (torch.sin(torch.clamp(torch.abs(alpha - half_angle), max=math.pi / 2))) ** 2 * torch.sum(v * v, dim=-1)
+
+
+__getattr__ = _reference.forwarder(globals(), "cone_fitter", ('compute_parameters', 'compute_residue_single', 'acos_safe'))

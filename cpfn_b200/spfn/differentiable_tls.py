@@ -2,7 +2,7 @@
 (SPFN/differentiable_tls.py:123-143, 200-209) on the CUDA moment kernels."""
 import torch
 
-from . import _train
+from . import _reference, _train
 
 guard_one_over_matrix = _train.guard_one_over_matrix
 
@@ -28,3 +28,6 @@ def solve_weighted_tls(A, W):
     M = _train.weighted_moments(W.unsqueeze(2), A.detach(), A)          # x x^T features carry A's gradient
     Mxx = _train._sym3(M[..., _train._X2:_train._X2 + 6]).squeeze(1)
     return _train.svd_v_last_column(Mxx).to(torch.float32)
+
+
+__getattr__ = _reference.forwarder(globals(), "differentiable_tls", ('guard_one_over_matrix', 'compute_svd_K', 'Custom_svd_v_colum', 'solve_weighted_tls'))

@@ -12,16 +12,10 @@ KEYS = (("plane_normal", 0, 3), ("plane_center", 3, 1), ("sphere_center", 4, 3),
         ("cylinder_radius_squared", 14, 1), ("cone_apex", 15, 3), ("cone_axis", 18, 3),
         ("cone_half_angle", 21, 1))
 
-_ws_cache = {}
-
-
 def _workspace(nbytes, device):
-    key = (device.type, device.index)
-    ws = _ws_cache.get(key)
-    if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
-        _ws_cache[key] = ws
-    return ws
+    """Scratch for the partial sums: a fresh block from torch's caching allocator per call, so that concurrent
+    callers on different streams never share it and a captured CUDA graph owns the block it was captured with."""
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
 def fit_primitives(P, W, X):

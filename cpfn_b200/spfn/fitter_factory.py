@@ -24,8 +24,12 @@ def get_n_registered_primitives():
 
 
 def create_primitive_from_dict(d):
-    """The reference builds numpy value objects (``SPFN/primitives.py``) here; those classes are
-    host-side metadata outside the hot path, so the validated dictionary itself is returned."""
-    if d['type'] not in KNOWN_TYPES:
+    """The reference's dispatch (SPFN/fitter_factory.py:21-31): the numpy value objects of ``SPFN/primitives.py`` are
+    host-side metadata outside the hot path, built by the reference's own ``<type>_fitter.create_primitive_from_dict``
+    (forwarded to its files, see _reference.py; needs the reference checkout on sys.path).  The data pipeline calls
+    ``get_primitive_name()`` and ``extract_parameter_data_as_dict`` on them (Utils/dataset_utils.py:79-112)."""
+    from . import cone_fitter, cylinder_fitter, plane_fitter, sphere_fitter
+    makers = {"plane": plane_fitter, "sphere": sphere_fitter, "cylinder": cylinder_fitter, "cone": cone_fitter}
+    if d['type'] not in makers:
         raise NotImplementedError
-    return dict(d)
+    return makers[d['type']].create_primitive_from_dict(d)

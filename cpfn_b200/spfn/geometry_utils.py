@@ -5,7 +5,7 @@ circle fit and the generic least squares on explicit [B',N,D] rows are thin torc
 (inside ``compute_parameters`` the cylinder's circle fit never builds those rows, see csrc/tls.cu)."""
 import torch
 
-from . import _train
+from . import _reference, _train
 
 compute_consistent_plane_frame = _train.compute_consistent_plane_frame
 
@@ -52,3 +52,6 @@ def weighted_sphere_fitting(P, W, division_eps=1e-10):
     center = guarded_matrix_solve_ls(A, b, W)
     r2 = torch.sum(W * torch.sum((P - center.unsqueeze(1)) ** 2, dim=2), dim=1) / denom
     return center, r2
+
+
+__getattr__ = _reference.forwarder(globals(), "geometry_utils", ('compute_consistent_plane_frame', 'weighted_plane_fitting', 'guarded_matrix_solve_ls', 'weighted_sphere_fitting'))

@@ -2,7 +2,7 @@
 and ``compute_residue_single`` (:54-55)."""
 import torch
 
-from . import fit
+from . import _reference, fit
 
 
 def compute_parameters(P, W):
@@ -12,3 +12,6 @@ def compute_parameters(P, W):
 
 def compute_residue_single(n, c, p):
     return (torch.sum(p * n, dim=-1) - c) ** 2
+
+
+__getattr__ = _reference.forwarder(globals(), "plane_fitter", ('compute_parameters', 'compute_residue_single'))

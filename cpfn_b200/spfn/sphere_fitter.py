@@ -2,7 +2,7 @@
 SPFN/sphere_fitter.py:9-19) and ``compute_residue_single`` (:58-62)."""
 import torch
 
-from . import fit
+from . import _reference, fit
 
 
 def sqrt_safe(x):
@@ -16,3 +16,6 @@ def compute_parameters(P, W):
 
 def compute_residue_single(center, radius_squared, p):
     return (sqrt_safe(torch.sum((p - center) ** 2, dim=-1)) - sqrt_safe(radius_squared)) ** 2
+
+
+__getattr__ = _reference.forwarder(globals(), "sphere_fitter", ('compute_parameters', 'compute_residue_single', 'sqrt_safe'))

@@ -184,7 +184,9 @@ typedef struct {
   int32_t relu;               /* ReLU after the bias */
   int32_t bias_per_cloud;     /* bias is [B, 128*ceil(cout/128)] instead of [128*ceil(cout/128)] */
   const float *bias;          /* BN-folded bias, zero padded to a multiple of 128 */
-  const float *mask;          /* optional multiplicative mask [B, cout, cols_per_cloud] after ReLU (dropout) */
+  const uint32_t *mask_bits;  /* optional dropout keep-mask after ReLU, one bit per (column, channel): word
+                               * [col * ceil(cout/32) + ch/32], bit ch%32 (cpfn_dropout_mask_bits); cout <= 128 */
+  float mask_scale;           /* kept values are multiplied by this (1 / keep probability), dropped ones are 0 */
   float *out_cm;              /* optional channel-major copy [B, cout, cols_per_cloud] of this layer's output */
 } cpfn_mlp_layer_t;
 
@@ -243,9 +245,22 @@ CPFN_API int cpfn_gather_xyz(const float *xyz, const int32_t *idx, int B, int N,
 
 /* out[r, co] = bias[co] + sum_k W[co,k] x[r,k] in fp32 (few rows): the per-cloud constant part of
  * the first FP layer when pos2 is None (pointset_feature_propagation.py:33-34: feats2 repeated over
- * all points contributes the same vector to every point of a cloud). */
+ * all points contributes the same vector to every point of a cloud).  Columns cout .. ldo-1 of every
+ * output row are set to zero (the chains read biases zero padded to a multiple of 128). */
 CPFN_API int cpfn_linear_rows(const float *x, const float *W, const float *bias, int rows, int cin,
                               int cout, int ldo, float *out, cpfn_stream_t stream);
+
+/* Dropout keep-mask of F.dropout(x, p) for a channel-major x [B, C, N] (pn2_network.py:63, always on), as ONE BIT
+ * per element instead of the fp32 mask tensor: bits[(b*N + n) * ceil(C/32) + c/32] bit c%32 = keep.  The random
+ * stream is torch's own for that call: Philox4x32-10 keyed by `seed`, thread t of torch's launch (`torch_threads`
+ * threads in all) owns the 4 consecutive elements 4*(t + k*torch_threads) .. +3 in its k-th iteration and draws
+ * them from counter (offset/4 + k, subsequence t); an element is kept iff uint32 * 2^-32 + 2^-33 < keep_prob
+ * (curand_uniform).  `rng_state` is a DEVICE pair {seed, offset} (uint64 each) so that a captured CUDA graph
+ * draws a fresh mask at every replay: cpfn_rng_set (a one-thread kernel) writes it, stream-ordered. */
+CPFN_API int cpfn_rng_set(unsigned long long *rng_state, unsigned long long seed, unsigned long long offset,
+                          cpfn_stream_t stream);
+CPFN_API int cpfn_dropout_mask_bits(const unsigned long long *rng_state, int B, int C, int N, float keep_prob,
+                                    long long torch_threads, uint32_t *bits, cpfn_stream_t stream);
 
 /* X = normalize(heads[:, x_off:x_off+3]), W = softmax(heads[:, w_off:w_off+K])
  * (Utils/training_utils.py:141-142); optionally inst = argmax_k W (hard_W_encoding's argmax) and

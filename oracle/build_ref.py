@@ -17,9 +17,14 @@ import os
 import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-REF_ROOT = "/root/reference/PointNet2/pointnet2_ops/cuda_ops"
+REF_TREE = "/root/reference"
+REF_ROOT = REF_TREE + "/PointNet2/pointnet2_ops/cuda_ops"
 OUT_DIR = os.path.join(_HERE, "_ref")
 NAME = "ref_cuda_ops"
+# The reference's Python (unmodified files) staged for the GPU box, where /root/reference does not exist:
+# baseline/_ref/ is git-ignored and travels with the gpurun snapshot.
+STAGE_DIR = os.path.join(os.path.dirname(_HERE), "baseline", "_ref")
+STAGED = ("PointNet2/pn2_network.py", "PointNet2/pointnet2_ops/modules", "SPFN", "Utils")
 
 
 def so_path():
@@ -45,6 +50,22 @@ def build(verbose=False):
     return so_path() if os.path.exists(so_path()) else None
 
 
+def stage_python():
+    """Copy the reference's Python packages on the hot path (PointNet2 modules, SPFN, Utils) byte for byte into
+    baseline/_ref/ (git-ignored).  Returns the directory, or None when neither the reference tree nor a staged
+    copy exists."""
+    import shutil
+    if os.path.isdir(REF_TREE):
+        for rel in STAGED:
+            src, dst = os.path.join(REF_TREE, rel), os.path.join(STAGE_DIR, rel)
+            os.makedirs(os.path.dirname(dst), exist_ok=True)
+            if os.path.isdir(src):
+                shutil.copytree(src, dst, dirs_exist_ok=True, ignore=shutil.ignore_patterns("__pycache__", "*.pyc"))
+            else:
+                shutil.copy2(src, dst)
+    return STAGE_DIR if os.path.isfile(os.path.join(STAGE_DIR, "PointNet2", "pn2_network.py")) else None
+
+
 def load_module():
     """Import the prebuilt extension (no compilation); None when absent."""
     path = so_path()
@@ -60,6 +81,7 @@ def load_module():
 if __name__ == "__main__":
     p = build(verbose="-v" in sys.argv)
     print("reference extension:", p)
+    print("reference python staged in:", stage_python())
     if p:
         m = load_module()
         print("exports:", sorted(n for n in dir(m) if not n.startswith("_")))

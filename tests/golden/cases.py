@@ -112,30 +112,7 @@ def fit_mask(case, key, W):
     return m & live
 
 
-def network_state(template, seed=7):
-    """Deterministic PointNet2 parameters for parity runs: every entry of `template`
-    (a reference-layout state dict: name -> tensor/array, only shapes are used) is
-    filled from numpy's default_rng, conv weights scaled He-style, BatchNorm with
-    non-trivial affine parameters and running statistics so that BN folding is
-    exercised.  Returns name -> np.ndarray (num_batches_tracked as int64 zeros)."""
-    rng = np.random.default_rng(seed)
-    out = {}
-    for name in sorted(template.keys()):
-        shape = tuple(template[name].shape)
-        if name.endswith("num_batches_tracked"):
-            out[name] = np.zeros(shape, dtype=np.int64)
-        elif name.endswith("running_var"):
-            out[name] = rng.uniform(0.5, 1.5, size=shape).astype(np.float32)
-        elif name.endswith("running_mean"):
-            out[name] = rng.normal(scale=0.1, size=shape).astype(np.float32)
-        elif ("bn" in name) and name.endswith("weight"):
-            out[name] = rng.uniform(0.8, 1.2, size=shape).astype(np.float32)
-        elif name.endswith("bias"):
-            out[name] = rng.normal(scale=0.05, size=shape).astype(np.float32)
-        else:  # conv weight [Co,Ci,1(,1)]
-            fan_in = shape[1]
-            out[name] = (rng.normal(size=shape) * np.sqrt(2.0 / fan_in)).astype(np.float32)
-    return out
+network_state = synth.network_state      # deterministic PointNet2 parameters (shared with bench.py)
 
 
 def network_input(batch=2, n_points=1024, seed=51):

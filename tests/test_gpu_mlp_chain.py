@@ -106,11 +106,16 @@ def test_interp_mask_and_channel_major_copy(cuda_dev, skip_ch, tile):
     idx = torch.from_numpy(rng.integers(0, M, size=(B, N, 3)).astype(np.int32)).to(cuda_dev)
     w = torch.from_numpy(rng.uniform(size=(B, N, 3)).astype(np.float32)).to(cuda_dev)
     w = (w / w.sum(2, keepdim=True)).contiguous()
-    mask = (torch.from_numpy(rng.integers(0, 2, size=(B, 128, N)).astype(np.float32)) * 2).to(cuda_dev)
+    keep = rng.integers(0, 2, size=(B, 128, N))
+    mask = (torch.from_numpy(keep.astype(np.float32)) * 2).to(cuda_dev)
+    # the kernel's form of the mask: one keep bit per (point, channel), word [b*N + n, c // 32], bit c % 32
+    kb = keep.transpose(0, 2, 1).reshape(B * N, 4, 32).astype(np.uint64)
+    bits = (kb << np.arange(32, dtype=np.uint64)).sum(axis=2).astype(np.uint32).view(np.int32)
+    bits = torch.from_numpy(np.ascontiguousarray(bits)).to(cuda_dev)
     feat_cm = torch.full((B, 128, N), float("nan"), device=cuda_dev)
     out = torch.full((B, N, 35), float("nan"), device=cuda_dev)
     fused.run_chain(pc, B, N, out, 35, tile_cols=tile, in_mode=fused.IN_INTERP, a_src=skip, a_ch=skip_ch, a_rows=N,
-                    idx=idx, b_src=f2, b_ch=C2, b_rows=M, nn_w=w, masks={0: mask}, out_cm={0: feat_cm})
+                    idx=idx, b_src=f2, b_ch=C2, b_rows=M, nn_w=w, masks={0: (bits, 2.0)}, out_cm={0: feat_cm})
     g = torch.gather(f2, 1, idx.long().reshape(B, N * 3, 1).expand(-1, -1, C2)).reshape(B, N, 3, C2)
     interp = (g * w[..., None]).sum(2)
     rows = interp if skip is None else torch.cat([skip, interp], dim=2)
