@@ -77,35 +77,65 @@ def model_state(template):
 
 
 # ----------------------------------------------------------------------------------------------
-# CPU baseline / reference arm: the oracle port on the host cores (the only place bench.py runs
-# anything under oracle/).
+# CPU baseline / reference arm (the only places bench.py runs anything under oracle/ or baseline/_ref).
+#   kind "reference": the UNMODIFIED reference Python staged under baseline/_ref (oracle/build_ref.py) on the host
+#       cores -- PointNet2.forward(x, fast=False), the reference's own torch composition of the pointnet2 ops, +
+#       softmax / normalise + SPFN.losses_implementation.compute_parameters (BASELINE.md section 3, C-a + C-b);
+#   kind "port": the oracle restatement (torch-CPU MLPs, OpenMP C index ops, numpy fitters) when nothing is staged.
 # ----------------------------------------------------------------------------------------------
 
-def cpu_step(sd, P):
-    from oracle import fitters as ofit
-    from oracle import network as onet
-    ref = onet.pointnet2_forward(sd, P, 3)
-    Xn, _, Wn = onet.spfn_postprocess(ref["heads"])
-    return ofit.compute_parameters(P, Wn, Xn)
+def _reference_cpu_step():
+    from oracle import build_ref, ref_runtime
+    ops = build_ref.load_module()
+    if ops is None or not ref_runtime.available():
+        return None
+    net = ref_runtime.load_pointnet2(ops)          # the extension only has to be importable: fast=False never calls it
+    spfn = ref_runtime.load_spfn()
+    model = net.PointNet2(dim_input=3, dim_pos=3, output_sizes=[3, 4, K_SLOTS]).eval()
+    model.load_state_dict(model_state(model.state_dict()), strict=True)
+
+    def step(P):
+        with torch.no_grad():
+            x = torch.from_numpy(P)
+            X, T, W, _, _ = model(x, fast=False)
+            X = X / torch.norm(X, dim=2, keepdim=True)                 # Utils/training_utils.py:141-142
+            W = torch.softmax(W, dim=2)
+            return spfn.compute_parameters(x, W, X)
+    return step
+
+
+def _port_cpu_step():
+    from cpfn_b200.pn2_network import PointNet2
+    from oracle import fitters as ofit, index_ops, network as onet
+    index_ops.set_threads(os.cpu_count() or 1)
+    sd = model_state(PointNet2(output_sizes=[3, 4, K_SLOTS]).state_dict())
+
+    def step(P):
+        ref = onet.pointnet2_forward(sd, P, 3)
+        Xn, _, Wn = onet.spfn_postprocess(ref["heads"])
+        return ofit.compute_parameters(P, Wn, Xn)
+    return step
 
 
 def cpu_baseline(steps, warmup, batch):
-    from cpfn_b200.pn2_network import PointNet2
-    from oracle import index_ops
+    import warnings
+    warnings.filterwarnings("ignore")
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    index_ops.set_threads(cores)
-    sd = model_state(PointNet2(output_sizes=[3, 4, K_SLOTS]).state_dict())
+    step, kind = _reference_cpu_step(), "reference"
+    if step is None:
+        step, kind = _port_cpu_step(), "port"
     inputs = make_inputs(2, batch, seed=4321)
     for i in range(warmup):
-        cpu_step(sd, inputs[i % 2])
+        step(inputs[i % 2])
     t0 = time.perf_counter()
     for i in range(steps):
-        cpu_step(sd, inputs[i % 2])
+        step(inputs[i % 2])
     dt = (time.perf_counter() - t0) / max(1, steps)
-    return {"value": batch * N_POINTS / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d steps of %d clouds x %d points (oracle/network.py torch-CPU MLPs + OpenMP C index ops, "
-                      "oracle/fitters.py numpy fitters)" % (steps, batch, N_POINTS),
+    what = ("unmodified reference: PointNet2.forward(fast=False) + SPFN compute_parameters, torch CPU" if kind == "reference"
+            else "oracle/network.py torch-CPU MLPs + OpenMP C index ops, oracle/fitters.py numpy fitters")
+    return {"value": batch * N_POINTS / dt, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": "%d steps (+%d warm-up) of %d clouds x %d points (%s)" % (steps, warmup, batch, N_POINTS, what),
             "ms_per_step": dt * 1e3}
 
 
@@ -113,12 +143,13 @@ def run_reference(args):
     rank, _, world = dist_env()
     if rank != 0:
         return
-    batch = 2
+    batch = B_PER_GPU
     cb = cpu_baseline(args.steps, args.warmup, batch)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample_batch": batch, "n_points": N_POINTS, "k_slots": K_SLOTS},
+            "config": {"workload": WORKLOAD, "batch_per_gpu": batch, "n_points": N_POINTS, "k_slots": K_SLOTS,
+                       "heads": [3, 4, K_SLOTS], "note": "host cores only; every step is one full batch of the workload"},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -128,6 +159,113 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------
 # Our arm
 # ----------------------------------------------------------------------------------------------
+
+def gpu_reference(dev, dev_inputs, steps=5, warmup=2):
+    """BASELINE.md section 3 "G-ref", the meaningful "before": the reference's own CUDA extension (built unmodified
+    for sm_100a into oracle/_ref) under the reference's own Python (fast=True, cuDNN convolutions, torch.svd fitters)
+    on this GPU, same inputs and weights, CUDA events."""
+    try:
+        from oracle import build_ref, ref_runtime
+        ops = build_ref.load_module()
+        if ops is None or not ref_runtime.available():
+            return {"unavailable": "oracle/_ref or baseline/_ref not staged"}
+        import warnings
+        warnings.filterwarnings("ignore")
+        net, spfn = ref_runtime.load_pointnet2(ops), ref_runtime.load_spfn()
+        model = net.PointNet2(dim_input=3, dim_pos=3, output_sizes=[3, 4, K_SLOTS]).to(dev).eval()
+        model.load_state_dict(model_state(model.state_dict()), strict=True)
+        ev = []
+        for i in range(warmup + steps):
+            P = dev_inputs[i % len(dev_inputs)]
+            a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            a.record()
+            with torch.no_grad():
+                X, T, W, _, _ = model(P, fast=True)
+                X = X / torch.norm(X, dim=2, keepdim=True)
+                W = torch.softmax(W, dim=2)
+                b.record()
+                spfn.compute_parameters(P, W, X)
+            c.record()
+            ev.append((a, b, c))
+        torch.cuda.synchronize()
+        net_ms = float(np.mean([a.elapsed_time(b) for a, b, _ in ev[warmup:]]))
+        fit_ms = float(np.mean([b.elapsed_time(c) for _, b, c in ev[warmup:]]))
+        return {"what": "reference cuda_ops (unmodified, sm_100a build) + reference PointNet2 / SPFN Python, fast=True, "
+                        "torch defaults (cuDNN may use TF32), same GPU / inputs / weights", "steps": steps,
+                "network_ms": net_ms, "fitters_ms": fit_ms, "ms_per_step": net_ms + fit_ms,
+                "value": B_PER_GPU * N_POINTS / ((net_ms + fit_ms) * 1e-3), "unit": UNIT}
+    except Exception as e:                                   # evidence only: never fails the bench
+        return {"unavailable": "%s: %s" % (type(e).__name__, e)}
+
+
+def module_api(eng, dev_inputs, steps=10, warmup=3):
+    """The drop-in seam B2: ``PointNet2.forward(x)`` of the reference-named module in eval mode (eager launches, no
+    CUDA graph, always-on dropout), CUDA events."""
+    ev = []
+    for i in range(warmup + steps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        with torch.no_grad():
+            eng.model(dev_inputs[i % len(dev_inputs)])
+        b.record()
+        ev.append((a, b))
+    torch.cuda.synchronize()
+    ms = float(np.mean([a.elapsed_time(b) for a, b in ev[warmup:]]))
+    return {"api": "cpfn_b200.pn2_network.PointNet2.forward (eval, eager, network only)", "ms_per_call": ms,
+            "value": B_PER_GPU * N_POINTS / (ms * 1e-3), "unit": UNIT}
+
+
+def cascade_bench(dev, rank, world, steps=10, warmup=3):
+    """The patch-sharded LocalSPFN cascade of ONE shape (BASELINE configs[3] / [4] shapes): 32 seeds ->
+    the 8192 nearest high-resolution points each -> per-patch normalisation -> LocalSPFN backbone (K = 21, patches
+    i mod G on rank i) -> NCCL all-gather of {W, X, T, indices} -> patch-to-object merge on rank 0
+    (evaluation_localSPFN.py:95-130).  Strong scaling: the shape is fixed, the ranks share its patches.
+    ms_per_shape = wall clock from a barrier to the merged result being complete on rank 0 (max over ranks)."""
+    from cpfn_b200 import api, synth
+    loc = api.LocalSPFN(n_max_local_instances=21, device=dev)
+    loc.load_state_dict(model_state(loc.engine.model.state_dict()))
+    if world > 1:
+        import torch.distributed as dist
+    records = []
+    for Ng in (131072, 1 << 20):
+        P, Xn, I = synth.shape_cloud(Ng, seed=4242)[:3]
+        rng = np.random.RandomState(7)
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        seeds = t(P[rng.choice(Ng, 32, replace=False)])
+        Pg, Xg = t(P), t(Xn)
+        S = torch.nn.functional.one_hot(t(I % K_SLOTS), K_SLOTS).float()       # object-level labels [Ng, 28]
+        Tg = t(rng.randn(Ng, 4).astype(np.float32))
+        wall, stages = [], []
+        for i in range(warmup + steps):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            tm = {}
+            t0 = time.perf_counter()
+            res = loc.run_shape_sharded(Pg, S, Xg, Tg, seeds=seeds, dropout=True, graphed=True, timings=tm)
+            if rank == 0:
+                exchange = res["exchange"]
+            torch.cuda.synchronize()
+            wall.append((time.perf_counter() - t0) * 1e3)
+            if rank == 0:
+                names = ("start", "extracted", "backbone", "gathered", "merged")
+                stages.append([tm[a].elapsed_time(tm[b]) for a, b in zip(names[:-1], names[1:])])
+        ms = torch.tensor([float(np.mean(wall[warmup:]))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            st = np.mean(np.array(stages[warmup:]), axis=0)
+            records.append({"shape_points": Ng, "patches": 32, "points_per_patch": 8192, "k_local": 21, "k_global": K_SLOTS,
+                            "n_gpus": world, "ms_per_shape": float(ms[0]), "shapes_per_s": 1e3 / float(ms[0]),
+                            "exchange": {"p2p": "fused into the producing kernel: peer-to-peer writes into the merge rank's "
+                                                "symmetric-memory buffers over NVLink + 2 device-side barriers",
+                                         "nccl": "NCCL all_gather_into_tensor (one per dtype)", "none": "single rank"}[exchange],
+                            "stages_ms_rank0": {"extract_patches": float(st[0]), "normalise+backbone(+p2p writes)": float(st[1]),
+                                                "exchange_wait": float(st[2]), "merge": float(st[3])}})
+        del Pg, Xg, S, Tg
+        torch.cuda.empty_cache()
+    return records
+
 
 class OpTimer:
     """Per-op CUDA-event timing on the launching stream (used in a separate profiling pass
@@ -259,6 +397,9 @@ def run_ours(args):
         e2e_s, pipelined = time.perf_counter() - t0, True
         assert n_done == args.steps
 
+    barrier()
+    cascade = cascade_bench(dev, rank, world) if not os.environ.get("CPFN_BENCH_NO_CASCADE") else []
+    barrier()
     t = torch.tensor([dev_ms, e2e_s * 1e3, lat_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         import torch.distributed as dist
@@ -296,7 +437,9 @@ def run_ours(args):
                 "algorithmic_bytes": fps_bytes, "kernel_us": round(fps_t * 1e6, 2),
                 "note": "effective bytes B*(m-1)*N*16 (SURVEY 8d); data is register/SMEM resident, compulsory HBM is 1.6 MB"}
 
-    cb = (cpu_baseline(steps=2, warmup=1, batch=2) if not os.environ.get('CPFN_BENCH_NO_CPU')
+    g_ref = gpu_reference(dev, dev_inputs) if not os.environ.get('CPFN_BENCH_NO_GREF') else {"unavailable": "skipped"}
+    mod_api = module_api(eng, dev_inputs)
+    cb = (cpu_baseline(steps=2, warmup=1, batch=B_PER_GPU) if not os.environ.get('CPFN_BENCH_NO_CPU')
           else {'value': None, 'unit': UNIT, 'cores': 0, 'kind': 'port', 'sample': 'skipped'})
     total_points = world * B_PER_GPU * N_POINTS
     ms_per_step = dev_ms / args.steps
@@ -317,6 +460,7 @@ def run_ours(args):
         "fits_per_s": 4 * world * B_PER_GPU * K_SLOTS / (ms_per_step * 1e-3),
         "breakdown_us": breakdown, "roofline": roofline,
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "gpu_reference": g_ref, "module_api": mod_api, "cascade": cascade,
         "clocks": clocks,
     }
     _emit(line)
@@ -355,8 +499,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
     if args.impl == "reference":
-        args.steps = min(args.steps, 20)
-        args.warmup = min(args.warmup, 2)
+        args.steps = min(args.steps, 5)          # a step is one full batch on the host cores: seconds each
+        args.warmup = min(args.warmup, 1)
         run_reference(args)
     else:
         run_ours(args)

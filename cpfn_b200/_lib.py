@@ -56,10 +56,13 @@ SIGNATURES = {
     "cpfn_three_nn_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "cpfn_linear_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "cpfn_gather_xyz": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "cpfn_normalise_patches": (c_int, [c_void_p, ctypes.c_longlong, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "cpfn_rng_set": (c_int, [c_void_p, ctypes.c_ulonglong, ctypes.c_ulonglong, c_void_p]),
     "cpfn_dropout_mask_bits": (c_int, [c_void_p, c_int, c_int, c_int, c_float, ctypes.c_longlong, c_void_p, c_void_p]),
     "cpfn_spfn_post": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_void_p]),
+    "cpfn_spfn_post_scatter": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "cpfn_extract_patches_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "cpfn_extract_patches": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_size_t, c_void_p]),
@@ -71,6 +74,9 @@ SIGNATURES = {
     "cpfn_heuristic_merging_host": (c_int, [c_void_p, c_void_p, ctypes.c_int64, c_void_p, ctypes.c_int64, c_void_p]),
     "cpfn_merge_solve_host": (c_int, [c_void_p, ctypes.c_int64, ctypes.c_double, c_void_p, c_void_p]),
     "cpfn_merge_solve_host_f32": (c_int, [c_void_p, ctypes.c_int64, c_float, c_void_p, c_void_p]),
+    "cpfn_merge_solve_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "cpfn_merge_solve": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_size_t, c_void_p]),
     "cpfn_merge_point_labels": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                         c_int, c_int, c_void_p, c_void_p]),
     "cpfn_merge_dense_labels": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),

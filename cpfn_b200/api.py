@@ -53,11 +53,13 @@ class GlobalSPFN:
         return changed
 
     @torch.no_grad()
-    def forward(self, P, dropout=True, fit=True):
+    def forward(self, P, dropout=True, fit=True, scatter=None):
         """P [B,N,3] float32 on the device.  Returns a dict: X [B,N,3] unit normals, T [B,N,n_types]
         type logits, W [B,N,K] soft memberships, X_raw/T_raw/W_raw head outputs, l3_feats,
         output_feat, sa1_fps (int32 [B,512]) and ``parameters`` (the reference's dictionary).
-        ``dropout=False`` replaces the reference's always-on dropout by the identity (parity runs)."""
+        ``dropout=False`` replaces the reference's always-on dropout by the identity (parity runs).
+        ``scatter``: see fused.spfn_post -- X / W / T are written into slabs of the given (possibly peer-mapped)
+        arrays instead of fresh tensors (patch-sharded cascade)."""
         from . import fused
         if fused.available():
             if not P.is_cuda:
@@ -75,7 +77,9 @@ class GlobalSPFN:
                 # SPFN post-processing (Utils/training_utils.py:141-142) in one kernel
                 nt = heads[1].shape[2]
                 out["X"], out["W"], out["instance"], out["type"] = fused.spfn_post(packed, 0, 3 + nt, heads[2].shape[2],
-                                                                                   t_off=3, n_types=nt)
+                                                                                   t_off=3, n_types=nt, scatter=scatter)
+            elif scatter is not None:
+                raise RuntimeError("scatter needs the SPFN head layout [3, n_types, K <= 64]")
             else:
                 out["X"] = torch.nn.functional.normalize(heads[0], p=2, dim=2, eps=1e-12)
                 out["W"] = torch.softmax(heads[2], dim=2)
@@ -104,13 +108,13 @@ class GlobalSPFN:
         return graph, out, cuda_ops.LAUNCHES - n0
 
     @torch.no_grad()
-    def forward_graphed(self, P, dropout=True, fit=True):
+    def forward_graphed(self, P, dropout=True, fit=True, scatter=None):
         """``forward`` replayed from a CUDA graph (captured once per input shape): the ~50 kernel
         launches of a step become one graph launch.  ``P`` may be a device tensor or a pinned host
         tensor (copied straight into the graph's input).  The returned tensors are STATIC buffers that
         the next call overwrites; the always-on dropout still draws a fresh mask per call (torch's
         graph-safe generator)."""
-        graph, static_in, out, n_launch = self._net_graph(P, dropout, fit, 0)
+        graph, static_in, out, n_launch = self._net_graph(P, dropout, fit, 0, scatter=scatter)
         static_in.copy_(P, non_blocking=True)
         if dropout:
             self._sync_rng(P.shape)
@@ -124,17 +128,20 @@ class GlobalSPFN:
         from . import fused
         fused.sync_rng(self.device, shape[0] * 128 * shape[1])
 
-    def _net_graph(self, P, dropout, fit, slot):
+    def _net_graph(self, P, dropout, fit, slot, scatter=None):
         """(graph, its static input, its static outputs, launches) for inputs shaped like P; ``slot`` selects one
         of several independent copies (own input / output buffers) so that consecutive batches can overlap."""
         if self._weights_changed():
             self._graphs.clear()
         key = (tuple(P.shape), bool(dropout), bool(fit)) + ((slot,) if slot else ())
+        if scatter is not None:                               # the destination pointers are baked into the graph
+            key += (("scatter", scatter["W"].data_ptr(), scatter["X"].data_ptr(), scatter["T"].data_ptr(),
+                     int(scatter["stride"]), int(scatter["offset"])),)
         entry = self._graphs.get(key)
         if entry is None:
             static_in = torch.empty(tuple(P.shape), dtype=torch.float32, device=self.device)
             static_in.copy_(P)
-            graph, out, n = self._capture(lambda: self.forward(static_in, dropout=dropout, fit=fit))
+            graph, out, n = self._capture(lambda: self.forward(static_in, dropout=dropout, fit=fit, scatter=scatter))
             entry = (graph, static_in, out, n)
             self._graphs[key] = entry
         return entry
@@ -311,12 +318,62 @@ class LocalSPFN:
     def load_state_dict(self, sd, strict=True):
         return self.engine.load_state_dict(sd, strict=strict)
 
+    def _peer_exchange(self, nb, Np, group, merge_rank):
+        """Receive buffers of the patch-sharded cascade in SYMMETRIC memory (torch.distributed._symmetric_memory: one
+        allocation per rank, every rank's copy mapped into every other rank's address space over NVLink): W [nb,Np,Kl]
+        | X [nb,Np,3] | T [nb,Np,n_types] float32 and the int64 patch indices [nb,Np].  Returns a dict with the
+        merge rank's buffers as seen from THIS rank (peer-mapped unless this is the merge rank) and the handles for
+        the device-side barriers; None when symmetric memory is unavailable (the NCCL all-gather path is used)."""
+        import torch.distributed as dist
+        key = (nb, Np, merge_rank, id(group))
+        cache = self.__dict__.setdefault("_exchanges", {})
+        if key in cache:
+            return cache[key]
+        ex = None
+        try:
+            import torch.distributed._symmetric_memory as symm
+            Kl, nt = self.engine.output_sizes[2], self.engine.output_sizes[1]
+            g = group if group is not None else dist.group.WORLD
+            n_f = nb * Np * (Kl + 3 + nt)
+            fbuf = symm.empty(n_f, dtype=torch.float32, device=self.device)
+            ibuf = symm.empty(nb * Np, dtype=torch.int64, device=self.device)
+            fh, ih = symm.rendezvous(fbuf, g), symm.rendezvous(ibuf, g)
+            views = {}
+            for name, hdl_rank in (("dst", merge_rank), ("own", dist.get_rank(group))):
+                o = 0
+                v = {}
+                for f, width in (("W", Kl), ("X", 3), ("T", nt)):
+                    v[f] = fh.get_buffer(hdl_rank, (nb, Np, width), torch.float32, o)
+                    o += nb * Np * width
+                v["idx"] = ih.get_buffer(hdl_rank, (nb, Np), torch.int64, 0)
+                views[name] = v
+            ex = {"dst": views["dst"], "own": views["own"], "fh": fh, "ih": ih, "keep": (fbuf, ibuf)}
+        except Exception as e:                                   # no peer mapping on this system: NCCL path
+            self.__dict__["_exchange_error"] = "%s: %s" % (type(e).__name__, e)
+        cache[key] = ex
+        return ex
+
     @staticmethod
     def normalise_patches(P_global, patch_indices):
-        """dataloaders.py:249-253: centre every patch on its mean and scale it into the unit ball."""
-        P = P_global[patch_indices.long()]
-        P = P - P.mean(dim=1, keepdim=True)
-        return P / P.norm(dim=2, keepdim=True).amax(dim=1, keepdim=True)
+        """dataloaders.py:249-253: centre every patch on its mean and scale it into the unit ball -- one kernel
+        (gather + mean + max norm + scale, csrc/glue.cu) whose per-patch result does not depend on how many patches
+        are normalised together (a sharded run is bit-identical to a single-GPU one)."""
+        from . import _lib
+        if not P_global.is_cuda:
+            raise RuntimeError("CPU not supported")
+        P_global = P_global.to(torch.float32).contiguous()
+        idx = patch_indices.contiguous()
+        if idx.dtype not in (torch.int32, torch.int64):
+            idx = idx.to(torch.int64)
+        nb, Np = idx.shape
+        out = torch.empty(nb, Np, 3, dtype=torch.float32, device=P_global.device)
+        with torch.cuda.device(P_global.device):
+            _lib.check(_lib.lib().cpfn_normalise_patches(P_global.data_ptr(), P_global.shape[0], idx.data_ptr(),
+                                                         int(idx.dtype == torch.int64), nb, Np, out.data_ptr(),
+                                                         torch.cuda.current_stream(P_global.device).cuda_stream),
+                       "normalise_patches")
+        cuda_ops.count_launches(1)
+        return out
 
     @torch.no_grad()
     def run_shape(self, P_global, spfn_labels, spfn_normals, spfn_type, seeds=None, patch_indices=None, dropout=True,
@@ -341,3 +398,90 @@ class LocalSPFN:
             spfn_type.to(self.device), threshold=threshold)
         return {"W_fusion": W_fusion, "X_global": X_global, "T_global": T_global, "labels": labels,
                 "patch_indices": patch_indices, "W": out["W"], "X": out["X"], "T": out["T"]}
+
+    @torch.no_grad()
+    def run_shape_sharded(self, P_global, spfn_labels, spfn_normals, spfn_type, seeds=None, patch_indices=None,
+                          dropout=True, graphed=True, threshold=0, group=None, merge_rank=0, timings=None,
+                          exchange="auto"):
+        """``run_shape`` with the shape's patches sharded over the ranks of ``group``: every rank passes
+        the SAME shape (high-resolution cloud, object-level prediction, seeds or patch indices); rank r extracts,
+        normalises and runs the LocalSPFN backbone on patches r, r+G, ... only (replicated weights, no collective),
+        the per-point outputs {W, X, T, patch indices} of all patches travel to rank ``merge_rank``, which runs the
+        merge (evaluation_localSPFN.py:99-130; Utils/merging_utils.similarity_soft needs every patch's memberships).
+        ``exchange``:
+          "p2p"   the kernel that produces W / X / T (softmax / normalise, cpfn_spfn_post_scatter) writes them straight
+                  into the merge rank's receive buffers -- symmetric memory, peer-mapped over NVLink -- so compute and
+                  transfer are one kernel; two device-side barriers order it against the merge (no NCCL on the path);
+          "nccl"  one all-gather per dtype (dist.all_gather_patches), then a row permutation;
+          "auto"  "p2p" when symmetric memory is available and the patch size is a multiple of 256 points.
+        Returns the ``run_shape`` dictionary on ``merge_rank`` (with "p2p" its W / X / T / patch_indices are views of
+        the receive buffers, valid until the next call) and None elsewhere.  ``timings``: optional dict that receives
+        CUDA events around the stages (bench.py)."""
+        import torch.distributed as dist
+        from . import dist as cdist, merging_utils, sampling_utils
+        alone = not (dist.is_available() and dist.is_initialized())          # no process group: a world of one rank
+        world, rank = (1, 0) if alone else (dist.get_world_size(group), dist.get_rank(group))
+        dev = self.device
+        P_global = P_global.to(dev, torch.float32).contiguous()
+        nb = int(seeds.shape[0] if patch_indices is None else patch_indices.shape[0])
+        if nb == 0:
+            raise ValueError("run_shape_sharded needs at least one patch")
+        Np = min(self.num_points_patch, P_global.shape[0]) if patch_indices is None else int(patch_indices.shape[1])
+        mine = cdist.shard_units(nb, rank, world)
+        sel = torch.tensor(mine, dtype=torch.int64, device=dev)
+        Kl, nt = self.engine.output_sizes[2], self.engine.output_sizes[1]
+        ex = None
+        if world > 1 and exchange in ("auto", "p2p") and Np % 256 == 0:
+            ex = self._peer_exchange(nb, Np, group, merge_rank)
+        if exchange == "p2p" and world > 1 and ex is None:
+            raise RuntimeError("peer exchange unavailable: %s" % self.__dict__.get("_exchange_error", "patch size"))
+
+        def mark(name):
+            if timings is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                timings[name] = e
+        mark("start")
+        if ex is not None:
+            ex["fh"].barrier(channel=0)          # the previous shape's merge has consumed the receive buffers
+        if len(mine):
+            if patch_indices is None:
+                my_idx = sampling_utils.extract_patches(P_global, seeds.to(dev, torch.float32).index_select(0, sel),
+                                                        self.num_points_patch)
+            else:
+                my_idx = patch_indices.to(dev).index_select(0, sel)
+            mark("extracted")
+            P = self.normalise_patches(P_global, my_idx)
+            run = self.engine.forward_graphed if graphed else self.engine.forward
+            if ex is not None:
+                ex["dst"]["idx"][rank::world][:len(mine)].copy_(my_idx)              # patch j -> slab j * G + rank
+                run(P, dropout=dropout, fit=False,
+                    scatter={"X": ex["dst"]["X"], "W": ex["dst"]["W"], "T": ex["dst"]["T"], "stride": world, "offset": rank})
+            else:
+                out = run(P, dropout=dropout, fit=False)
+                if world > 1:
+                    feats = torch.cat([out["W"], out["X"], out["T"]], dim=2)         # [b, Np, Kl + 3 + n_types]
+        else:                                                                        # more ranks than patches
+            my_idx = torch.empty(0, Np, dtype=torch.int64, device=dev)
+            mark("extracted")
+            feats = torch.empty(0, Np, Kl + 3 + nt, dtype=torch.float32, device=dev)
+        mark("backbone")
+        if ex is not None:
+            ex["fh"].barrier(channel=1)          # every rank's writes have landed in the merge rank's memory
+            own = ex["own"]
+            W, X, T, idx_all = own["W"], own["X"], own["T"], own["idx"]
+        elif world == 1:
+            W, X, T, idx_all = out["W"], out["X"], out["T"], my_idx.to(torch.int64)
+        else:
+            feats_all, idx_all = cdist.all_gather_patches(feats, my_idx, nb, group=group)
+            W, X, T = (feats_all[:, :, :Kl].contiguous(), feats_all[:, :, Kl:Kl + 3].contiguous(),
+                       feats_all[:, :, Kl + 3:].contiguous())
+        mark("gathered")
+        if rank != merge_rank:
+            return None
+        W_fusion, X_global, T_global, labels = merging_utils.merge_shape(
+            W, X, T, idx_all, spfn_labels.to(dev), spfn_normals.to(dev), spfn_type.to(dev), threshold=threshold)
+        mark("merged")
+        return {"W_fusion": W_fusion, "X_global": X_global, "T_global": T_global, "labels": labels,
+                "patch_indices": idx_all, "W": W, "X": X, "T": T,
+                "exchange": "p2p" if ex is not None else ("none" if world == 1 else "nccl")}

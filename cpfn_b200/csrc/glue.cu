@@ -81,13 +81,28 @@ template <int KMAX>
 __global__ void __launch_bounds__(kGlueThreads)
 spfn_post_kernel(const float *__restrict__ heads, long long rows, int ld, int x_off, int t_off, int n_types,
                  int w_off, int K, float *__restrict__ X, float *__restrict__ W, int32_t *__restrict__ inst,
-                 int32_t *__restrict__ type) {
+                 int32_t *__restrict__ type, float *__restrict__ T_out, int rows_per_patch, int patch_stride,
+                 int patch_offset) {
   extern __shared__ float s_rows[];          // [kGlueThreads * max(ld, K)]
   const long long r0 = static_cast<long long>(blockIdx.x) * kGlueThreads;
   const int nr = static_cast<int>(min(static_cast<long long>(kGlueThreads), rows - r0));
+  // destination rows of X / W / T_out: identity, or -- patch-sharded cascade -- local patch j goes to the slab of
+  // patch j * patch_stride + patch_offset of the (possibly peer-mapped) destination (blocks never straddle patches)
+  long long q0 = r0;
+  if (rows_per_patch > 0) {
+    const long long j = r0 / rows_per_patch;
+    q0 = (j * patch_stride + patch_offset) * rows_per_patch + (r0 - j * rows_per_patch);
+  }
   const float *src = heads + r0 * ld;
   for (int i = threadIdx.x; i < nr * ld; i += kGlueThreads) s_rows[i] = __ldg(src + i);
   __syncthreads();
+  if (T_out != nullptr) {                      // the type logits as their own [rows, n_types] array
+    float *dt = T_out + q0 * n_types;
+    for (int i = threadIdx.x; i < nr * n_types; i += kGlueThreads) {
+      const int r = i / n_types;
+      dt[i] = s_rows[r * ld + t_off + (i - r * n_types)];
+    }
+  }
   float v[KMAX];
   float xn = 0.f, yn = 0.f, zn = 0.f;
   if (threadIdx.x < nr) {
@@ -128,10 +143,10 @@ spfn_post_kernel(const float *__restrict__ heads, long long rows, int ld, int x_
 #pragma unroll
     for (int k = 0; k < KMAX; ++k)
       if (k < K) o[k] = v[k];
-    X[(r0 + threadIdx.x) * 3] = xn; X[(r0 + threadIdx.x) * 3 + 1] = yn; X[(r0 + threadIdx.x) * 3 + 2] = zn;
+    X[(q0 + threadIdx.x) * 3] = xn; X[(q0 + threadIdx.x) * 3 + 1] = yn; X[(q0 + threadIdx.x) * 3 + 2] = zn;
   }
   __syncthreads();
-  float *dst = W + r0 * K;
+  float *dst = W + q0 * K;
   for (int i = threadIdx.x; i < nr * K; i += kGlueThreads) dst[i] = s_rows[i];
 }
 
@@ -172,6 +187,75 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 // curand_uniform: x * 2^-32 + 2^-33 in fp32, in (0, 1]
 __device__ __forceinline__ bool keep_bit(unsigned int x, float keep) {
   return __fmaf_rn(__uint2float_rn(x), 2.3283064e-10f, 1.16415322e-10f) < keep;
+}
+
+// Per-patch normalisation of the LocalSPFN input (Dataset/dataloaders.py:249-253): gather the patch's points, centre
+// them on their mean, scale by the largest distance from it.  One CTA per patch; the mean is accumulated in fp64 in
+// a FIXED order (thread-strided partial sums, shuffle tree, warp 0 over the warp sums), so a patch's result does not
+// depend on how many patches share the call -- torch's reductions pick their strategy from the tensor shape.
+template <typename IndexT>
+__global__ void __launch_bounds__(1024)
+normalise_patches_kernel(const float *__restrict__ P, const IndexT *__restrict__ idx, int Np, long long Ng,
+                         float *__restrict__ out) {
+  __shared__ double s_sum[32][3];
+  __shared__ float s_mean[3], s_max[32], s_scale;
+  const IndexT *my = idx + static_cast<size_t>(blockIdx.x) * Np;
+  float *o = out + static_cast<size_t>(blockIdx.x) * Np * 3;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double sx = 0.0, sy = 0.0, sz = 0.0;
+  for (int i = threadIdx.x; i < Np; i += 1024) {
+    const long long g = static_cast<long long>(my[i]);
+    const float *p = P + (g >= 0 && g < Ng ? g : 0) * 3;
+    sx += static_cast<double>(__ldg(p)); sy += static_cast<double>(__ldg(p + 1)); sz += static_cast<double>(__ldg(p + 2));
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    sx += __shfl_down_sync(0xffffffffu, sx, off);
+    sy += __shfl_down_sync(0xffffffffu, sy, off);
+    sz += __shfl_down_sync(0xffffffffu, sz, off);
+  }
+  if (lane == 0) { s_sum[warp][0] = sx; s_sum[warp][1] = sy; s_sum[warp][2] = sz; }
+  __syncthreads();
+  if (warp == 0) {
+    double a = s_sum[lane][0], b = s_sum[lane][1], c = s_sum[lane][2];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      a += __shfl_down_sync(0xffffffffu, a, off);
+      b += __shfl_down_sync(0xffffffffu, b, off);
+      c += __shfl_down_sync(0xffffffffu, c, off);
+    }
+    if (lane == 0) {
+      s_mean[0] = static_cast<float>(a / Np); s_mean[1] = static_cast<float>(b / Np); s_mean[2] = static_cast<float>(c / Np);
+    }
+  }
+  __syncthreads();
+  const float mx = s_mean[0], my_ = s_mean[1], mz = s_mean[2];
+  float best = 0.f;
+  for (int i = threadIdx.x; i < Np; i += 1024) {
+    const long long g = static_cast<long long>(my[i]);
+    const float *p = P + (g >= 0 && g < Ng ? g : 0) * 3;
+    const float dx = __fsub_rn(__ldg(p), mx), dy = __fsub_rn(__ldg(p + 1), my_), dz = __fsub_rn(__ldg(p + 2), mz);
+    best = fmaxf(best, __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz))));
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, off));
+  if (lane == 0) s_max[warp] = best;
+  __syncthreads();
+  if (warp == 0) {
+    float m = s_max[lane];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if (lane == 0) s_scale = m;
+  }
+  __syncthreads();
+  const float scale = s_scale;
+  for (int i = threadIdx.x; i < Np; i += 1024) {
+    const long long g = static_cast<long long>(my[i]);
+    const float *p = P + (g >= 0 && g < Ng ? g : 0) * 3;
+    o[i * 3] = __fdiv_rn(__fsub_rn(__ldg(p), mx), scale);
+    o[i * 3 + 1] = __fdiv_rn(__fsub_rn(__ldg(p + 1), my_), scale);
+    o[i * 3 + 2] = __fdiv_rn(__fsub_rn(__ldg(p + 2), mz), scale);
+  }
 }
 
 __global__ void rng_set_kernel(unsigned long long *state, unsigned long long seed, unsigned long long offset) {
@@ -249,6 +333,19 @@ extern "C" int cpfn_linear_rows(const float *x, const float *W, const float *bia
   return check_launch();
 }
 
+extern "C" int cpfn_normalise_patches(const float *points, long long Ng, const void *patch_idx, int idx_is_int64,
+                                      int nb, int Np, float *out, cpfn_stream_t stream) {
+  using namespace cpfn;
+  if (nb < 0 || Np <= 0 || Ng <= 0) return CPFN_EINVAL;
+  if (nb == 0) return CPFN_OK;
+  if (!points || !patch_idx || !out) return CPFN_EINVAL;
+  if (idx_is_int64)
+    normalise_patches_kernel<long long><<<nb, 1024, 0, as_stream(stream)>>>(points, static_cast<const long long *>(patch_idx), Np, Ng, out);
+  else
+    normalise_patches_kernel<int32_t><<<nb, 1024, 0, as_stream(stream)>>>(points, static_cast<const int32_t *>(patch_idx), Np, Ng, out);
+  return check_launch();
+}
+
 extern "C" int cpfn_rng_set(unsigned long long *rng_state, unsigned long long seed, unsigned long long offset,
                             cpfn_stream_t stream) {
   using namespace cpfn;
@@ -297,12 +394,15 @@ extern "C" int cpfn_gather_xyz(const float *xyz, const int32_t *idx, int B, int 
   return check_launch();
 }
 
-extern "C" int cpfn_spfn_post(const float *heads, long long rows, int ld, int x_off, int t_off, int n_types,
-                              int w_off, int K, float *X, float *W, int32_t *inst, int32_t *type,
-                              cpfn_stream_t stream) {
+extern "C" int cpfn_spfn_post_scatter(const float *heads, long long rows, int ld, int x_off, int t_off, int n_types,
+                                      int w_off, int K, float *X, float *W, float *T_out, int32_t *inst, int32_t *type,
+                                      int rows_per_patch, int patch_stride, int patch_offset, cpfn_stream_t stream) {
   using namespace cpfn;
   if (rows < 0 || K <= 0 || K > 64 || ld < 3 || x_off < 0 || w_off < 0 || x_off + 3 > ld || w_off + K > ld ||
-      (type != nullptr && (t_off < 0 || n_types <= 0 || t_off + n_types > ld))) return CPFN_EINVAL;
+      ((type != nullptr || T_out != nullptr) && (t_off < 0 || n_types <= 0 || t_off + n_types > ld))) return CPFN_EINVAL;
+  if (rows_per_patch < 0 || (rows_per_patch > 0 && ((rows_per_patch % kGlueThreads) != 0 || patch_stride <= 0 ||
+                                                     patch_offset < 0 || patch_offset >= patch_stride)))
+    return CPFN_EINVAL;
   if (rows == 0) return CPFN_OK;
   if (!heads || !X || !W) return CPFN_EINVAL;
   const unsigned grid = static_cast<unsigned>((rows + kGlueThreads - 1) / kGlueThreads);
@@ -310,10 +410,16 @@ extern "C" int cpfn_spfn_post(const float *heads, long long rows, int ld, int x_
   const size_t smem = static_cast<size_t>(kGlueThreads) * (ld > K ? ld : K) * sizeof(float);
   if (K <= 32) {
     if (smem > 48 * 1024) CPFN_CUDA_TRY(cudaFuncSetAttribute(spfn_post_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    spfn_post_kernel<32><<<grid, kGlueThreads, smem, as_stream(stream)>>>(heads, rows, ld, x_off, t_off, n_types, w_off, K, X, W, inst, type);
+    spfn_post_kernel<32><<<grid, kGlueThreads, smem, as_stream(stream)>>>(heads, rows, ld, x_off, t_off, n_types, w_off, K, X, W, inst, type, T_out, rows_per_patch, patch_stride, patch_offset);
   } else {
     if (smem > 48 * 1024) CPFN_CUDA_TRY(cudaFuncSetAttribute(spfn_post_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    spfn_post_kernel<64><<<grid, kGlueThreads, smem, as_stream(stream)>>>(heads, rows, ld, x_off, t_off, n_types, w_off, K, X, W, inst, type);
+    spfn_post_kernel<64><<<grid, kGlueThreads, smem, as_stream(stream)>>>(heads, rows, ld, x_off, t_off, n_types, w_off, K, X, W, inst, type, T_out, rows_per_patch, patch_stride, patch_offset);
   }
   return check_launch();
+}
+
+extern "C" int cpfn_spfn_post(const float *heads, long long rows, int ld, int x_off, int t_off, int n_types,
+                              int w_off, int K, float *X, float *W, int32_t *inst, int32_t *type,
+                              cpfn_stream_t stream) {
+  return cpfn_spfn_post_scatter(heads, rows, ld, x_off, t_off, n_types, w_off, K, X, W, nullptr, inst, type, 0, 0, 0, stream);
 }

@@ -19,6 +19,40 @@ def units_per_rank(n_units, world):
     return (n_units + world - 1) // world
 
 
+def all_gather_patches(feats, indices, n_units, group=None):
+    """The exchange step of the patch-sharded cascade on tensors: rank r holds its patches' per-point outputs
+    ``feats`` f32 [b, Np, F] (memberships | normals | type logits, concatenated along F) and ``indices`` int [b, Np]
+    (global point ids) for units r, r+G, ... in that order (b may be 0).  Returns (feats [n_units, Np, F], indices
+    int64 [n_units, Np]) in UNIT order on every rank: one collective per dtype (``all_gather_into_tensor`` on NCCL --
+    NVLink / NVSwitch on one box -- plain ``all_gather`` on gloo), then one row permutation."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    nccl = dist.get_backend(group) == "nccl"
+    per = units_per_rank(n_units, world)
+    mine = len(shard_units(n_units, rank, world))
+    if feats.shape[0] != mine or indices.shape[0] != mine:
+        raise ValueError("rank %d passes %d patches, its share of %d units is %d" % (rank, feats.shape[0], n_units, mine))
+    if feats.dtype != torch.float32:
+        raise TypeError("all_gather_patches: float32 features required")
+    Np, F = feats.shape[1], feats.shape[2]            # every rank knows the record shape (it depends on the model only)
+    dev = feats.device
+    send = torch.zeros(per, Np, F, dtype=torch.float32, device=dev) if mine < per else feats.contiguous()
+    send_idx = torch.zeros(per, Np, dtype=torch.int64, device=dev)
+    if mine < per:
+        send[:mine] = feats
+    send_idx[:mine] = indices.to(torch.int64)
+    recv = torch.empty(world * per, Np, F, dtype=torch.float32, device=dev)
+    recv_idx = torch.empty(world * per, Np, dtype=torch.int64, device=dev)
+    if nccl:
+        dist.all_gather_into_tensor(recv, send, group=group)
+        dist.all_gather_into_tensor(recv_idx, send_idx, group=group)
+    else:
+        dist.all_gather(list(recv.view(world, per, Np, F).unbind(0)), send, group=group)
+        dist.all_gather(list(recv_idx.view(world, per, Np).unbind(0)), send_idx, group=group)
+    order = torch.tensor([(u % world) * per + u // world for u in range(n_units)], dtype=torch.int64, device=dev)
+    return recv.index_select(0, order), recv_idx.index_select(0, order)
+
+
 def gather_patch_records(records, n_units, group=None):
     """All-gather the per-patch records of every rank; returns the list of `n_units` records in unit
     order (unit i lives on rank i mod G) on every rank.  A record is a dict with ``W`` f32 [n,K] memberships,

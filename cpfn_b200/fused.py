@@ -238,19 +238,34 @@ def gather_xyz(xyz, idx):
     return out
 
 
-def spfn_post(heads, x_off, w_off, K, t_off=None, n_types=0):
+def spfn_post(heads, x_off, w_off, K, t_off=None, n_types=0, scatter=None):
     """heads [B,N,ld] contiguous -> (X [B,N,3] unit normals, W [B,N,K] softmax memberships,
-    instance int32 [B,N] = argmax W, type int32 [B,N] = argmax of the type logits | None)."""
+    instance int32 [B,N] = argmax W, type int32 [B,N] = argmax of the type logits | None).
+    ``scatter`` = dict(X=, W=, T=, stride=, offset=): the patch-sharded cascade's exchange fused into this kernel --
+    X / W and the type logits T of local patch j are written into the slabs j * stride + offset of the given
+    [n_patches, N, .] arrays, which may live in ANOTHER GPU's memory (peer-mapped, see api.LocalSPFN); the returned
+    X / W are then those destination arrays."""
     B, N, ld = heads.shape
     dev = heads.device
-    X = torch.empty(B, N, 3, dtype=torch.float32, device=dev)
-    W = torch.empty(B, N, K, dtype=torch.float32, device=dev)
     inst = torch.empty(B, N, dtype=torch.int32, device=dev)
     typ = torch.empty(B, N, dtype=torch.int32, device=dev) if t_off is not None else None
+    if scatter is None:
+        X = torch.empty(B, N, 3, dtype=torch.float32, device=dev)
+        W = torch.empty(B, N, K, dtype=torch.float32, device=dev)
+        T_out, geom = None, (0, 0, 0)
+    else:
+        X, W, T_out = scatter["X"], scatter["W"], scatter["T"]
+        geom = (N, int(scatter["stride"]), int(scatter["offset"]))
+        if N % 256 or X.shape[1:] != (N, 3) or W.shape[1:] != (N, K) or T_out.shape[1:] != (N, n_types) or \
+                not (X.is_contiguous() and W.is_contiguous() and T_out.is_contiguous()) or \
+                (B - 1) * geom[1] + geom[2] >= W.shape[0]:
+            raise ValueError("spfn_post: scatter destination does not match the batch")
     with torch.cuda.device(dev):
-        _lib.check(_lib.lib().cpfn_spfn_post(heads.data_ptr(), B * N, ld, x_off, t_off or 0, n_types, w_off, K,
-                                             X.data_ptr(), W.data_ptr(), inst.data_ptr(),
-                                             typ.data_ptr() if typ is not None else None, _stream(heads)), "spfn_post")
+        _lib.check(_lib.lib().cpfn_spfn_post_scatter(heads.data_ptr(), B * N, ld, x_off, t_off or 0, n_types, w_off, K,
+                                                     X.data_ptr(), W.data_ptr(),
+                                                     T_out.data_ptr() if T_out is not None else None, inst.data_ptr(),
+                                                     typ.data_ptr() if typ is not None else None, *geom,
+                                                     _stream(heads)), "spfn_post")
     cuda_ops.count_launches(1)
     return X, W, inst, typ
 

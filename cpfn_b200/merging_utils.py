@@ -11,9 +11,11 @@ Same function names, argument order and results as the reference module:
 The reference builds the dense point-to-primitive matrix [N_global, nb*Kl+Kg] (367 MB at 131 072 points,
 2.8 GB at 1 M) and multiplies it with itself; here ``similarity_soft`` works from an inverse patch index
 and never builds it (csrc/merge.cu).  ``fuse_patches`` / ``merge_normals_types`` do the evaluation script's
-fusion block the same way, and ``merge_shape`` chains the whole thing.  The greedy merge is sequential and
-tiny (<= a few hundred nodes): it runs on the host in C (``cpfn_heuristic_merging_host``), as the reference
-runs it on the host in numba.
+fusion block the same way, and ``merge_shape`` chains the whole thing.  The greedy label merge -- on the host in
+numba in the reference, after a device->host copy of the similarity matrix -- is a device solve here
+(``solve_labels_device``: csrc/merge_solve.cu), so that a shape's merge is a sequence of kernels with a single
+4-byte read-back (the number of labels, which sizes the result); ``run_heuristic_solver`` / ``heuristic_merging``
+keep the reference's host signatures (numpy in, numpy out) on a C implementation of the same pass.
 """
 import ctypes
 
@@ -109,6 +111,40 @@ def run_heuristic_solver(similarity_matrix, nb_patches, max_label_per_object, ma
     return labels
 
 
+MAX_DEVICE_PATCHES = 63          # patch sets are 64-bit masks on the device (patches + the object "patch")
+
+
+def solve_labels_device(similarity_matrix, nb_patches, max_label_per_object, max_label_per_patch, threshold=0,
+                        return_segments=False):
+    """``run_heuristic_solver`` (merging_utils.py:35-44, incl. heuristic_merging :17-33) on the device, from the
+    float32 CUDA matrix ``similarity_soft`` returns.  -> (labels int32 [M] CUDA, label_weight f32 [M] CUDA with
+    entry l = 1 / (members of label l + 1e-10), n_labels int32 [1] CUDA[, raw segment ids int32 [M]]).  Nothing is
+    copied to the host and nothing synchronises."""
+    _need_cuda(similarity_matrix)
+    nb, Kg, Kl = int(nb_patches), int(max_label_per_object), int(max_label_per_patch)
+    M = nb * Kl + Kg
+    if similarity_matrix.dtype != torch.float32 or tuple(similarity_matrix.shape) != (M, M):
+        raise ValueError("similarity_matrix must be float32 [nb*Kl+Kg, nb*Kl+Kg]")
+    if nb > MAX_DEVICE_PATCHES:
+        raise ValueError("solve_labels_device handles up to %d patches (use run_heuristic_solver)" % MAX_DEVICE_PATCHES)
+    sim = similarity_matrix.contiguous()
+    dev = sim.device
+    labels = torch.empty(M, dtype=torch.int32, device=dev)
+    weights = torch.empty(M, dtype=torch.float32, device=dev)
+    n_labels = torch.empty(1, dtype=torch.int32, device=dev)
+    segments = torch.empty(M, dtype=torch.int32, device=dev) if return_segments else None
+    lib = _lib.lib()
+    with torch.cuda.device(dev):
+        nbytes = lib.cpfn_merge_solve_workspace_bytes(nb, Kl, Kg)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _lib.check(lib.cpfn_merge_solve(sim.data_ptr(), nb, Kl, Kg, float(np.float32(threshold)), labels.data_ptr(),
+                                        weights.data_ptr(), n_labels.data_ptr(),
+                                        segments.data_ptr() if segments is not None else None, ws.data_ptr(), nbytes,
+                                        _stream(sim)), "merge_solve")
+    cuda_ops.count_launches(4)
+    return (labels, weights, n_labels, segments) if return_segments else (labels, weights, n_labels)
+
+
 def _labels_and_weights(labels, device):
     """labels (numpy / list / tensor) -> (int32 labels on the device, 1/(members + 1e-10) per label, L).  The label
     vector has a few hundred entries and normally comes from the host solver: counted on the host, no sync."""
@@ -134,15 +170,16 @@ def get_point_final(point2primitive_prediction, output_labels_heuristic):
     return out
 
 
-def fuse_patches(spfn_labels, predicted_labels, point_indices, labels, inverse=None):
+def fuse_patches(spfn_labels, predicted_labels, point_indices, labels, inverse=None, device_solution=None):
     """evaluation_localSPFN.py:103-111 in one kernel: what ``get_point_final(point2primitive_fusion, labels)``
-    returns there, without building point2primitive_fusion."""
+    returns there, without building point2primitive_fusion.  ``device_solution`` = (labels int32 CUDA, label_weight,
+    number of labels as a Python int) from ``solve_labels_device`` skips the host-side label bookkeeping."""
     _need_cuda(spfn_labels, predicted_labels, point_indices)
     S, W = _f32(spfn_labels), _f32(predicted_labels)
     Ng, Kg = S.shape
     nb, Np, Kl = W.shape
     idx, inv = inverse if inverse is not None else inverse_index(point_indices, Ng)
-    labels, v, L = _labels_and_weights(labels, W.device)
+    labels, v, L = device_solution if device_solution is not None else _labels_and_weights(labels, W.device)
     out = torch.empty(Ng, L, dtype=torch.float32, device=W.device)
     with torch.cuda.device(W.device):
         _lib.check(_lib.lib().cpfn_merge_point_labels(W.data_ptr(), S.data_ptr(), inv.data_ptr(), labels.data_ptr(),
@@ -169,14 +206,22 @@ def merge_normals_types(X, T, point_indices, spfn_normals, spfn_type, inverse=No
     return Xg, Tg
 
 
-def merge_shape(W, X, T, point_indices, spfn_labels, spfn_normals, spfn_type, threshold=0):
+def merge_shape(W, X, T, point_indices, spfn_labels, spfn_normals, spfn_type, threshold=0, solver="device"):
     """The whole fusion block of evaluation_localSPFN.py:99-130 for one shape.  W [nb,Np,Kl] soft-maxed
     memberships, X [nb,Np,3] unit normals, T [nb,Np,n_types].  Returns (W_fusion [Ng,L], X_global, T_global,
-    labels int64 [nb*Kl+Kg])."""
+    labels int64 [nb*Kl+Kg] numpy).  ``solver``: "device" (csrc/merge_solve.cu; the one host read-back is the
+    number of labels) or "host" (the reference's arrangement: matrix to the host, C greedy pass there)."""
     nb, Np, Kl = W.shape
     Ng, Kg = spfn_labels.shape
     inverse = inverse_index(point_indices, Ng)
     sim = similarity_soft(spfn_labels, W, point_indices, inverse=inverse)
+    if solver == "device" and nb <= MAX_DEVICE_PATCHES:
+        labels_dev, weights, n_labels = solve_labels_device(sim, nb, Kg, Kl, threshold=threshold)
+        X_global, T_global = merge_normals_types(X, T, point_indices, spfn_normals, spfn_type, inverse=inverse)
+        L = int(n_labels.item())                                        # sizes W_fusion: the only synchronisation
+        W_fusion = fuse_patches(spfn_labels, W, point_indices, None, inverse=inverse,
+                                device_solution=(labels_dev, weights, L))
+        return W_fusion, X_global, T_global, labels_dev.cpu().numpy().astype(np.int64)
     labels = run_heuristic_solver(sim.cpu().numpy(), nb, Kg, Kl, threshold=threshold)      # host, as in the reference
     W_fusion = fuse_patches(spfn_labels, W, point_indices, labels, inverse=inverse)
     X_global, T_global = merge_normals_types(X, T, point_indices, spfn_normals, spfn_type, inverse=inverse)

@@ -250,6 +250,13 @@ CPFN_API int cpfn_gather_xyz(const float *xyz, const int32_t *idx, int B, int N,
 CPFN_API int cpfn_linear_rows(const float *x, const float *W, const float *bias, int rows, int cin,
                               int cout, int ldo, float *out, cpfn_stream_t stream);
 
+/* LocalSPFN input normalisation (Dataset/dataloaders.py:249-253): out[b, i] = (P[idx[b, i]] - mean_b) / max_i |P[idx[b, i]]
+ * - mean_b|, mean_b = the patch's mean point (fp64 accumulation in a fixed order, rounded to fp32: the result of a
+ * patch does not depend on the number of patches in the call).  points f32 [Ng,3], patch_idx int32 or int64 [nb,Np]
+ * -> out f32 [nb,Np,3]. */
+CPFN_API int cpfn_normalise_patches(const float *points, long long Ng, const void *patch_idx, int idx_is_int64,
+                                    int nb, int Np, float *out, cpfn_stream_t stream);
+
 /* Dropout keep-mask of F.dropout(x, p) for a channel-major x [B, C, N] (pn2_network.py:63, always on), as ONE BIT
  * per element instead of the fp32 mask tensor: bits[(b*N + n) * ceil(C/32) + c/32] bit c%32 = keep.  The random
  * stream is torch's own for that call: Philox4x32-10 keyed by `seed`, thread t of torch's launch (`torch_threads`
@@ -269,6 +276,16 @@ CPFN_API int cpfn_dropout_mask_bits(const unsigned long long *rng_state, int B, 
 CPFN_API int cpfn_spfn_post(const float *heads, long long rows, int ld, int x_off, int t_off, int n_types,
                             int w_off, int K, float *X, float *W, int32_t *inst, int32_t *type,
                             cpfn_stream_t stream);
+
+/* cpfn_spfn_post for the patch-sharded cascade: additionally writes the type logits as T_out
+ * [rows, n_types] (NULL to skip), and sends the X / W / T_out rows of local patch j (rows_per_patch rows each, a
+ * multiple of 256) to the slab of patch j * patch_stride + patch_offset of the destination arrays.  X, W and T_out
+ * may be PEER-MAPPED device pointers (the receive buffers of the rank that runs the merge, reached over NVLink): the
+ * kernel that produces the per-point outputs is then also the exchange step -- no separate all-gather.  inst / type
+ * stay in local row order.  rows_per_patch = 0: plain cpfn_spfn_post. */
+CPFN_API int cpfn_spfn_post_scatter(const float *heads, long long rows, int ld, int x_off, int t_off, int n_types,
+                                    int w_off, int K, float *X, float *W, float *T_out, int32_t *inst, int32_t *type,
+                                    int rows_per_patch, int patch_stride, int patch_offset, cpfn_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * Patch extraction: the k nearest high-resolution points of every seed.
@@ -318,6 +335,17 @@ CPFN_API int cpfn_merge_solve_host(const double *similarity, int64_t n_nodes, do
 /* The same for the float32 matrix similarity_soft returns (what the reference passes): no conversion, 32-bit sort keys. */
 CPFN_API int cpfn_merge_solve_host_f32(const float *similarity, int64_t n_nodes, float threshold,
                                        const int64_t *patch_id, int64_t *segment_id);
+
+/* The same solve on the DEVICE, straight from the similarity matrix cpfn_merge_similarity left there (f32 [M,M],
+ * M = nb*Kl + Kg <= 4096, nb + 1 <= 64 patches): pair keys -> radix sort -> one-CTA greedy pass -> label replacement
+ * of the empty slots and np.unique (merging_utils.py:35-44 + :17-33) without the device->host copy of the matrix and
+ * the host loop.  labels int32 [M] (consecutive, in np.unique's order), label_weight f32 [M] (entry l = 1 / (members
+ * of label l + 1e-10), what get_point_final divides by; 0 beyond the last label), n_labels int32 [1] (device),
+ * segments int32 [M] | NULL (heuristic_merging's raw segment ids, before the replacement). */
+CPFN_API size_t cpfn_merge_solve_workspace_bytes(int nb, int Kl, int Kg);
+CPFN_API int cpfn_merge_solve(const float *similarity, int nb, int Kl, int Kg, float threshold, int32_t *labels,
+                              float *label_weight, int32_t *n_labels, int32_t *segments, void *workspace,
+                              size_t workspace_bytes, cpfn_stream_t stream);
 
 /* Fused evaluation_localSPFN.py:103-111 + get_point_final (merging_utils.py:46-50): labels int32 [M] in
  * [0,L), label_weight f32 [L] = 1/(members+1e-10); out [Ng,L].  Points inside a patch drop the object block. */

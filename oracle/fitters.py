@@ -169,6 +169,19 @@ def compute_parameters(P, W, X, classes=("plane", "sphere", "cylinder", "cone"))
     return out
 
 
+def compute_parameters_f64(P, W, X, classes=("plane", "sphere", "cylinder", "cone")):
+    """The same algebra carried out in float64: the conditioning yardstick of the parity tests.  The distance of
+    the float32 restatement above (= the reference's own arithmetic) from this result says how much of a difference
+    on a given slot is rounding noise amplified by an ill-conditioned fit (a cylinder axis from near-parallel
+    normals ...) rather than a disagreement about the algorithm."""
+    global F
+    saved, F = F, np.float64
+    try:
+        return compute_parameters(np.asarray(P, np.float64), np.asarray(W, np.float64), np.asarray(X, np.float64), classes)
+    finally:
+        F = saved
+
+
 # --- point-to-primitive residuals (compute_residue_single of each fitter) ---------------------
 
 def _sqrt_safe(x):

@@ -93,28 +93,35 @@ def _param_err(got, ref):
     return err
 
 
+WELL_POSED = ("plane_normal", "plane_center", "sphere_center", "sphere_radius_squared")
+
+
 def test_fitted_parameters_at_bench_config(bench_forward):
-    """Network -> softmax -> fit, end to end.  A slot counts when the oracle's own answer is stable under the
-    MLP-path perturbation of the memberships (oracle fitters on the GPU's W / X vs on the oracle's W / X agree to
-    1e-3): ill-conditioned fits (a cone on a planar patch ...) amplify any input difference and pin nothing."""
+    """Network -> softmax -> fit, end to end, all 16 x 28 slots, all ten keys.
+      * against the all-oracle pipeline (oracle network + oracle fitters): 1e-3, the north star's bar for results
+        downstream of the bf16 / tf32 MLP path;
+      * against the fitters' oracle on the SAME memberships / normals: 1e-5 (its fp32 TLS bar) for the plane and
+        sphere keys outright.  The memberships of a randomly initialised network are near-uniform, which makes the
+        cylinder and cone fits on them ill conditioned (axis = smallest eigenvector of a nearly isotropic normal
+        scatter): there the yardstick is the reference arithmetic itself -- the float32 oracle's distance from the
+        same algebra in float64 -- and the GPU result must be no further from that float64 answer than twice what
+        the reference's own float32 arithmetic is (or 1e-5)."""
     eng, sd, P, out, ref = bench_forward
     got = {k: v.cpu().numpy() for k, v in out["parameters"].items()}
     Wg, Xg = out["W"].cpu().numpy(), out["X"].cpu().numpy()
     Xn, _, Wn = onet.spfn_postprocess(ref["heads"])
-    same_input = ofit.compute_parameters(P, Wg, Xg)            # oracle fitters on the GPU's memberships / normals
     all_oracle = ofit.compute_parameters(P, Wn, Xn)            # oracle network + oracle fitters
-    sens = _param_err(same_input, all_oracle)
-    e_same, e_all = _param_err(got, same_input), _param_err(got, all_oracle)
-    stable_frac = []
+    e_all = _param_err(got, all_oracle)
     for key in got:
-        stable = sens[key] < 1e-3
-        stable_frac.append(stable.mean())
-        assert stable.any(), key
-        assert e_all[key][stable].max() < 1e-3, (key, float(e_all[key][stable].max()))
-        tight = sens[key] < 1e-4                                # well conditioned: the fp32 TLS bar applies
-        assert tight.any(), key
-        assert e_same[key][tight].max() < 1e-5, (key, float(e_same[key][tight].max()))
-    assert np.mean(stable_frac) > 0.5, stable_frac             # the mask must not hollow the test out
+        assert e_all[key].max() < 1e-3, (key, float(e_all[key].max()))
+    same_input = ofit.compute_parameters(P, Wg, Xg)            # oracle fitters on the GPU's memberships / normals
+    exact = ofit.compute_parameters_f64(P, Wg, Xg)
+    e_same, e_gpu, e_ref = _param_err(got, same_input), _param_err(got, exact), _param_err(same_input, exact)
+    for key in got:
+        if key in WELL_POSED:
+            assert e_same[key].max() < 1e-5, (key, float(e_same[key].max()))
+        assert e_gpu[key].max() <= max(1e-5, 2 * e_ref[key].max()), (key, float(e_gpu[key].max()), float(e_ref[key].max()))
+        assert np.median(e_gpu[key]) <= max(1e-6, 2 * np.median(e_ref[key])), key
     packed = out["parameters_packed"].cpu().numpy()
     assert packed.size == 22 * 16 * 28 and np.isfinite(packed).all()
 

@@ -106,3 +106,66 @@ def test_full_size_against_dense_fp64(cuda_dev):
     Tw = num / den.clamp(min=1)[:, None]
     Tw[~covered] = ot[~covered].double()
     assert float((Tg.double() - Tw).abs().max()) <= 1e-5
+
+
+def _device_solve(sim_np, nb, Kg, Kl, dev, threshold=0):
+    sim = torch.from_numpy(np.ascontiguousarray(sim_np, dtype=np.float32)).to(dev)
+    labels, weights, n_labels, seg = merging_utils.solve_labels_device(sim, nb, Kg, Kl, threshold=threshold,
+                                                                       return_segments=True)
+    L = int(n_labels.item())
+    return labels.cpu().numpy().astype(np.int64), weights.cpu().numpy(), L, seg.cpu().numpy().astype(np.int64)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_device_solver_matches_reference_labels(name, cuda_dev):
+    """The on-device label solve (csrc/merge_solve.cu) against the labels of the UNMODIFIED reference
+    (tests/golden/ref_merging.npz) and the host C pass, from the same float32 similarity matrix."""
+    c, d = CASES[name], _dev(CASES[name], cuda_dev)
+    nb, Np, Kl = c["W"].shape
+    Kg = c["S"].shape[1]
+    sim = merging_utils.similarity_soft(d["S"], d["W"], d["idx"])
+    labels, weights, L, _ = _device_solve(sim.cpu().numpy(), nb, Kg, Kl, cuda_dev)
+    assert np.array_equal(labels, GOLD[name + "/labels"])
+    host = merging_utils.run_heuristic_solver(sim.cpu().numpy(), nb, Kg, Kl)
+    assert np.array_equal(labels, host) and L == host.max() + 1
+    counts = np.bincount(host, minlength=L).astype(np.float32)
+    assert np.array_equal(weights[:L], np.float32(1) / (counts + np.float32(1e-10))) and not weights[L:].any()
+    Wf, Xg, Tg, lab = merging_utils.merge_shape(d["W"], d["X"], d["T"], d["idx"], d["S"], d["obj_normals"], d["obj_types"])
+    Wh, Xh, Th, labh = merging_utils.merge_shape(d["W"], d["X"], d["T"], d["idx"], d["S"], d["obj_normals"],
+                                                 d["obj_types"], solver="host")
+    assert np.array_equal(lab, labh) and torch.equal(Wf, Wh) and torch.equal(Xg, Xh) and torch.equal(Tg, Th)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_device_solver_random_matrices(seed, cuda_dev):
+    """Random symmetric matrices with the structures that steer the greedy pass: many exact ties (quantised
+    values), a first arg-max inside one patch, empty slots (diagonal below the threshold), no pair at all, a
+    threshold above most entries -- against the literal repeated-argmax loop of the reference (oracle) and the
+    host pass; raw segment ids included."""
+    rng = np.random.RandomState(100 + seed)
+    nb, Kl, Kg = [(3, 4, 5), (7, 6, 7), (32, 21, 28), (1, 5, 4), (12, 3, 9), (63, 2, 3)][seed % 6]
+    M = nb * Kl + Kg
+    A = rng.rand(M, M).astype(np.float32)
+    if seed % 3 == 0:
+        A = np.round(A * 8) / 8                                   # ties everywhere
+    sim = ((A + A.T) * (rng.rand(M, M) < (0.3 if seed % 2 else 0.9))).astype(np.float32)
+    sim = np.maximum(sim, sim.T)
+    np.fill_diagonal(sim, rng.rand(M).astype(np.float32) * (rng.rand(M) < 0.8))     # some empty slots (diagonal 0)
+    thr = [0, 0, 0.5, 0, 1.5, 0][seed % 6]
+    if seed == 4:
+        sim[1, 2] = sim[2, 1] = 50.0                              # the first arg-max lies inside patch 0
+    if seed == 5:
+        sim[~np.eye(M, dtype=bool)] = 0.0                         # no pair above the threshold
+    labels, weights, L, seg = _device_solve(sim, nb, Kg, Kl, cuda_dev, threshold=thr)
+    host = merging_utils.run_heuristic_solver(sim, nb, Kg, Kl, threshold=thr)
+    assert np.array_equal(labels, host), (seed, np.flatnonzero(labels != host)[:10])
+    if M <= 200:                                                  # the literal loop is O(pairs x merges)
+        want = omerge.run_heuristic_solver(sim, nb, Kg, Kl, threshold=thr)
+        assert np.array_equal(labels, want)
+    idx = np.where(sim > np.float32(thr))
+    keep = idx[0] < idx[1]
+    pairs = np.stack([idx[0][keep], idx[1][keep]], axis=1).astype(np.int64)
+    patch_id = np.concatenate((np.repeat(np.arange(nb), Kl), nb * np.ones(Kg, dtype=int))).astype(np.int64)
+    if len(pairs):
+        seg_host = merging_utils.heuristic_merging(pairs, patch_id, sim[pairs[:, 0], pairs[:, 1]].astype(np.float64))
+        assert np.array_equal(seg, seg_host)
