@@ -26,6 +26,10 @@ SIGNATURES = {
     "cpfn_error_string": (ctypes.c_char_p, [c_int]),
     "cpfn_last_cuda_error": (ctypes.c_char_p, []),
     "cpfn_sm_count": (c_int, []),
+    "cpfn_debug_fps_profile": (c_int, [c_void_p]),
+    "cpfn_fps_rounds_supported": (c_int, [c_int, c_int]),
+    "cpfn_furthest_point_sampling_rounds": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                                    c_size_t, c_size_t, c_void_p]),
     "cpfn_fps_workspace_bytes": (c_size_t, [c_int, c_int]),
     "cpfn_furthest_point_sampling": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
                                              c_size_t, c_void_p]),
@@ -57,6 +61,7 @@ SIGNATURES = {
     "cpfn_linear_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "cpfn_gather_xyz": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "cpfn_normalise_patches": (c_int, [c_void_p, ctypes.c_longlong, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "cpfn_zero_fill": (c_int, [c_void_p, c_size_t, c_void_p]),
     "cpfn_rng_set": (c_int, [c_void_p, ctypes.c_ulonglong, ctypes.c_ulonglong, c_void_p]),
     "cpfn_dropout_mask_bits": (c_int, [c_void_p, c_int, c_int, c_int, c_float, ctypes.c_longlong, c_void_p, c_void_p]),
     "cpfn_spfn_post": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
@@ -92,6 +97,8 @@ SIGNATURES = {
     "cpfn_ball_query_grid_build": (c_int, [c_void_p, c_int, c_int, c_float, c_void_p, c_size_t, c_void_p]),
     "cpfn_ball_query_grid_query": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p,
                                            c_size_t, c_void_p]),
+    "cpfn_ball_query_grid_query_range": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int,
+                                                 c_void_p, c_void_p, c_size_t, c_void_p]),
     "cpfn_furthest_point_sampling_xyz": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
                                                  c_void_p]),
     "cpfn_mlp_packed_bytes": (c_size_t, [c_int, c_int]),

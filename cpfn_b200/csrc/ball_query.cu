@@ -208,7 +208,7 @@ bq_grid_build_kernel(const float *__restrict__ xyz, int N, float radius, GridHea
 }
 
 __global__ void __launch_bounds__(kGridQueryWarps * 32)
-bq_grid_query_kernel(const float *__restrict__ new_xyz, int N, int S, float radius, int nsample,
+bq_grid_query_kernel(const float *__restrict__ new_xyz, int N, int S, int s_begin, int s_end, float radius, int nsample,
                      const GridHeader *__restrict__ hdr, const int *__restrict__ cell_start,
                      const float4 *__restrict__ sorted, int32_t *__restrict__ idx) {
   extern __shared__ unsigned int s_bits[];             // [kGridQueryWarps][words]
@@ -219,7 +219,7 @@ bq_grid_query_kernel(const float *__restrict__ new_xyz, int N, int S, float radi
   const int *cs = cell_start + static_cast<size_t>(b) * (kGridMaxCells + 1);
   const float4 *pts = sorted + static_cast<size_t>(b) * N;
   const float r2 = __fmul_rn(radius, radius);
-  for (int q = blockIdx.x * kGridQueryWarps + warp; q < S; q += gridDim.x * kGridQueryWarps) {
+  for (int q = s_begin + blockIdx.x * kGridQueryWarps + warp; q < s_end; q += gridDim.x * kGridQueryWarps) {
     const float *c = new_xyz + (static_cast<size_t>(b) * S + q) * 3;
     const float qx = __ldg(c), qy = __ldg(c + 1), qz = __ldg(c + 2);
     for (int i = lane; i < words; i += 32) bits[i] = 0u;
@@ -358,14 +358,13 @@ extern "C" int cpfn_ball_query_grid_build(const float *xyz, int B, int N, float 
   return check_launch();
 }
 
-extern "C" int cpfn_ball_query_grid_query(const float *new_xyz, const float *xyz, int B, int N, int S, float radius,
-                                          int nsample, int32_t *idx, void *workspace, size_t workspace_bytes,
-                                          cpfn_stream_t stream) {
+extern "C" int cpfn_ball_query_grid_query_range(const float *new_xyz, const float *xyz, int B, int N, int S,
+                                                int s_begin, int s_count, float radius, int nsample, int32_t *idx,
+                                                void *workspace, size_t workspace_bytes, cpfn_stream_t stream) {
   using namespace cpfn;
-  if (B < 0 || N < 0 || S < 0 || nsample < 0) return CPFN_EINVAL;
-  if (B == 0 || S == 0 || nsample == 0) return CPFN_OK;
-  if (!grid_applies(B, N, radius))                                           // small / huge clouds: the scan kernel
-    return cpfn_ball_query(new_xyz, xyz, B, N, S, radius, nsample, idx, stream);
+  if (B < 0 || N < 0 || S < 0 || nsample < 0 || s_begin < 0 || s_count < 0 || s_begin + s_count > S) return CPFN_EINVAL;
+  if (B == 0 || s_count == 0 || nsample == 0) return CPFN_OK;
+  if (!grid_applies(B, N, radius)) return CPFN_EINVAL;                       // ranges exist for the grid kernel only
   if (!new_xyz || !idx) return CPFN_EINVAL;
   if (!workspace || workspace_bytes < cpfn_ball_query_grid_workspace_bytes(B, N)) return CPFN_EWORKSPACE;
   cudaStream_t st = as_stream(stream);
@@ -375,12 +374,24 @@ extern "C" int cpfn_ball_query_grid_query(const float *new_xyz, const float *xyz
     CPFN_CUDA_TRY(cudaFuncSetAttribute(bq_grid_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem)));
   const int sms = sm_count() > 0 ? sm_count() : 148;
-  int gx = (S + kGridQueryWarps - 1) / kGridQueryWarps;
+  int gx = (s_count + kGridQueryWarps - 1) / kGridQueryWarps;
   const int cap = (4 * sms + B - 1) / B;
   if (gx > cap) gx = cap < 1 ? 1 : cap;
-  bq_grid_query_kernel<<<dim3(gx, B), kGridQueryWarps * 32, smem, st>>>(new_xyz, N, S, radius, nsample, g.hdr,
-                                                                        g.cell_start, g.sorted, idx);
+  bq_grid_query_kernel<<<dim3(gx, B), kGridQueryWarps * 32, smem, st>>>(new_xyz, N, S, s_begin, s_begin + s_count, radius,
+                                                                        nsample, g.hdr, g.cell_start, g.sorted, idx);
   return check_launch();
+}
+
+extern "C" int cpfn_ball_query_grid_query(const float *new_xyz, const float *xyz, int B, int N, int S, float radius,
+                                          int nsample, int32_t *idx, void *workspace, size_t workspace_bytes,
+                                          cpfn_stream_t stream) {
+  using namespace cpfn;
+  if (B < 0 || N < 0 || S < 0 || nsample < 0) return CPFN_EINVAL;
+  if (B == 0 || S == 0 || nsample == 0) return CPFN_OK;
+  if (!grid_applies(B, N, radius))                                           // small / huge clouds: the scan kernel
+    return cpfn_ball_query(new_xyz, xyz, B, N, S, radius, nsample, idx, stream);
+  return cpfn_ball_query_grid_query_range(new_xyz, xyz, B, N, S, 0, S, radius, nsample, idx, workspace, workspace_bytes,
+                                          stream);
 }
 
 extern "C" int cpfn_ball_query_grid(const float *new_xyz, const float *xyz, int B, int N, int S, float radius,

@@ -65,10 +65,43 @@ __device__ __forceinline__ uint32_t block_argmax(uint32_t hi, uint32_t lo,
   return L;
 }
 
-// Stage xyz [N,3] (AoS, global) into shared SoA sx|sy|sz with pitch Np.
+// Stage xyz [N,3] (AoS, global) into shared SoA sx|sy|sz with pitch Np.  16-byte loads, eight in flight per thread
+// (a cluster CTA stages its whole 96 KB cloud before the first round; with scalar loads that was ~7 us of every
+// launch).
 __device__ __forceinline__ void stage_soa(const float *__restrict__ p, int N, int Np,
                                           float *s) {
-  for (int f = threadIdx.x; f < 3 * N; f += blockDim.x) {
+  const int total = 3 * N;
+  if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+    const int nv = total >> 2;
+    const float4 *pv = reinterpret_cast<const float4 *>(p);
+    for (int v0 = threadIdx.x; v0 < nv; v0 += 8 * blockDim.x) {
+      float4 q[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int v = v0 + u * blockDim.x;
+        q[u] = v < nv ? __ldg(pv + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int v = v0 + u * blockDim.x;
+        if (v < nv) {
+          const int f = 4 * v;
+          const float e[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const int k = (f + w) / 3, c = (f + w) - 3 * k;
+            s[c * Np + k] = e[w];
+          }
+        }
+      }
+    }
+    for (int f = (nv << 2) + threadIdx.x; f < total; f += blockDim.x) {
+      const int k = f / 3, c = f - 3 * k;
+      s[c * Np + k] = __ldg(p + f);
+    }
+    return;
+  }
+  for (int f = threadIdx.x; f < total; f += blockDim.x) {
     const int k = f / 3, c = f - 3 * k;
     s[c * Np + k] = __ldg(p + f);
   }
@@ -189,6 +222,46 @@ __device__ __forceinline__ void fps_mbar_wait_cluster(unsigned long long *bar, u
       "}\n" ::"r"(fps_smem_u32(bar)), "r"(parity) : "memory");
 }
 
+// Polling exchange (no mbarrier): a key carries a 2-bit round tag in bits 30-31 of its low word (the rank needs 29
+// bits and its complement always has bit 29 set), the sender stores it into the peer's shared memory with a plain
+// DSMEM store and the receiver spins on its OWN shared memory until every slot shows the tag of the round.  The
+// mbarrier form costs one complete_tx transaction per 8-byte message at the receiver (32-64 per round), which is
+// what bounded the round time.
+__device__ __forceinline__ void st_cluster_u64(uint32_t remote_addr, unsigned long long v) {
+  asm volatile("st.relaxed.cluster.shared::cluster.b64 [%0], %1;" ::"r"(remote_addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_volatile_shared_u64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.shared::cta.b64 %0, [%1];" : "=l"(v) : "r"(fps_smem_u32(p)) : "memory");
+  return v;
+}
+// Key low word of the cluster kernels (N <= 16384, reference block T = 512): bits 14-27 = the complement of the
+// 14-bit reference rank (bitrev9(k mod 512) << 5 | k >> 9: larger = wins ties), bits 0-13 = k itself, so the
+// arg-max over (distance, code) is the reference's winner and its index needs no decoding.  Never 0 for a point.
+__device__ __forceinline__ uint32_t fps_code(uint32_t k) {
+  const uint32_t rank14 = ((__brev(k & 511u) >> 23) << 5) | (k >> 9);
+  return ((~rank14 & 0x3FFFu) << 14) | (k & 0x3FFFu);
+}
+__device__ __forceinline__ uint32_t fps_tag(int j) { return ((static_cast<uint32_t>(j - 1) >> 1) & 1u) + 1u; }
+
+// Waits until this lane's (up to two) slots carry `tag`, returns the larger key with the tag stripped.
+__device__ __forceinline__ unsigned long long fps_poll_keys(const unsigned long long *slots, int lane, int nkeys,
+                                                            uint32_t tag) {
+  unsigned long long v0 = 0ull, v1 = 0ull;
+  while (true) {
+    bool ok = true;
+    if (lane < nkeys) { v0 = ld_volatile_shared_u64(slots + lane); ok = ((static_cast<uint32_t>(v0) >> 30) == tag); }
+    if (lane + 32 < nkeys) { v1 = ld_volatile_shared_u64(slots + lane + 32); ok = ok && ((static_cast<uint32_t>(v1) >> 30) == tag); }
+    if (__all_sync(0xffffffffu, ok)) break;
+  }
+  const unsigned long long v = v0 > v1 ? v0 : v1;
+  return v & 0xFFFFFFFF3FFFFFFFull;
+}
+
+// Round-phase profile of fps_cluster_kernel (cycles summed over the rounds by thread 0 of CTA 0 when the kernel is
+// built into its PROFILE form): read back with cpfn_debug_fps_profile.
+__device__ long long g_fps_prof[8];
+
 constexpr int kFpsClusterThreads = 256;
 constexpr int kFpsClusterWarps = kFpsClusterThreads / 32;
 
@@ -196,10 +269,10 @@ constexpr int kFpsClusterWarps = kFpsClusterThreads / 32;
 // point i is (bitrev9(k mod 512) << 20) | (k >> 9): even i share k mod 512 = t, odd i have t + 256 whose
 // bit-reversal is one larger, so scanning the even i first and then the odd i visits a thread's points
 // in increasing reference rank and the strict '>' keeps the right one on ties.
-template <int PPT>
+template <int PPT, bool POLL, bool PROFILE = false>
 __global__ void __launch_bounds__(kFpsClusterThreads, 1)
 fps_cluster_kernel(const float *__restrict__ xyz, float *__restrict__ new_xyz, int N, int m, int log2T, int Nc,
-                   int32_t *__restrict__ idx) {
+                   int32_t *__restrict__ idx, int j_begin, int j_end, float *__restrict__ state) {
   extern __shared__ float s_xyz[];
   __shared__ __align__(8) unsigned long long xslot[2][8 * kFpsClusterWarps];   // [parity][sender CTA * 8 + sender warp]
   __shared__ __align__(8) unsigned long long xbar[2];
@@ -223,6 +296,7 @@ fps_cluster_kernel(const float *__restrict__ xyz, float *__restrict__ new_xyz, i
   cluster_sync_all();                    // all barriers exist before any peer can complete_tx on them
 
   float px[PPT], py[PPT], pz[PPT], tmp[PPT];
+  uint32_t code[PPT];
   const int k0 = static_cast<int>(r) * Nc + t;
 #pragma unroll
   for (int i = 0; i < PPT; ++i) {
@@ -235,6 +309,10 @@ fps_cluster_kernel(const float *__restrict__ xyz, float *__restrict__ new_xyz, i
     }
     px[i] = x; py[i] = y; pz[i] = z;
     tmp[i] = live ? 1e10f : -1.0f;
+    // resumed launch (rounds j_begin .. j_end-1 of a sampling split over several launches): the running minima of
+    // the rounds before come back from `state`
+    if (j_begin > 1 && live) tmp[i] = state[static_cast<size_t>(cloud) * N + k];
+    code[i] = fps_code(static_cast<uint32_t>(k));      // tie-break order and the index itself, computed once
   }
   // lane l < C of every warp delivers the warp's key to CTA l: slot [parity][r*8 + warp], barrier [parity]
   uint32_t my_slot0 = 0, my_slot1 = 0, my_bar0 = 0, my_bar1 = 0;
@@ -246,53 +324,91 @@ fps_cluster_kernel(const float *__restrict__ xyz, float *__restrict__ new_xyz, i
   }
   const int nkeys = static_cast<int>(C) * kFpsClusterWarps;      // <= 64: two per lane
 
-  if (r == 0 && t == 0) out[0] = 0;
-  float cx = sx[0], cy = sy[0], cz = sz[0];
   float *nx = (new_xyz && r == 0 && t == 0) ? new_xyz + static_cast<size_t>(cloud) * m * 3 : nullptr;
-  if (nx) { nx[0] = cx; nx[1] = cy; nx[2] = cz; }
-  for (int j = 1; j < m; ++j) {
+  float cx, cy, cz;
+  if (j_begin <= 1) {
+    if (r == 0 && t == 0) out[0] = 0;
+    cx = sx[0]; cy = sy[0]; cz = sz[0];
+    if (nx) { nx[0] = cx; nx[1] = cy; nx[2] = cz; }
+  } else {
+    const int last = __ldg(out + j_begin - 1);             // written by the launch before this one
+    cx = sx[last]; cy = sy[last]; cz = sz[last];
+  }
+  long long pt[6] = {0, 0, 0, 0, 0, 0}, c0 = 0;
+#define FPS_MARK(i) if (PROFILE) { const long long c1 = clock64(); pt[i] += c1 - c0; c0 = c1; }
+  if (PROFILE) c0 = clock64();
+  for (int j = max(1, j_begin); j < j_end; ++j) {
     float best = -1.0f;
-    int bi = 0;
+    uint32_t bc = 0u;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
 #pragma unroll
       for (int i = h; i < PPT; i += 2) {     // even i first, then odd i: increasing reference rank
         const float d2 = fminf(sqdist3(px[i], py[i], pz[i], cx, cy, cz), tmp[i]);
         tmp[i] = d2;
-        if (d2 > best) { best = d2; bi = i; }
+        if (d2 > best) { best = d2; bc = code[i]; }
       }
     }
     uint32_t hi = 0u, lo = 0u;
     if (best >= 0.0f) {
       hi = __float_as_uint(best);
-      lo = ~fps_rank(static_cast<uint32_t>(k0 + bi * NT), log2T);
+      lo = bc;
     }
+    FPS_MARK(0)                                            // distance update
     const uint32_t Mw = __reduce_max_sync(0xffffffffu, hi);
     const uint32_t Lw = __reduce_max_sync(0xffffffffu, hi == Mw ? lo : 0u);
-    const unsigned long long key = (static_cast<unsigned long long>(Mw) << 32) | Lw;
     const int par = j & 1;
-    if (t == 0) fps_mbar_expect_tx(&xbar[par], 8u * nkeys);
-    if (lane < static_cast<int>(C)) st_async_u64(par ? my_slot1 : my_slot0, key, par ? my_bar1 : my_bar0);
-    fps_mbar_wait_cluster(&xbar[par], ((j - 1) >> 1) & 1);   // (j-1)/2-th use of this barrier
-    const unsigned long long v0 = lane < nkeys ? xslot[par][lane] : 0ull;
-    const unsigned long long v1 = lane + 32 < nkeys ? xslot[par][lane + 32] : 0ull;
-    const unsigned long long v = v0 > v1 ? v0 : v1;
+    unsigned long long v;
+    FPS_MARK(1)                                            // warp arg-max (2 REDUX)
+    if (POLL) {
+      const uint32_t tag = fps_tag(j);
+      const unsigned long long key = (static_cast<unsigned long long>(Mw) << 32) | Lw | (tag << 30);
+      if (lane < static_cast<int>(C)) st_cluster_u64(par ? my_slot1 : my_slot0, key);
+      FPS_MARK(2)                                          // push
+      v = fps_poll_keys(&xslot[par][0], lane, nkeys, tag);
+      FPS_MARK(3)                                          // wait for all keys
+    } else {
+      const unsigned long long key = (static_cast<unsigned long long>(Mw) << 32) | Lw;
+      if (t == 0) fps_mbar_expect_tx(&xbar[par], 8u * nkeys);
+      if (lane < static_cast<int>(C)) st_async_u64(par ? my_slot1 : my_slot0, key, par ? my_bar1 : my_bar0);
+      fps_mbar_wait_cluster(&xbar[par], ((j - 1) >> 1) & 1);   // (j-1)/2-th use of this barrier
+      const unsigned long long v0 = lane < nkeys ? xslot[par][lane] : 0ull;
+      const unsigned long long v1 = lane + 32 < nkeys ? xslot[par][lane + 32] : 0ull;
+      v = v0 > v1 ? v0 : v1;
+    }
     const uint32_t h2 = static_cast<uint32_t>(v >> 32), l2 = static_cast<uint32_t>(v);
     const uint32_t M = __reduce_max_sync(0xffffffffu, h2);
     const uint32_t L = __reduce_max_sync(0xffffffffu, h2 == M ? l2 : 0u);
-    const int old = L ? static_cast<int>(fps_unrank(~L, log2T)) : 0;
+    const int old = static_cast<int>(L & 0x3FFFu);          // the low 14 bits of a code are the point index (0 if none)
+    FPS_MARK(4)                                            // cluster arg-max (2 REDUX) + unrank
     if (r == 0 && t == 0) out[j] = old;
     cx = sx[old]; cy = sy[old]; cz = sz[old];
     if (nx) { nx[3 * j] = cx; nx[3 * j + 1] = cy; nx[3 * j + 2] = cz; }
+    if (PROFILE) { if (cx + cy + cz == 12345.f) pt[5] += 1; }
+    FPS_MARK(5)                                            // centroid look-up
   }
+#undef FPS_MARK
+  if (state != nullptr && j_end < m) {                     // more rounds follow in another launch
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+      const int k = k0 + i * NT;
+      if (k < N && i * NT + t < Nc) state[static_cast<size_t>(cloud) * N + k] = tmp[i];
+    }
+  }
+  if (PROFILE && blockIdx.x == 0 && t == 0)
+    for (int i = 0; i < 6; ++i) g_fps_prof[i] = pt[i];
   cluster_sync_all();                    // nobody leaves while a peer may still write into its shared memory
 }
 
 template <int PPT>
 int launch_cluster(const float *xyz, float *new_xyz, int B, int N, int m, int log2T, int C, int Nc, int32_t *idx,
-                   cudaStream_t st) {
-  const size_t smem = 3u * static_cast<size_t>((N + 31) & ~31) * sizeof(float);
-  auto kern = fps_cluster_kernel<PPT>;
+                   cudaStream_t st, int j_begin = 0, int j_end = -1, float *state = nullptr, size_t smem_floor = 0) {
+  size_t smem = 3u * static_cast<size_t>((N + 31) & ~31) * sizeof(float);
+  if (smem < smem_floor) smem = smem_floor;      // keeps other kernels' CTAs off the sampling SMs (see ..._rounds)
+  if (j_end < 0) j_end = m;
+  const char *poll_env = getenv("CPFN_FPS_POLL");
+  auto kern = (poll_env && poll_env[0] == '0') ? fps_cluster_kernel<PPT, false> : fps_cluster_kernel<PPT, true>;
+  if (getenv("CPFN_FPS_PROFILE") != nullptr) kern = fps_cluster_kernel<PPT, true, true>;
   CPFN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(B) * C);
@@ -306,7 +422,7 @@ int launch_cluster(const float *xyz, float *new_xyz, int B, int N, int m, int lo
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CPFN_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, xyz, new_xyz, N, m, log2T, Nc, idx));
+  CPFN_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, xyz, new_xyz, N, m, log2T, Nc, idx, j_begin, j_end, state));
   return check_launch();
 }
 
@@ -373,9 +489,49 @@ int launch_cta(const float *xyz, float *new_xyz, int B, int N, int m, int log2T,
 }  // namespace
 }  // namespace cpfn
 
+extern "C" int cpfn_debug_fps_profile(long long *cycles6) {
+  if (!cycles6) return CPFN_EINVAL;
+  CPFN_CUDA_TRY(cudaMemcpyFromSymbol(cycles6, cpfn::g_fps_prof, 6 * sizeof(long long)));
+  return CPFN_OK;
+}
+
 extern "C" size_t cpfn_fps_workspace_bytes(int B, int N) {
   if (B <= 0 || N <= cpfn::kMaxSmemN) return 0;
   return static_cast<size_t>(B) * static_cast<size_t>(N) * sizeof(float);
+}
+
+extern "C" int cpfn_fps_rounds_supported(int B, int N) {
+  using namespace cpfn;
+  if (B <= 0 || N < 2048 || N > kMaxSmemN || (1 << ref_log2_threads(N)) != 512) return 0;
+  const int sms = sm_count() > 0 ? sm_count() : 148;
+  int C = 8;
+  while (C > 1 && N / C < 2048) C >>= 1;
+  while (C > 1 && static_cast<long long>(B) * C > sms) C >>= 1;
+  return C > 1 ? 1 : 0;
+}
+
+extern "C" int cpfn_furthest_point_sampling_rounds(const float *xyz, int B, int N, int nsamples, int j_begin, int j_end,
+                                                   int32_t *idx, float *new_xyz, float *state, size_t state_bytes,
+                                                   size_t smem_floor_bytes, cpfn_stream_t stream) {
+  using namespace cpfn;
+  if (B <= 0 || nsamples <= 0 || j_begin < 0 || j_end > nsamples || j_begin >= j_end || !xyz || !idx) return CPFN_EINVAL;
+  if (!cpfn_fps_rounds_supported(B, N)) return CPFN_EINVAL;
+  if ((j_end < nsamples || j_begin > 0) && (!state || state_bytes < sizeof(float) * static_cast<size_t>(B) * N))
+    return CPFN_EWORKSPACE;
+  if (smem_floor_bytes > 200u * 1024u) return CPFN_EINVAL;
+  const int sms = sm_count() > 0 ? sm_count() : 148;
+  int C = 8;
+  while (C > 1 && N / C < 2048) C >>= 1;
+  while (C > 1 && static_cast<long long>(B) * C > sms) C >>= 1;
+  const int log2T = ref_log2_threads(N);
+  const int Nc = ((N + C - 1) / C + 511) / 512 * 512;
+  const int ppt = Nc / 256;
+  cudaStream_t st = as_stream(stream);
+  if (ppt <= 2) return launch_cluster<2>(xyz, new_xyz, B, N, nsamples, log2T, C, Nc, idx, st, j_begin, j_end, state, smem_floor_bytes);
+  if (ppt <= 4) return launch_cluster<4>(xyz, new_xyz, B, N, nsamples, log2T, C, Nc, idx, st, j_begin, j_end, state, smem_floor_bytes);
+  if (ppt <= 8) return launch_cluster<8>(xyz, new_xyz, B, N, nsamples, log2T, C, Nc, idx, st, j_begin, j_end, state, smem_floor_bytes);
+  if (ppt <= 16) return launch_cluster<16>(xyz, new_xyz, B, N, nsamples, log2T, C, Nc, idx, st, j_begin, j_end, state, smem_floor_bytes);
+  return CPFN_EINVAL;
 }
 
 extern "C" int cpfn_furthest_point_sampling(const float *xyz, int B, int N, int nsamples,

@@ -346,6 +346,14 @@ extern "C" int cpfn_normalise_patches(const float *points, long long Ng, const v
   return check_launch();
 }
 
+extern "C" int cpfn_zero_fill(void *dst, size_t bytes, cpfn_stream_t stream) {
+  using namespace cpfn;
+  if (bytes == 0) return CPFN_OK;
+  if (!dst) return CPFN_EINVAL;
+  CPFN_CUDA_TRY(cudaMemsetAsync(dst, 0, bytes, as_stream(stream)));
+  return CPFN_OK;
+}
+
 extern "C" int cpfn_rng_set(unsigned long long *rng_state, unsigned long long seed, unsigned long long offset,
                             cpfn_stream_t stream) {
   using namespace cpfn;

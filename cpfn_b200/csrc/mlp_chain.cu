@@ -75,8 +75,19 @@ struct ChainP {
   int out_mode; float *out; int ldo, pool_g;
   const float *l0_w, *l0_b; int l0_cout;   // GROUP mode without features: first layer (3 -> l0_cout) on CUDA cores
   const float *in_bias;                    // INTERP mode: relu(interpolated + in_bias) enters layer 0
+  int win_cols, win_off;                   // column window: win_cols columns of every cloud, from column win_off (0: all)
   int act_bytes0, act_bytes1, nstage, tmem_cols;
 };
+
+// First column of tile `tile`.  With a column window the launch covers columns [win_off, win_off + win_cols) of every
+// cloud only (tiles never straddle a window): tile t is the t-th tile of that sub-range, at its real column.
+template <int NT>
+__device__ __forceinline__ long long tile_col0(const ChainP &p, int tile) {
+  const long long v = static_cast<long long>(tile) * NT;
+  if (p.win_cols == 0) return v;
+  const long long cloud = v / p.win_cols;
+  return cloud * p.cols_per_cloud + p.win_off + (v - cloud * p.win_cols);
+}
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -91,16 +102,19 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// try_wait parks the thread in hardware until the phase completes or the suspend-time hint expires; with the default
+// (short) hint the producer, the MMA thread and 256 epilogue threads re-issue it continuously and took ~24 % of all
+// issue slots of the chain kernels (ncu source counters, round 1).
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
       ".reg .pred P1;\n\t"
       "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
       "@P1 bra DONE;\n\t"
       "bra WAIT_LOOP;\n\t"
       "DONE:\n\t"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -136,6 +150,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void st_shared_b32(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
@@ -422,7 +444,7 @@ mlp_chain_kernel(const __grid_constant__ ChainP p) {
     constexpr int HC = NT / 2;                        // columns per worker warp
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-      const long long col0 = static_cast<long long>(tile) * NT;
+      const long long col0 = tile_col0<NT>(p, tile);
       const long long cloud = col0 / p.cols_per_cloud;
       const long long n_in_cloud = col0 - cloud * p.cols_per_cloud;
       load_tile<NT, 8>(p, smem_u32(act0), col0, w8, lane, s_arow, s_brow, s_w, 1);
@@ -640,7 +662,7 @@ mlp_chain_pm1_kernel(const __grid_constant__ ChainP p) {
     const int r7 = row & 7;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-      const long long col0 = static_cast<long long>(tile) * NT;
+      const long long col0 = tile_col0<NT>(p, tile);
       const long long col = col0 + row;
       const bool row_ok = col < p.cols;
       // thread = point: the cloud of THIS row (a tile may straddle two clouds when N is not a multiple of 128)
@@ -677,15 +699,17 @@ mlp_chain_pm1_kernel(const __grid_constant__ ChainP p) {
             for (int cb = half ? split : 0; cb < (half ? nch : split); cb += 16) {
               const int ch0 = chunk0 + cb;
               uint32_t r[16];
+              float4 b4[4];                            // the bias loads are in flight while the accumulators arrive
+#pragma unroll
+              for (int i4 = 0; i4 < 4; ++i4) b4[i4] = __ldg(reinterpret_cast<const float4 *>(bias_base + ch0) + i4);
               tmem_ld16(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + m * 128 + cb, r);
               float v[16];
 #pragma unroll
               for (int i4 = 0; i4 < 4; ++i4) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bias_base + ch0) + i4);
-                v[i4 * 4] = __uint_as_float(r[i4 * 4]) + b4.x;
-                v[i4 * 4 + 1] = __uint_as_float(r[i4 * 4 + 1]) + b4.y;
-                v[i4 * 4 + 2] = __uint_as_float(r[i4 * 4 + 2]) + b4.z;
-                v[i4 * 4 + 3] = __uint_as_float(r[i4 * 4 + 3]) + b4.w;
+                v[i4 * 4] = __uint_as_float(r[i4 * 4]) + b4[i4].x;
+                v[i4 * 4 + 1] = __uint_as_float(r[i4 * 4 + 1]) + b4[i4].y;
+                v[i4 * 4 + 2] = __uint_as_float(r[i4 * 4 + 2]) + b4[i4].z;
+                v[i4 * 4 + 3] = __uint_as_float(r[i4 * 4 + 3]) + b4[i4].w;
               }
               if (L.relu) {
 #pragma unroll
@@ -866,7 +890,7 @@ mlp_chain_pm_kernel(const __grid_constant__ ChainP p) {
     for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
       const int tile = 2 * pair + g;
       if (tile >= p.n_tiles) continue;
-      const long long col0 = static_cast<long long>(tile) * NT;
+      const long long col0 = tile_col0<NT>(p, tile);
       const long long col = col0 + row;
       const bool row_ok = col < p.cols;
       // thread = point: the cloud of THIS row (a tile may straddle two clouds when N is not a multiple of 128)
@@ -895,15 +919,17 @@ mlp_chain_pm_kernel(const __grid_constant__ ChainP p) {
 #pragma unroll 1
         for (int ch0 = 0; ch0 < cout16; ch0 += 16) {
           uint32_t r[16];
+          float4 b4[4];                                // the bias loads are in flight while the accumulators arrive
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4) b4[i4] = __ldg(reinterpret_cast<const float4 *>(bias_base + ch0) + i4);
           tmem_ld16(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + g * sub_cols + ch0, r);
           float v[16];
 #pragma unroll
           for (int i4 = 0; i4 < 4; ++i4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bias_base + ch0) + i4);
-            v[i4 * 4] = __uint_as_float(r[i4 * 4]) + b4.x;
-            v[i4 * 4 + 1] = __uint_as_float(r[i4 * 4 + 1]) + b4.y;
-            v[i4 * 4 + 2] = __uint_as_float(r[i4 * 4 + 2]) + b4.z;
-            v[i4 * 4 + 3] = __uint_as_float(r[i4 * 4 + 3]) + b4.w;
+            v[i4 * 4] = __uint_as_float(r[i4 * 4]) + b4[i4].x;
+            v[i4 * 4 + 1] = __uint_as_float(r[i4 * 4 + 1]) + b4[i4].y;
+            v[i4 * 4 + 2] = __uint_as_float(r[i4 * 4 + 2]) + b4[i4].z;
+            v[i4 * 4 + 3] = __uint_as_float(r[i4 * 4 + 3]) + b4[i4].w;
           }
           if (L.relu) {
 #pragma unroll
@@ -1011,6 +1037,17 @@ int launch_chain(const cpfn_mlp_chain_t *c, cudaStream_t st) {
   p.in_mode = c->in_mode; p.B = c->B; p.cols_per_cloud = c->cols_per_cloud;
   p.cols = static_cast<long long>(c->B) * c->cols_per_cloud;
   p.n_tiles = static_cast<int>((p.cols + NT - 1) / NT);
+  p.win_cols = 0; p.win_off = 0;
+  if (c->win_cols > 0) {
+    // a window must be made of whole tiles and whole pooling groups, inside the cloud; pooled outputs are merged
+    // with atomics into a buffer the CALLER zero-fills once (several windows of one output run as separate launches)
+    if ((c->win_cols % NT) != 0 || (c->win_off % NT) != 0 || c->win_off < 0 || c->win_off + c->win_cols > c->cols_per_cloud ||
+        (c->out_mode == CPFN_MLP_OUT_POOL && (!c->out_prezeroed || (c->win_cols % c->pool_g) != 0 || (c->win_off % c->pool_g) != 0)) ||
+        c->split_cout)
+      return CPFN_EINVAL;
+    p.win_cols = c->win_cols; p.win_off = c->win_off;
+    p.n_tiles = static_cast<int>(static_cast<long long>(c->B) * c->win_cols / NT);
+  }
   p.a_src = c->a_src; p.a_ch = c->a_ch; p.a_rows = c->a_rows;
   p.idx = c->idx; p.xyz = c->xyz; p.centers = c->centers; p.group_k = c->group_k;
   p.b_src = c->b_src; p.b_ch = c->b_ch; p.b_rows = c->b_rows; p.nn_w = c->nn_w;
@@ -1085,7 +1122,8 @@ int launch_chain(const cpfn_mlp_chain_t *c, cudaStream_t st) {
   CPFN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const int sms = sm_count() > 0 ? sm_count() : 148;
   const int units = (NT == 128 && two_sub) ? (p.n_tiles + 1) / 2 : p.n_tiles;   // the ping-pong kernel takes tile pairs
-  const int grid = units < per_sm * sms ? units : per_sm * sms;
+  int grid = units < per_sm * sms ? units : per_sm * sms;
+  if (c->max_ctas > 0 && grid > c->max_ctas) grid = c->max_ctas;      // caller shares the GPU with another kernel
   if (grid <= 0) return CPFN_OK;
   if (atomic_pool && !c->out_prezeroed)
     CPFN_CUDA_TRY(cudaMemsetAsync(c->out, 0, sizeof(float) * static_cast<size_t>(p.cols / c->pool_g) * c->ldo, st));

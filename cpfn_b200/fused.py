@@ -41,7 +41,8 @@ class _Chain(ctypes.Structure):
                 ("out_mode", ctypes.c_int32), ("out", ctypes.c_void_p), ("ldo", ctypes.c_int32),
                 ("pool_g", ctypes.c_int32), ("split_cout", ctypes.c_int32),
                 ("l0_w", ctypes.c_void_p), ("l0_b", ctypes.c_void_p), ("l0_cout", ctypes.c_int32),
-                ("in_bias", ctypes.c_void_p), ("out_prezeroed", ctypes.c_int32)]
+                ("in_bias", ctypes.c_void_p), ("out_prezeroed", ctypes.c_int32),
+                ("win_cols", ctypes.c_int32), ("win_off", ctypes.c_int32), ("max_ctas", ctypes.c_int32)]
 
 
 def available():
@@ -104,8 +105,8 @@ class PackedChain:
 def run_chain(pc, B, cols_per_cloud, out, ldo, tile_cols=128, in_mode=IN_DENSE, a_src=None, a_ch=0, a_rows=0,
               idx=None, xyz=None, centers=None, group_k=0, b_src=None, b_ch=0, b_rows=0, nn_w=None,
               out_mode=OUT_ROWS, pool_g=0, biases=None, bias_per_cloud=(), masks=None, out_cm=None, split_cout=False,
-              l0=None, in_bias=None, out_prezeroed=False):
-    """Enqueue one fused chain on torch's current stream."""
+              l0=None, in_bias=None, out_prezeroed=False, window=None, max_ctas=0):
+    """Enqueue one fused chain on torch's current stream.  ``window`` = (first column, columns) of every cloud."""
     c = _Chain()
     c.n_layers = len(pc.dims)
     keep = []
@@ -131,6 +132,9 @@ def run_chain(pc, B, cols_per_cloud, out, ldo, tile_cols=128, in_mode=IN_DENSE, 
     if in_bias is not None:
         c.in_bias = in_bias.data_ptr()
     c.out_prezeroed = int(bool(out_prezeroed))
+    if window is not None:
+        c.win_off, c.win_cols = int(window[0]), int(window[1])
+    c.max_ctas = int(max_ctas)
     with torch.cuda.device(out.device):
         _lib.check(_lib.lib().cpfn_mlp_chain(ctypes.byref(c), torch.cuda.current_stream(out.device).cuda_stream),
                    "mlp_chain")
@@ -387,6 +391,71 @@ def sa_indices_overlapped(module, xyz, side):
     return new_xyz, idx
 
 
+def sa1_pipelined(module, xyz, worker, n_chunks=4):
+    """Set abstraction on bare positions with the sampling, the ball query and the MLP PIPELINED over chunks of
+    centroids.  Furthest point sampling is a chain of dependent rounds that keeps fewer than half of the SMs busy
+    (16 clouds x 4 CTAs); its centroids come out in order, so the sampling runs as ``n_chunks`` launches
+    (cpfn_furthest_point_sampling_rounds, bit-identical to one) on the current stream and, as soon as a chunk of
+    centroids exists, their ball query (cpfn_ball_query_grid_query_range) and their column window of the fused MLP
+    chain run on the stream ``worker`` -- on the SMs the sampling leaves idle -- while the next chunk is being
+    sampled.  Returns (new_xyz [B,S,3], new_feats_pm [B,S,D'], event): wait for the event before reading new_feats_pm;
+    new_xyz is complete on the current stream.  None when the shapes do not allow it (caller falls back)."""
+    B, N, _ = xyz.shape
+    dev = xyz.device
+    L = _lib.lib()
+    S, K = int(module.num_points), int(module.num_samples_list[0])
+    radius = float(module.radius_list[0])
+    pc = _sa_chain(module, dev)
+    tile = pick_tile(pc.dims, S * K, name='SA1', prefer=128)
+    if (n_chunks < 2 or S % n_chunks or ((S // n_chunks) * K) % tile or K % 32 or not (2048 <= N <= 16384) or radius <= 0
+            or getattr(pc, "l0", None) is None or not L.cpfn_fps_rounds_supported(B, N) or os.environ.get("CPFN_BQ_NO_GRID")):
+        return None
+    main = torch.cuda.current_stream(dev)
+    cout = pc.dims[-1][1]
+    fps_idx = torch.empty(B, S, dtype=torch.int32, device=dev)
+    new_xyz = torch.empty(B, S, 3, dtype=torch.float32, device=dev)
+    state = torch.empty(B, N, dtype=torch.float32, device=dev)
+    gidx = torch.empty(B, S, K, dtype=torch.int32, device=dev)
+    out = torch.empty(B, S, cout, dtype=torch.float32, device=dev)
+    nbytes = L.cpfn_ball_query_grid_workspace_bytes(B, N)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    floor = int(os.environ.get("CPFN_FPS_FLOOR_KB", "120")) * 1024
+    # while the sampling runs, the chain may only use the SMs it leaves free (two CTAs each): no CTA of a chunk's
+    # chain is left pending that could slip onto the sampling SMs between two sampling launches
+    sms = L.cpfn_sm_count()
+    cap = int(os.environ.get("CPFN_SA1_CAP", "0")) or max(2, 2 * (sms - 4 * B))
+    fork = torch.cuda.Event()
+    fork.record(main)
+    with torch.cuda.stream(worker), torch.cuda.device(dev):
+        worker.wait_event(fork)
+        _lib.check(L.cpfn_zero_fill(out.data_ptr(), out.numel() * 4, worker.cuda_stream), "zero_fill")
+        _lib.check(L.cpfn_ball_query_grid_build(xyz.data_ptr(), B, N, radius, ws.data_ptr(), nbytes, worker.cuda_stream),
+                   "ball_query_grid_build")
+    per = S // n_chunks
+    for c in range(n_chunks):
+        j0, j1 = c * per, (c + 1) * per
+        with torch.cuda.device(dev):
+            _lib.check(L.cpfn_furthest_point_sampling_rounds(xyz.data_ptr(), B, N, S, j0, j1, fps_idx.data_ptr(),
+                                                             new_xyz.data_ptr(), state.data_ptr(), state.numel() * 4,
+                                                             floor, main.cuda_stream), "furthest_point_sampling_rounds")
+        sampled = torch.cuda.Event()
+        sampled.record(main)
+        with torch.cuda.stream(worker), torch.cuda.device(dev):
+            worker.wait_event(sampled)
+            _lib.check(L.cpfn_ball_query_grid_query_range(new_xyz.data_ptr(), xyz.data_ptr(), B, N, S, j0, per, radius, K,
+                                                          gidx.data_ptr(), ws.data_ptr(), nbytes, worker.cuda_stream),
+                       "ball_query_grid_query_range")
+            run_chain(pc, B, S * K, out, cout, tile_cols=tile, in_mode=IN_GROUP, a_src=None, a_ch=0, a_rows=N, idx=gidx,
+                      xyz=xyz, centers=new_xyz, group_k=K, out_mode=OUT_POOL, pool_g=K, l0=pc.l0, out_prezeroed=True,
+                      window=(j0 * K, per * K), max_ctas=(cap if c + 1 < n_chunks else 0))
+    done = torch.cuda.Event()
+    done.record(worker)
+    for t in (fps_idx, new_xyz, state, gidx, out, ws):
+        t.record_stream(worker)
+    cuda_ops.count_launches(2 + 2 * n_chunks)
+    return new_xyz, out, done
+
+
 def sa_forward_pm(module, xyz, feats_pm, indices=None, out=None):
     """Point-major set abstraction.  xyz [B,N,3], feats_pm [B,N,D] | None ->
     (new_xyz [B,S,3] | None, new_feats_pm [B,S,D']).  ``out``: a ZERO-FILLED [B,S,D'] buffer for the pooled
@@ -495,8 +564,8 @@ _side_streams = {}
 USE_SIDE_STREAM = True      # bench.py's per-op profiling pass serialises everything on one stream
 
 
-def _side_stream(dev):
-    key = (dev.type, dev.index)
+def _side_stream(dev, which=0):
+    key = (dev.type, dev.index, which)
     if key not in _side_streams:
         _side_streams[key] = torch.cuda.Stream(device=dev)
     return _side_streams[key]
@@ -613,8 +682,15 @@ def pointnet2_forward(model, P, dropout=True):
     # FP3) runs on a side stream, concurrently with SA1's ball query and MLP chain on the main stream.
     main = torch.cuda.current_stream(dev)
     side = _side_stream(dev) if USE_SIDE_STREAM else main
-    idx1 = sa_indices_overlapped(model.sa1, P, side if side is not main else None)
-    l1_xyz = idx1[0]
+    mask = None
+    # SA1: sampling pipelined with its own ball query / MLP (sa1_pipelined) when the shapes allow it
+    n_chunks = int(os.environ.get("CPFN_SA1_CHUNKS", "1"))      # off by default: measured slower
+    piped = sa1_pipelined(model.sa1, P, _side_stream(dev, 1), n_chunks) if (side is not main and n_chunks > 1) else None
+    if piped is not None:
+        l1_xyz, l1, l1_done = piped
+    else:
+        idx1 = sa_indices_overlapped(model.sa1, P, side if side is not main else None)
+        l1_xyz = idx1[0]
     fork = torch.cuda.Event()
     fork.record(main)
     with torch.cuda.stream(side):
@@ -622,11 +698,16 @@ def pointnet2_forward(model, P, dropout=True):
         idx2 = sa_indices(model.sa2, l1_xyz)
         nn3 = three_nn_weights(P, l1_xyz)
         nn2 = three_nn_weights(l1_xyz, idx2[0])
-        # the reference's always-on dropout (pn2_network.py:63): same generator, same mask, as 1 bit per element
-        mask = dropout_bits(B, 128, N, dev, p=0.5) if dropout else None
+        # the reference's always-on dropout (pn2_network.py:63): same generator, same mask, as 1 bit per element.
+        # (Not under the sampling: its CTAs would share the sampling SMs and stretch every round -- measured.)
+        if dropout:
+            mask = dropout_bits(B, 128, N, dev, p=0.5)
         join = torch.cuda.Event()
         join.record(side)
-    _, l1 = sa_forward_pm(model.sa1, P, None, indices=idx1)
+    if piped is not None:
+        main.wait_event(l1_done)
+    else:
+        _, l1 = sa_forward_pm(model.sa1, P, None, indices=idx1)
     main.wait_event(join)
     if side is not main:
         for t in (*idx2, *nn3, *nn2) + ((mask[0],) if mask is not None else ()):

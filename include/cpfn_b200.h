@@ -54,6 +54,25 @@ CPFN_API int cpfn_sm_count(void);                      /* SMs of the current dev
  * The nine pointnet2 ops (drop-in for the pybind module `cuda_ops`).
  * ------------------------------------------------------------------------- */
 
+/* Furthest point sampling split over several launches: rounds j_begin .. j_end-1 of an nsamples-round sampling
+ * (sample j is chosen in round j; round 0 = the first point).  idx [B,nsamples] / new_xyz [B,nsamples,3] receive
+ * the samples of these rounds; `state` f32 [B,N] carries the running minimum distances from one launch to the next
+ * (required unless the call covers all rounds).  Bit-identical to one launch.  Why: a sampling is a chain of
+ * nsamples dependent rounds on a fraction of the SMs; cutting it lets the ball query and the set-abstraction MLP of
+ * the centroids already chosen run on the other SMs while the later rounds are still being sampled
+ * (fused.pointnet2_forward).  smem_floor_bytes > 0 raises the sampling CTAs' shared-memory request to that many
+ * bytes so that the co-running kernels' CTAs do not fit beside them.  Only for the cluster kernel's domain:
+ * cpfn_fps_rounds_supported(B, N) != 0 (2048 <= N <= 16384, B clouds x >= 2 CTAs fit the GPU). */
+CPFN_API int cpfn_fps_rounds_supported(int B, int N);
+CPFN_API int cpfn_furthest_point_sampling_rounds(const float *xyz, int B, int N, int nsamples, int j_begin, int j_end,
+                                                 int32_t *idx, float *new_xyz, float *state, size_t state_bytes,
+                                                 size_t smem_floor_bytes, cpfn_stream_t stream);
+
+/* Diagnostic: with the environment variable CPFN_FPS_PROFILE set, the cluster FPS kernel sums, over its rounds, the
+ * cycles thread 0 of CTA 0 spends in {distance update, warp arg-max, key push, waiting for the cluster's keys,
+ * cluster arg-max, centroid look-up}; this copies the six sums of the last such launch to the host (synchronises). */
+CPFN_API int cpfn_debug_fps_profile(long long *cycles6);
+
 /* Furthest point sampling.  Replaces farthest_point_sampling
  * (src/sampling.cpp:65-86, kernel src/sampling_gpu.cu:63-159).
  * xyz [B,N,3] f32 -> idx [B,nsamples] i32.  Bit-exact with the reference,
@@ -95,6 +114,12 @@ CPFN_API int cpfn_ball_query_grid_build(const float *xyz, int B, int N, float ra
 CPFN_API int cpfn_ball_query_grid_query(const float *new_xyz, const float *xyz, int B, int N, int S, float radius,
                                         int nsample, int32_t *idx, void *workspace, size_t workspace_bytes,
                                         cpfn_stream_t stream);
+/* The same query for centroids s_begin .. s_begin+s_count-1 of every cloud only (new_xyz and idx keep their full
+ * [B,S,.] shapes): lets the ball query follow a furthest point sampling that is still running
+ * (cpfn_furthest_point_sampling_rounds).  Grid kernel only (2048 <= N <= 32768, radius > 0). */
+CPFN_API int cpfn_ball_query_grid_query_range(const float *new_xyz, const float *xyz, int B, int N, int S, int s_begin,
+                                              int s_count, float radius, int nsample, int32_t *idx, void *workspace,
+                                              size_t workspace_bytes, cpfn_stream_t stream);
 
 /* Gather / group (+ gradients).  Replace gather_points(_grad)
  * (src/sampling.cpp:15-64, src/sampling_gpu.cu:8-53) and group_points(_grad)
@@ -220,6 +245,13 @@ typedef struct {
   /* OUT_POOL with atomic merging needs the pooled output zero-filled; non-zero = the caller has already done
    * that (e.g. off the critical path, on another stream), the library skips its own cudaMemsetAsync. */
   int32_t out_prezeroed;
+  /* Column window: when win_cols > 0 the launch processes columns [win_off, win_off + win_cols) of EVERY cloud only
+   * (both multiples of tile_cols and, for OUT_POOL, of pool_g; OUT_POOL then needs out_prezeroed).  All other fields
+   * keep describing the whole arrays.  Lets a set-abstraction MLP start on the centroids already sampled. */
+  int32_t win_cols, win_off;
+  /* > 0: upper bound on the number of (persistent) CTAs of the launch, for a chain that shares the GPU with another
+   * kernel which must keep its SMs (the CTAs loop over the tiles, so any number works). */
+  int32_t max_ctas;
 } cpfn_mlp_chain_t;
 
 /* Replaces the conv+BN+ReLU(+max) chains of pointset_abstraction.py:61-74,
@@ -249,6 +281,10 @@ CPFN_API int cpfn_gather_xyz(const float *xyz, const int32_t *idx, int B, int N,
  * output row are set to zero (the chains read biases zero padded to a multiple of 128). */
 CPFN_API int cpfn_linear_rows(const float *x, const float *W, const float *bias, int rows, int cin,
                               int cout, int ldo, float *out, cpfn_stream_t stream);
+
+/* Stream-ordered zero fill (cudaMemsetAsync): the pooled output of a set-abstraction chain that runs as several
+ * column windows is cleared once by the caller (cpfn_mlp_chain_t.out_prezeroed). */
+CPFN_API int cpfn_zero_fill(void *dst, size_t bytes, cpfn_stream_t stream);
 
 /* LocalSPFN input normalisation (Dataset/dataloaders.py:249-253): out[b, i] = (P[idx[b, i]] - mean_b) / max_i |P[idx[b, i]]
  * - mean_b|, mean_b = the patch's mean point (fp64 accumulation in a fixed order, rounded to fp32: the result of a
