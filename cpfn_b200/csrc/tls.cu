@@ -19,13 +19,16 @@
 // and three tiny solve kernels do the 3x3 / 2x2 eigen problems and linear solves in registers
 // (fp64 Jacobi).
 //   pass 1: sum w, sum w p, sum w |p|^2, sum w x, sum w x x^T, sum w' x x^T, sum w' x (p.x)
-//   solve1: means (rounded to fp32 like the reference's), cylinder axis, cone apex
+//   solve1: means (rounded to fp32 like the reference's), cylinder axis, cone apex, cone axis (the scatter of
+//           the normals about their fp32-rounded mean follows from the raw normal moments by exact algebra in
+//           fp64: the normals are unit vectors, so the shift costs no accuracy worth the name)
 //   pass 2: centred moments about the per-slot means: S = sum w d d^T, S' = sum w' d d^T,
-//           sum w' d, third-order T' = sum w' d d d, Cx = sum w (x-mx)(x-mx)^T
+//           sum w' d, third-order T' = sum w' d d d; and, with the apex and the axis of solve1, the cone's
+//           sum w (dir.axis), sum w acos|dir.axis|
 //   solve2: plane, sphere, cylinder (the 2-D circle fit is obtained by projecting the 3-D
 //           centred moments onto the cylinder frame -- no pass over the points is needed
-//           once the axis is known), cone axis
-//   pass 3: cone: sum w (dir.axis), sum w acos|dir.axis|;  solve3: sign fix, half angle.
+//           once the axis is known), cone sign fix and half angle.
+// Two passes over W -- SURVEY 8(d)'s model of 2 B N (4K + 24) bytes; round 1 took a third pass for the cone.
 // (w' = max(w, 1e-10), d = p - mean.)  Thread t of a CTA owns slot k = t % K and point lane
 // g = t / K, so a warp reads W as one contiguous stream (coalesced, every byte used once);
 // point coordinates are staged once per CTA in shared memory as float4.  Each thread sums at
@@ -41,7 +44,7 @@ namespace {
 constexpr int kTlsThreads = 256;
 constexpr int kMaxCP = 1024;      // points staged per sub-chunk
 constexpr int kPPT = 32;          // points per thread and sub-chunk (weights preloaded in registers)
-constexpr int kF1 = 23, kF2 = 31, kF3 = 2, kF4 = 32;   // kF4: raw moments up to third order (training path)
+constexpr int kF1 = 23, kF2 = 27, kF3 = 2, kF4 = 32;   // kF4: raw moments up to third order (training path)
 constexpr int kFP = 32;           // padded feature stride of the partial arrays
 constexpr int kState = 24;        // doubles per (b,k)
 // state layout
@@ -76,8 +79,10 @@ template <int PASS>
 __global__ void __launch_bounds__(kTlsThreads, 2)
 tls_pass_kernel(const float *__restrict__ P, const float *__restrict__ X,
                 const float *__restrict__ W, const double *__restrict__ state,
-                double *__restrict__ part, int N, int K, int G, int CP, int iters, int chunks) {
+                double *__restrict__ part, int N, int K, int G, int CP, int iters, int chunks,
+                double *__restrict__ pivots) {
   constexpr int F = NFeat<PASS>::F;
+  __shared__ float s_piv[4];                 // PASS 1: the CTA's pivot for the first and second normal moments
   extern __shared__ float4 s_pts[];          // [CP] positions (+ |p|^2), [CP] normals (+ p.x)
   float4 *sp = s_pts, *sx = s_pts + CP;
   double *red = reinterpret_cast<double *>(s_pts + 2 * CP);   // [kTlsThreads][8]
@@ -90,16 +95,12 @@ tls_pass_kernel(const float *__restrict__ P, const float *__restrict__ X,
   const float *Wb = W + static_cast<size_t>(b) * N * K;
   const int ppt = CP / G;
 
-  float c0 = 0.f, c1 = 0.f, c2 = 0.f, e0 = 0.f, e1 = 0.f, e2 = 0.f;   // per-slot constants
-  if (PASS == 2 || PASS == 3) {
+  float c0 = 0.f, c1 = 0.f, c2 = 0.f, e0 = 0.f, e1 = 0.f, e2 = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f;   // per-slot constants
+  if (PASS == 2) {
     const double *st = state + (static_cast<size_t>(b) * K + k) * kState;
-    if (PASS == 2) {
-      c0 = static_cast<float>(st[ST_MU]); c1 = static_cast<float>(st[ST_MU + 1]); c2 = static_cast<float>(st[ST_MU + 2]);
-      e0 = static_cast<float>(st[ST_MUX]); e1 = static_cast<float>(st[ST_MUX + 1]); e2 = static_cast<float>(st[ST_MUX + 2]);
-    } else {
-      c0 = static_cast<float>(st[ST_APEX]); c1 = static_cast<float>(st[ST_APEX + 1]); c2 = static_cast<float>(st[ST_APEX + 2]);
-      e0 = static_cast<float>(st[ST_CONEAX]); e1 = static_cast<float>(st[ST_CONEAX + 1]); e2 = static_cast<float>(st[ST_CONEAX + 2]);
-    }
+    c0 = static_cast<float>(st[ST_MU]); c1 = static_cast<float>(st[ST_MU + 1]); c2 = static_cast<float>(st[ST_MU + 2]);
+    a0 = static_cast<float>(st[ST_APEX]); a1 = static_cast<float>(st[ST_APEX + 1]); a2 = static_cast<float>(st[ST_APEX + 2]);
+    e0 = static_cast<float>(st[ST_CONEAX]); e1 = static_cast<float>(st[ST_CONEAX + 1]); e2 = static_cast<float>(st[ST_CONEAX + 2]);
   }
   for (int o = t; o < K * kFP; o += kTlsThreads) tot[o] = 0.0;
 
@@ -132,6 +133,28 @@ tls_pass_kernel(const float *__restrict__ P, const float *__restrict__ X,
       sx[i] = make_float4(xx, xy, xz, px * xx + py * xy + pz * xz);
     }
     __syncthreads();
+    if (PASS == 1 && it == 0) {
+      // Pivot of this CTA's normal moments: the plain mean of the normals it staged first.  sum w x and sum w x x^T
+      // are accumulated about it and shifted back to the origin in fp64 by solve1 (exact algebra per CTA): when the
+      // normals a slot weights are concentrated around the cloud's mean normal -- near-uniform memberships -- the
+      // fp32 terms are small and the scatter about the slot mean, which the cone axis comes from, keeps its digits.
+      float a = 0.f, bq = 0.f, c = 0.f;
+      for (int i = t; i < cn; i += kTlsThreads) { const float4 x = sx[i]; a += x.x; bq += x.y; c += x.z; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o); bq += __shfl_xor_sync(0xffffffffu, bq, o); c += __shfl_xor_sync(0xffffffffu, c, o);
+      }
+      float *wsum = reinterpret_cast<float *>(red);            // [8 warps][3], free at this point
+      if ((t & 31) == 0) { wsum[(t >> 5) * 3] = a; wsum[(t >> 5) * 3 + 1] = bq; wsum[(t >> 5) * 3 + 2] = c; }
+      __syncthreads();
+      if (t < 3) {
+        float v = 0.f;
+        for (int w8 = 0; w8 < kTlsThreads / 32; ++w8) v += wsum[w8 * 3 + t];
+        s_piv[t] = v / static_cast<float>(cn);
+      }
+      __syncthreads();
+    }
+    const float pv0 = PASS == 1 ? s_piv[0] : 0.f, pv1 = PASS == 1 ? s_piv[1] : 0.f, pv2 = PASS == 1 ? s_piv[2] : 0.f;
     float acc[F];
 #pragma unroll
     for (int f = 0; f < F; ++f) acc[f] = 0.f;
@@ -151,16 +174,16 @@ tls_pass_kernel(const float *__restrict__ P, const float *__restrict__ X,
         acc[0] += w;
         acc[1] = fmaf(w, p.x, acc[1]); acc[2] = fmaf(w, p.y, acc[2]); acc[3] = fmaf(w, p.z, acc[3]);
         acc[4] = fmaf(w, p.w, acc[4]);
-        const float wx = w * x.x, wy = w * x.y, wz = w * x.z;
+        const float qx = x.x - pv0, qy = x.y - pv1, qz = x.z - pv2;      // about the CTA's pivot
+        const float wx = w * qx, wy = w * qy, wz = w * qz;
         acc[5] += wx; acc[6] += wy; acc[7] += wz;
-        acc[8] = fmaf(wx, x.x, acc[8]); acc[9] = fmaf(wx, x.y, acc[9]); acc[10] = fmaf(wx, x.z, acc[10]);
-        acc[11] = fmaf(wy, x.y, acc[11]); acc[12] = fmaf(wy, x.z, acc[12]); acc[13] = fmaf(wz, x.z, acc[13]);
+        acc[8] = fmaf(wx, qx, acc[8]); acc[9] = fmaf(wx, qy, acc[9]); acc[10] = fmaf(wx, qz, acc[10]);
+        acc[11] = fmaf(wy, qy, acc[11]); acc[12] = fmaf(wy, qz, acc[12]); acc[13] = fmaf(wz, qz, acc[13]);
         const float vx = wc * x.x, vy = wc * x.y, vz = wc * x.z;
         acc[14] = fmaf(vx, x.x, acc[14]); acc[15] = fmaf(vx, x.y, acc[15]); acc[16] = fmaf(vx, x.z, acc[16]);
         acc[17] = fmaf(vy, x.y, acc[17]); acc[18] = fmaf(vy, x.z, acc[18]); acc[19] = fmaf(vz, x.z, acc[19]);
         acc[20] = fmaf(vx, x.w, acc[20]); acc[21] = fmaf(vy, x.w, acc[21]); acc[22] = fmaf(vz, x.w, acc[22]);
       } else if (PASS == 2) {
-        const float4 x = xp[i * G];
         const float wc = ok ? fmaxf(w, 1e-10f) : 0.f;
         const float dx = p.x - c0, dy = p.y - c1, dz = p.z - c2;
         const float wx = w * dx, wy = w * dy, wz = w * dz;
@@ -174,10 +197,23 @@ tls_pass_kernel(const float *__restrict__ P, const float *__restrict__ X,
         acc[18] = fmaf(uxy, dy, acc[18]); acc[19] = fmaf(uxy, dz, acc[19]); acc[20] = fmaf(uxz, dz, acc[20]);
         acc[21] = fmaf(uyy, dy, acc[21]); acc[22] = fmaf(uyy, dz, acc[22]); acc[23] = fmaf(uyz, dz, acc[23]);
         acc[24] = fmaf(uzz, dz, acc[24]);
-        const float ax = x.x - e0, ay = x.y - e1, az = x.z - e2;
-        const float qx = w * ax, qy = w * ay, qz = w * az;
-        acc[25] = fmaf(qx, ax, acc[25]); acc[26] = fmaf(qx, ay, acc[26]); acc[27] = fmaf(qx, az, acc[27]);
-        acc[28] = fmaf(qy, ay, acc[28]); acc[29] = fmaf(qy, az, acc[29]); acc[30] = fmaf(qz, az, acc[30]);
+        // cone_fitter.py:25-33: dir = normalize(p - apex, eps 1e-12); dot = axis . dir; acos(clamp |dot|)
+        const float hx = p.x - a0, hy = p.y - a1, hz = p.z - a2;
+        const float n2 = fmaf(hz, hz, fmaf(hy, hy, hx * hx));
+        const float inv = n2 > 1e-24f ? rsqrtf(n2) : 1e12f;              // 1 / max(|v|, 1e-12)
+        const float dot = fmaf(e2, hz, fmaf(e1, hy, e0 * hx)) * inv;
+        acc[25] = fmaf(w, dot, acc[25]);
+        const float a = fminf(fabsf(dot), 1.0f - 1e-6f);
+        // acos on [0,1): sqrt(1-a) * P7(a) (Abramowitz & Stegun 4.4.46, |error| <= 2e-8): the sum below is
+        // divided by sum w afterwards, far inside the 1e-5 tolerance, at a third of acosf's instruction count
+        float poly = fmaf(-0.0012624911f, a, 0.0066700901f);
+        poly = fmaf(poly, a, -0.0170881256f);
+        poly = fmaf(poly, a, 0.0308918810f);
+        poly = fmaf(poly, a, -0.0501743046f);
+        poly = fmaf(poly, a, 0.0889789874f);
+        poly = fmaf(poly, a, -0.2145988016f);
+        poly = fmaf(poly, a, 1.5707963050f);
+        acc[26] = fmaf(w, sqrtf(1.0f - a) * poly, acc[26]);
       } else if (PASS == 4) {
         // raw moments  sum w * [1, p, p p^T, p p p, x, x x^T, x (p.x)]  (feature order of cpfn_weighted_moments)
         const float4 x = xp[i * G];
@@ -194,24 +230,6 @@ tls_pass_kernel(const float *__restrict__ P, const float *__restrict__ X,
         acc[23] = fmaf(vx, x.x, acc[23]); acc[24] = fmaf(vx, x.y, acc[24]); acc[25] = fmaf(vx, x.z, acc[25]);
         acc[26] = fmaf(vy, x.y, acc[26]); acc[27] = fmaf(vy, x.z, acc[27]); acc[28] = fmaf(vz, x.z, acc[28]);
         acc[29] = fmaf(vx, x.w, acc[29]); acc[30] = fmaf(vy, x.w, acc[30]); acc[31] = fmaf(vz, x.w, acc[31]);
-      } else {
-        // cone_fitter.py:25-33: dir = normalize(p - apex, eps 1e-12); dot = axis . dir; acos(clamp |dot|)
-        const float vx = p.x - c0, vy = p.y - c1, vz = p.z - c2;
-        const float n2 = fmaf(vz, vz, fmaf(vy, vy, vx * vx));
-        const float inv = n2 > 1e-24f ? rsqrtf(n2) : 1e12f;              // 1 / max(|v|, 1e-12)
-        const float dot = fmaf(e2, vz, fmaf(e1, vy, e0 * vx)) * inv;
-        acc[0] = fmaf(w, dot, acc[0]);
-        const float a = fminf(fabsf(dot), 1.0f - 1e-6f);
-        // acos on [0,1): sqrt(1-a) * P7(a) (Abramowitz & Stegun 4.4.46, |error| <= 2e-8): the sum below is
-        // divided by sum w afterwards, far inside the 1e-5 tolerance, at a third of acosf's instruction count
-        float poly = fmaf(-0.0012624911f, a, 0.0066700901f);
-        poly = fmaf(poly, a, -0.0170881256f);
-        poly = fmaf(poly, a, 0.0308918810f);
-        poly = fmaf(poly, a, -0.0501743046f);
-        poly = fmaf(poly, a, 0.0889789874f);
-        poly = fmaf(poly, a, -0.2145988016f);
-        poly = fmaf(poly, a, 1.5707963050f);
-        acc[1] = fmaf(w, sqrtf(1.0f - a) * poly, acc[1]);
       }
     }
     // Combine the G point lanes of every slot in fp64 (fixed order) into the CTA totals.
@@ -239,6 +257,7 @@ tls_pass_kernel(const float *__restrict__ P, const float *__restrict__ X,
   double *out = part + (static_cast<size_t>(b) * chunks + chunk) * K * kFP;
   for (int o = t; o < K * kFP; o += kTlsThreads)
     if ((o & (kFP - 1)) < F) out[o] = tot[o];
+  if (PASS == 1 && t < 3) pivots[(static_cast<size_t>(b) * chunks + chunk) * 4 + t] = static_cast<double>(s_piv[t]);
 }
 
 // ---- small dense algebra in registers (fp64) -------------------------------------------------
@@ -368,21 +387,52 @@ __device__ __forceinline__ double sum_partials(const double *part, int b, int k,
 constexpr int kSolveWarps = 4;
 
 __global__ void __launch_bounds__(kSolveWarps * 32)
-tls_solve1_kernel(const double *__restrict__ part, double *__restrict__ state, int BK, int K,
-                  int chunks) {
+tls_solve1_kernel(const double *__restrict__ part, const double *__restrict__ pivots, double *__restrict__ state,
+                  int BK, int K, int chunks) {
   __shared__ double sm[kSolveWarps][kFP];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bk = blockIdx.x * kSolveWarps + warp;
   if (bk >= BK) return;
   const int b = bk / K, k = bk - b * K;
-  sm[warp][lane] = lane < kF1 ? sum_partials(part, b, k, K, chunks, lane) : 0.0;
+  double v = 0.0;
+  if (lane < kF1 && (lane < 5 || lane > 13)) {
+    v = sum_partials(part, b, k, K, chunks, lane);
+  } else if (lane < kF1) {
+    // features 5-13 were accumulated about each CTA's pivot c: back to the origin, chunk by chunk, in fp64:
+    //   sum w x = s + Sw c,   sum w x_i x_j = M_ij + c_i s_j + s_i c_j + Sw c_i c_j
+    const int ij[9][2] = {{0, 0}, {1, 1}, {2, 2}, {0, 0}, {0, 1}, {0, 2}, {1, 1}, {1, 2}, {2, 2}};
+    const int i = ij[lane - 5][0], j = ij[lane - 5][1];
+    for (int c = 0; c < chunks; ++c) {
+      const double *p = part + ((static_cast<size_t>(b) * chunks + c) * K + k) * kFP;
+      const double *pv = pivots + (static_cast<size_t>(b) * chunks + c) * 4;
+      const double sw = p[0];
+      if (lane < 8) v += p[lane] + sw * pv[i];
+      else v += p[lane] + pv[i] * p[5 + j] + p[5 + i] * pv[j] + sw * pv[i] * pv[j];
+    }
+  }
+  sm[warp][lane] = v;
   __syncwarp();
   const double *m = sm[warp];
   double *st = state + static_cast<size_t>(bk) * kState;
-  // The two 3x3 eigen problems of a slot run on two lanes of the SAME branch (in lock step), not one
-  // after the other: lane 1 = cylinder axis (TLS on the normals, uncentred), lane 2 = cone apex.
-  double lam[3], V[3][3];
-  if (lane == 1 || lane == 2) eig_sym3(m + (lane == 1 ? 8 : 14), lam, V);
+  // The three 3x3 eigen problems of a slot run on three lanes of the SAME branch (in lock step), not one
+  // after the other: lane 1 = cylinder axis (TLS on the normals, uncentred), lane 2 = cone apex, lane 3 = cone
+  // axis (plane-fit normal of the normals: the smallest eigenvector of their scatter about the mean).
+  double lam[3], V[3][3], Cx[6];
+  {
+    // sum w (x - mx)(x - mx)^T with the reference's fp32-rounded mean mx, from the raw moments (exact algebra)
+    const double sw = m[0];
+    const double denom = static_cast<double>(fmaxf(static_cast<float>(sw), 1e-10f));
+    double mx[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) mx[i] = static_cast<double>(static_cast<float>(m[5 + i] / denom));
+    const int ij[6][2] = {{0, 0}, {0, 1}, {0, 2}, {1, 1}, {1, 2}, {2, 2}};
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      const int i = ij[q][0], j = ij[q][1];
+      Cx[q] = m[8 + q] - mx[i] * m[5 + j] - m[5 + i] * mx[j] + sw * mx[i] * mx[j];
+    }
+  }
+  if (lane >= 1 && lane <= 3) eig_sym3(lane == 1 ? m + 8 : (lane == 2 ? m + 14 : Cx), lam, V);
   if (lane == 0) {
     const double sw = m[0];
     const double denom = static_cast<double>(fmaxf(static_cast<float>(sw), 1e-10f));
@@ -403,6 +453,11 @@ tls_solve1_kernel(const double *__restrict__ part, double *__restrict__ state, i
     double apex[3];
     guarded_solve3_eigs(m + 14, m + 20, lam, apex);   // rows sqrt(w') x, rhs sqrt(w') (p.x)
     st[ST_APEX] = apex[0]; st[ST_APEX + 1] = apex[1]; st[ST_APEX + 2] = apex[2];
+  } else if (lane == 3) {
+    double ax[3];
+    pick_min_eigvec(lam, V, ax);                      // sign fixed in solve2 (cone_fitter.py:29-30)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) st[ST_CONEAX + i] = static_cast<double>(static_cast<float>(ax[i]));
   }
 }
 
@@ -418,7 +473,7 @@ tls_solve2_kernel(const double *__restrict__ part, double *__restrict__ state,
   __syncwarp();
   if (lane > 3) return;
   const double *m = sm[warp];
-  const double *S = m, *Sp = m + 6, *s1p = m + 12, *T = m + 15, *Cx = m + 25;
+  const double *S = m, *Sp = m + 6, *s1p = m + 12, *T = m + 15;
   double *st = state + static_cast<size_t>(bk) * kState;
   const double sw = st[ST_SW], denom = st[ST_DENOM], m2 = st[ST_M2];
   const double mu[3] = {st[ST_MU], st[ST_MU + 1], st[ST_MU + 2]};
@@ -428,12 +483,12 @@ tls_solve2_kernel(const double *__restrict__ part, double *__restrict__ state,
         *o_ca = out + 8 * BKs, *o_cc = out + 11 * BKs, *o_cr = out + 14 * BKs,
         *o_ap = out + 15 * BKs, *o_ax = out + 18 * BKs;
 
-  // The four sub-problems of a slot are independent: lanes 0..3 take one each.  The three 3x3 eigen
-  // problems (plane S, sphere 4S', cone Cx) run in lock step on lanes 0, 1, 3 in ONE branch.
+  // The four sub-problems of a slot are independent: lanes 0..3 take one each.  The two 3x3 eigen
+  // problems (plane S, sphere 4S') run in lock step on lanes 0 and 1 in ONE branch.
   double lam[3], V[3][3], AtA[6];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) AtA[i] = lane == 0 ? S[i] : (lane == 1 ? 4.0 * Sp[i] : Cx[i]);
-  if (lane != 2) eig_sym3(AtA, lam, V);
+  for (int i = 0; i < 6; ++i) AtA[i] = lane == 0 ? S[i] : 4.0 * Sp[i];
+  if (lane < 2) eig_sym3(AtA, lam, V);
   if (lane == 0) {
     // plane: normal = TLS of the centred points, c = n . mean
     double n[3];
@@ -444,15 +499,19 @@ tls_solve2_kernel(const double *__restrict__ part, double *__restrict__ state,
     return;
   }
   if (lane == 3) {
-    // cone: apex from solve1; axis = plane-fit normal of the normals (sign fixed in solve3)
-    double ax[3];
-    pick_min_eigvec(lam, V, ax);
+    // cone: apex and axis from solve1; sign so that the weighted mean of axis . dir is positive, 0 -> +1
+    // (cone_fitter.py:29-30); half angle = sum w acos|axis . dir| / (sum w + 1e-10), clamped (:33-35)
+    float *o_ha = out + 21 * BKs;
+    const float sf = static_cast<float>(m[25]);
+    const float sgn = sf > 0.f ? 1.f : (sf < 0.f ? -1.f : 1.f);
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      st[ST_CONEAX + i] = static_cast<double>(static_cast<float>(ax[i]));
       o_ap[bk * 3 + i] = static_cast<float>(st[ST_APEX + i]);
-      o_ax[bk * 3 + i] = static_cast<float>(ax[i]);
+      o_ax[bk * 3 + i] = static_cast<float>(st[ST_CONEAX + i]) * sgn;
     }
+    float half = static_cast<float>(m[26]) / (static_cast<float>(sw) + 1e-10f);
+    half = fminf(fmaxf(half, 1e-3f), 1.57079632679489661923f - 1e-3f);
+    o_ha[bk] = half;
     return;
   }
   if (lane == 1) {
@@ -539,28 +598,6 @@ tls_solve2_kernel(const double *__restrict__ part, double *__restrict__ state,
   }
 }
 
-__global__ void __launch_bounds__(kSolveWarps * 32)
-tls_solve3_kernel(const double *__restrict__ part, const double *__restrict__ state,
-                  float *__restrict__ out, int BK, int K, int chunks) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int bk = blockIdx.x * kSolveWarps + warp;
-  if (bk >= BK) return;
-  const int b = bk / K, k = bk - b * K;
-  const double v = lane < kF3 ? sum_partials(part, b, k, K, chunks, lane) : 0.0;
-  const double s = __shfl_sync(0xffffffffu, v, 0), a = __shfl_sync(0xffffffffu, v, 1);
-  if (lane != 0) return;
-  const size_t BKs = static_cast<size_t>(BK);
-  float *o_ax = out + 18 * BKs, *o_ha = out + 21 * BKs;
-  const float sf = static_cast<float>(s);
-  const float sgn = sf > 0.f ? 1.f : (sf < 0.f ? -1.f : 1.f);   // sign(), 0 -> +1 (cone_fitter.py:29-30)
-#pragma unroll
-  for (int i = 0; i < 3; ++i) o_ax[bk * 3 + i] *= sgn;
-  const float wsum = static_cast<float>(state[static_cast<size_t>(bk) * kState + ST_SW]);
-  float half = static_cast<float>(a) / (wsum + 1e-10f);
-  half = fminf(fmaxf(half, 1e-3f), 1.57079632679489661923f - 1e-3f);
-  o_ha[bk] = half;
-}
-
 // ---- training path: raw weighted moments and their gradients -----------------------------------
 // M[b,k,f] = sum_n Wt[b,n,k] * psi_f(p_n, x_n), psi = [1, p(3), p p^T(6), p p p(10), x(3), x x^T(6), x (p.x)(3)].
 // Linear in the weights, so the backward is dWt[b,n,k] = sum_f psi_f(n) dM[b,k,f] (same thread mapping as
@@ -643,7 +680,7 @@ moments_grad_x_kernel(const float *__restrict__ P, const float *__restrict__ X, 
 }
 
 struct TlsWs {
-  double *state, *part;
+  double *state, *part, *pivots;
   size_t bytes;
 };
 
@@ -651,9 +688,11 @@ TlsWs tls_carve(void *ws, int B, int K, const TlsGeom &g) {
   TlsWs w;
   const size_t n_state = static_cast<size_t>(B) * K * kState;
   const size_t n_part = static_cast<size_t>(B) * g.chunks * K * kFP;
+  const size_t n_piv = static_cast<size_t>(B) * g.chunks * 4;
   w.state = static_cast<double *>(ws);
   w.part = w.state + n_state;
-  w.bytes = (n_state + n_part) * sizeof(double);
+  w.pivots = w.part + n_part;
+  w.bytes = (n_state + n_part + n_piv) * sizeof(double);
   return w;
 }
 
@@ -685,20 +724,16 @@ extern "C" int cpfn_fit_primitives(const float *P, const float *W, const float *
   if (smem > 48 * 1024) {
     CPFN_CUDA_TRY(cudaFuncSetAttribute(tls_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     CPFN_CUDA_TRY(cudaFuncSetAttribute(tls_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    CPFN_CUDA_TRY(cudaFuncSetAttribute(tls_pass_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   }
   const dim3 grid(g.chunks, B);
   const int BK = B * K;
   const int sgrid = (BK + kSolveWarps - 1) / kSolveWarps;
   tls_pass_kernel<1><<<grid, kTlsThreads, smem, st>>>(P, X, W, ws.state, ws.part, N, K, g.G, g.CP,
-                                                      g.iters, g.chunks);
-  tls_solve1_kernel<<<sgrid, kSolveWarps * 32, 0, st>>>(ws.part, ws.state, BK, K, g.chunks);
-  tls_pass_kernel<2><<<grid, kTlsThreads, smem, st>>>(P, X, W, ws.state, ws.part, N, K, g.G, g.CP,
-                                                      g.iters, g.chunks);
+                                                      g.iters, g.chunks, ws.pivots);
+  tls_solve1_kernel<<<sgrid, kSolveWarps * 32, 0, st>>>(ws.part, ws.pivots, ws.state, BK, K, g.chunks);
+  tls_pass_kernel<2><<<grid, kTlsThreads, smem, st>>>(P, nullptr, W, ws.state, ws.part, N, K, g.G, g.CP,
+                                                      g.iters, g.chunks, nullptr);     // pass 2 reads no normals
   tls_solve2_kernel<<<sgrid, kSolveWarps * 32, 0, st>>>(ws.part, ws.state, out, BK, K, g.chunks);
-  tls_pass_kernel<3><<<grid, kTlsThreads, smem, st>>>(P, X, W, ws.state, ws.part, N, K, g.G, g.CP,
-                                                      g.iters, g.chunks);
-  tls_solve3_kernel<<<sgrid, kSolveWarps * 32, 0, st>>>(ws.part, ws.state, out, BK, K, g.chunks);
   return check_launch();
 }
 
@@ -720,7 +755,7 @@ extern "C" int cpfn_weighted_moments(const float *P, const float *X, const float
   if (smem > 48 * 1024)
     CPFN_CUDA_TRY(cudaFuncSetAttribute(tls_pass_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   tls_pass_kernel<4><<<dim3(g.chunks, B), kTlsThreads, smem, st>>>(P, X, Wt, ws.state, ws.part, N, K, g.G, g.CP, g.iters,
-                                                               g.chunks);
+                                                               g.chunks, nullptr);
   const int BK = B * K;
   tls_sum_partials_kernel<<<(BK + kSolveWarps - 1) / kSolveWarps, kSolveWarps * 32, 0, st>>>(ws.part, M, BK, K, g.chunks);
   return check_launch();

@@ -47,7 +47,7 @@ def fit_primitives_packed(P, W, X):
                                          out.data_ptr(), ws.data_ptr(), ws.numel(),
                                          torch.cuda.current_stream(P.device).cuda_stream),
                    "fit_primitives")
-    cuda_ops.count_launches(6)
+    cuda_ops.count_launches(4)
     BK = B * K
     res = {}
     for name, off, width in KEYS:

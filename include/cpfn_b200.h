@@ -174,7 +174,7 @@ CPFN_API int cpfn_three_weighted_sum_grad(const float *grad_out, const int32_t *
  *   [18BK) cone_axis [B,K,3]           [21BK) cone_half_angle [B,K]
  * plane_normal and cylinder_axis are defined up to sign (as the reference's SVD);
  * here the component of largest magnitude is made positive.  K <= 256.
- * Six kernels are enqueued on `stream`; no host synchronisation. */
+ * Four kernels (two passes over W, two per-slot solves) are enqueued on `stream`; no host synchronisation. */
 CPFN_API size_t cpfn_fit_workspace_bytes(int B, int N, int K);
 CPFN_API int cpfn_fit_primitives(const float *P, const float *W, const float *X, int B,
                                  int N, int K, float *out, void *workspace,
