@@ -53,7 +53,7 @@ class GlobalSPFN:
         return changed
 
     @torch.no_grad()
-    def forward(self, P, dropout=True, fit=True, scatter=None):
+    def forward(self, P, dropout=True, fit=True, scatter=None, rng_slot=0):
         """P [B,N,3] float32 on the device.  Returns a dict: X [B,N,3] unit normals, T [B,N,n_types]
         type logits, W [B,N,K] soft memberships, X_raw/T_raw/W_raw head outputs, l3_feats,
         output_feat, sa1_fps (int32 [B,512]) and ``parameters`` (the reference's dictionary).
@@ -64,7 +64,8 @@ class GlobalSPFN:
         if fused.available():
             if not P.is_cuda:
                 raise RuntimeError("CPU not supported")
-            heads, l3_feats, feat, l1_xyz, l2_xyz, packed = fused.pointnet2_forward(self.model, P, dropout=dropout)
+            heads, l3_feats, feat, l1_xyz, l2_xyz, packed = fused.pointnet2_forward(self.model, P, dropout=dropout,
+                                                                                    rng_slot=rng_slot)
             out = {"heads": list(heads), "l3_feats": l3_feats, "output_feat": feat,
                    "l1_pos": l1_xyz.permute(0, 2, 1), "l2_pos": l2_xyz.permute(0, 2, 1)}
             if len(heads) != 3:
@@ -122,11 +123,11 @@ class GlobalSPFN:
         cuda_ops.count_launches(n_launch)
         return out
 
-    def _sync_rng(self, shape):
-        """A captured forward draws its dropout mask from the device-side RNG state: refresh it from torch's
-        generator before every replay (fused.sync_rng)."""
+    def _sync_rng(self, shape, slot=0):
+        """A captured forward draws its dropout mask from the device-side RNG state (one per graph slot): refresh
+        it from torch's generator before every replay (fused.sync_rng)."""
         from . import fused
-        fused.sync_rng(self.device, shape[0] * 128 * shape[1])
+        fused.sync_rng(self.device, shape[0] * 128 * shape[1], slot)
 
     def _net_graph(self, P, dropout, fit, slot, scatter=None):
         """(graph, its static input, its static outputs, launches) for inputs shaped like P; ``slot`` selects one
@@ -141,7 +142,8 @@ class GlobalSPFN:
         if entry is None:
             static_in = torch.empty(tuple(P.shape), dtype=torch.float32, device=self.device)
             static_in.copy_(P)
-            graph, out, n = self._capture(lambda: self.forward(static_in, dropout=dropout, fit=fit, scatter=scatter))
+            graph, out, n = self._capture(lambda: self.forward(static_in, dropout=dropout, fit=fit, scatter=scatter,
+                                                               rng_slot=slot))
             entry = (graph, static_in, out, n)
             self._graphs[key] = entry
         return entry
@@ -169,61 +171,98 @@ class GlobalSPFN:
         i's per-point results travel back under its own fitters.  Every batch still does its full H2D, forward,
         fit and D2H; only their overlap changes.  Yields (results, h2d_bytes, d2h_bytes) in order; the result
         tensors of a batch are pinned buffers that are reused two batches later."""
+        yield from self._stream(batches, dropout, host=True)
+
+    @torch.no_grad()
+    def stream_device(self, batches, dropout=True):
+        """The same pipeline for batches that already live on the device: yields (forward dictionary incl.
+        ``parameters``, 0, 0) per batch.  The tensors are the static buffers of the batch's graph slot: valid until
+        the batch after next is submitted."""
+        yield from self._stream(batches, dropout, host=False)
+
+    def _stream(self, batches, dropout, host):
+        """Two graph slots, each with its own stream, input / output buffers and RNG state.  Consecutive batches
+        alternate between the slots, so batch i+1's sampling -- a chain of dependent rounds that keeps 64 of the 148
+        SMs busy -- runs beside batch i's MLP chains and fitters instead of in front of them (the GPU interleaves
+        the two graphs; each graph is unchanged and so are its results)."""
         from . import fused
-        main = torch.cuda.current_stream(self.device)
-        copy_in = self.__dict__.setdefault("_copy_in", torch.cuda.Stream(device=self.device))
-        copier = fused._side_stream(self.device)
+        dev = self.device
+        caller = torch.cuda.current_stream(dev)
+        lanes = self.__dict__.setdefault("_lanes", [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)])
+        copy_in = self.__dict__.setdefault("_copy_in", torch.cuda.Stream(device=dev))
+        copier = fused._side_stream(dev)
         free = [None, None]                                   # slot's input may be overwritten after this event
         sent = [None, None]                                   # slot's per-point outputs have left the device
+        start = torch.cuda.Event()
+        start.record(caller)
+        for lane in lanes:
+            lane.wait_event(start)                            # whatever the caller enqueued before comes first
         pending = None
-        for i, P_host in enumerate(batches):
-            if not P_host.is_pinned():
+        for i, P_in in enumerate(batches):
+            if host and not P_in.is_pinned():
                 raise RuntimeError("stream_host needs pinned host tensors (torch.Tensor.pin_memory())")
+            if not host and not P_in.is_cuda:
+                raise RuntimeError("stream_device needs CUDA tensors")
             slot = i & 1
-            graph, static_in, out, n_launch = self._net_graph(P_host, dropout, False, slot)
+            lane = lanes[slot]
+            graph, static_in, out, n_launch = self._net_graph(P_in, dropout, False, slot)
             if "instance" not in out or self.classes != ['plane', 'sphere', 'cylinder', 'cone']:
-                raise RuntimeError("stream_host supports the SPFN head layout [3, n_types, K <= 64] with all four fitters")
-            with torch.cuda.stream(copy_in):                  # H2D on its own stream, as early as the slot allows
-                if free[slot] is not None:
-                    copy_in.wait_event(free[slot])
-                static_in.copy_(P_host, non_blocking=True)
-                arrived = torch.cuda.Event()
-                arrived.record(copy_in)
-            main.wait_event(arrived)
-            if sent[slot] is not None:
-                main.wait_event(sent[slot])                   # the graph overwrites what that copy reads
-            if dropout:
-                self._sync_rng(P_host.shape)
-            graph.replay()
-            cuda_ops.count_launches(n_launch)
-            ready = torch.cuda.Event()
-            ready.record(main)
+                raise RuntimeError("streaming supports the SPFN head layout [3, n_types, K <= 64] with all four fitters")
+            if host:
+                with torch.cuda.stream(copy_in):              # H2D on its own stream, as early as the slot allows
+                    if free[slot] is not None:
+                        copy_in.wait_event(free[slot])
+                    static_in.copy_(P_in, non_blocking=True)
+                    arrived = torch.cuda.Event()
+                    arrived.record(copy_in)
+                lane.wait_event(arrived)
             res, tag = {}, "s%d_" % slot
-            with torch.cuda.stream(copier):                   # per-point results go home while the fitters run
-                copier.wait_event(ready)
-                for k, v in (("normals", out["X"]), ("instance", out["instance"]), ("type", out["type"])):
-                    res[k] = self._pinned(tag + k, v.shape, v.dtype)
-                    res[k].copy_(v, non_blocking=True)
-                copied = torch.cuda.Event()
-                copied.record(copier)
-            params, packed = self._fit_graphed(static_in, out)
-            hp = self._pinned(tag + "params", packed.shape, packed.dtype)
-            hp.copy_(packed, non_blocking=True)
-            o = 0
-            for k, v in params.items():
-                res[k] = hp[o:o + v.numel()].view(v.shape)
-                o += v.numel()
-            done = torch.cuda.Event()
-            done.record(main)
+            with torch.cuda.stream(lane):
+                if not host:
+                    static_in.copy_(P_in, non_blocking=True)
+                if sent[slot] is not None:
+                    lane.wait_event(sent[slot])               # the graph overwrites what that copy reads
+                if dropout:
+                    self._sync_rng(P_in.shape, slot)
+                graph.replay()
+                cuda_ops.count_launches(n_launch)
+                ready = torch.cuda.Event()
+                ready.record(lane)
+                copied = ready
+                if host:
+                    with torch.cuda.stream(copier):           # per-point results go home while the fitters run
+                        copier.wait_event(ready)
+                        for k, v in (("normals", out["X"]), ("instance", out["instance"]), ("type", out["type"])):
+                            res[k] = self._pinned(tag + k, v.shape, v.dtype)
+                            res[k].copy_(v, non_blocking=True)
+                        copied = torch.cuda.Event()
+                        copied.record(copier)
+                params, packed = self._fit_graphed(static_in, out)
+                if host:
+                    hp = self._pinned(tag + "params", packed.shape, packed.dtype)
+                    hp.copy_(packed, non_blocking=True)
+                    o = 0
+                    for k, v in params.items():
+                        res[k] = hp[o:o + v.numel()].view(v.shape)
+                        o += v.numel()
+                else:
+                    res = dict(out)
+                    res["parameters"], res["parameters_packed"] = params, packed
+                done = torch.cuda.Event()
+                done.record(lane)
             free[slot], sent[slot] = done, copied             # the fitters were the last readers of static_in
-            d2h = packed.numel() * 4 + sum(res[k].numel() * res[k].element_size() for k in ("normals", "instance", "type"))
+            h2d = P_in.numel() * 4 if host else 0
+            d2h = (packed.numel() * 4 + sum(res[k].numel() * res[k].element_size() for k in ("normals", "instance", "type"))
+                   if host else 0)
             if pending is not None:                           # hand out the previous batch while this one runs
                 pending[1].synchronize(); pending[2].synchronize()
                 yield pending[0], pending[3], pending[4]
-            pending = (res, done, copied, P_host.numel() * 4, d2h)
+            pending = (res, done, copied, h2d, d2h)
         if pending is not None:
             pending[1].synchronize(); pending[2].synchronize()
             yield pending[0], pending[3], pending[4]
+        for lane in lanes:
+            caller.wait_stream(lane)
 
     def _pinned(self, name, shape, dtype):
         t = self._pin.get(name)

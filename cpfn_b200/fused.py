@@ -576,8 +576,8 @@ def _side_stream(dev, which=0):
 _rng_state = {}
 
 
-def _rng_state_tensor(dev):
-    key = (dev.type, dev.index)
+def _rng_state_tensor(dev, slot=0):
+    key = (dev.type, dev.index, slot)
     t = _rng_state.get(key)
     if t is None:
         t = _rng_state[key] = torch.zeros(2, dtype=torch.int64, device=dev)      # {seed, offset}, read by the mask kernel
@@ -594,32 +594,33 @@ def dropout_plan(nelem, dev):
     return threads, ((max(nelem, 1) - 1) // (threads * 4) + 1) * 4
 
 
-def sync_rng(dev, nelem):
+def sync_rng(dev, nelem, slot=0):
     """Hand the current (seed, offset) of torch's CUDA generator to the device-side RNG state the mask kernel
     reads, and advance the generator exactly as F.dropout on `nelem` elements would: torch.manual_seed governs the
     masks, and they are the ones the reference's own F.dropout call draws on this GPU.  Stream-ordered (a one-thread
-    kernel); call it before every replay of a captured forward -- it cannot be part of the capture."""
+    kernel); call it before every replay of a captured forward -- it cannot be part of the capture.  ``slot``
+    selects one of several independent device-side states, for forwards that are in flight at the same time."""
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
     gen = torch.cuda.default_generators[idx]
     seed, offset = gen.initial_seed(), gen.get_offset()
     gen.set_offset(offset + dropout_plan(nelem, dev)[1])
-    state = _rng_state_tensor(dev)
+    state = _rng_state_tensor(dev, slot)
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().cpfn_rng_set(state.data_ptr(), seed & 0xFFFFFFFFFFFFFFFF, offset,
                                            torch.cuda.current_stream(dev).cuda_stream), "rng_set")
     cuda_ops.count_launches(1)
 
 
-def dropout_bits(B, C, N, dev, p=0.5):
+def dropout_bits(B, C, N, dev, p=0.5, slot=0):
     """Keep bits of F.dropout(x [B,C,N], p): (int32 [B*N, ceil(C/32)], scale of the kept values).  Outside a graph
     capture the RNG state is taken from torch's generator here; a captured launch reads whatever ``sync_rng`` wrote
     before the replay."""
     if not torch.cuda.is_current_stream_capturing():
-        sync_rng(dev, B * C * N)
+        sync_rng(dev, B * C * N, slot)
     words = (C + 31) // 32
     bits = torch.empty(B * N, words, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
-        _lib.check(_lib.lib().cpfn_dropout_mask_bits(_rng_state_tensor(dev).data_ptr(), B, C, N, 1.0 - p,
+        _lib.check(_lib.lib().cpfn_dropout_mask_bits(_rng_state_tensor(dev, slot).data_ptr(), B, C, N, 1.0 - p,
                                                      dropout_plan(B * C * N, dev)[0], bits.data_ptr(),
                                                      torch.cuda.current_stream(dev).cuda_stream), "dropout_mask_bits")
     cuda_ops.count_launches(1)
@@ -670,7 +671,7 @@ def _head_chain(model, device):
 
 
 @torch.no_grad()
-def pointnet2_forward(model, P, dropout=True):
+def pointnet2_forward(model, P, dropout=True, rng_slot=0):
     """Whole PointNet2 forward (reference pn2_network.py:38-73) on the fused kernels.
     P [B,N,3] float32 CUDA.  FP3, fc1 + bn1 + ReLU, dropout and the heads are ONE chain.
     Returns (heads [list of [B,N,o_i]], l3_feats [B,1024,1], output_feat [B,128,N], l1_xyz, l2_xyz)."""
@@ -701,7 +702,7 @@ def pointnet2_forward(model, P, dropout=True):
         # the reference's always-on dropout (pn2_network.py:63): same generator, same mask, as 1 bit per element.
         # (Not under the sampling: its CTAs would share the sampling SMs and stretch every round -- measured.)
         if dropout:
-            mask = dropout_bits(B, 128, N, dev, p=0.5)
+            mask = dropout_bits(B, 128, N, dev, p=0.5, slot=rng_slot)
         join = torch.cuda.Event()
         join.record(side)
     if piped is not None:
