@@ -5,8 +5,10 @@
 //   cpfn_gather_xyz        centroid gather new_xyz = xyz[fps_idx] (pointset_abstraction.py:50)
 //   cpfn_spfn_post         X = normalize(head0), W = softmax(head2) (Utils/training_utils.py:141-142)
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
+#include "nn_grid.cuh"
 
 namespace cpfn {
 namespace {
@@ -59,6 +61,35 @@ three_nn_weights_kernel(const float *__restrict__ unknown, const float *__restri
     const size_t o = (static_cast<size_t>(b) * n + j) * 3;
     weight[o] = __fdiv_rn(r1, s); weight[o + 1] = __fdiv_rn(r2, s); weight[o + 2] = __fdiv_rn(r3, s);
     idx[o] = i1; idx[o + 1] = i2; idx[o + 2] = i3;
+  }
+}
+
+// The same result through the shared-memory grid of nn_grid.cuh (known clouds of <= kNnGridMax points): ~50
+// candidates per query instead of all m.  Every CTA builds the grid once and answers kNnGridQ queries per thread.
+constexpr int kNnGridQ = 2;
+
+__global__ void __launch_bounds__(kGlueThreads)
+three_nn_weights_grid_kernel(const float *__restrict__ unknown, const float *__restrict__ known, int n, int m,
+                             float *__restrict__ weight, int32_t *__restrict__ idx) {
+  extern __shared__ __align__(16) unsigned char s_grid_raw[];
+  const int b = blockIdx.y;
+  NnGrid g;
+  float4 *recs;
+  int *cell_start;
+  nn_grid_build(known + static_cast<size_t>(b) * m * 3, m, s_grid_raw, g, recs, cell_start);
+#pragma unroll 1
+  for (int q = 0; q < kNnGridQ; ++q) {
+    const int j = (blockIdx.x * kNnGridQ + q) * kGlueThreads + threadIdx.x;
+    if (j >= n) continue;
+    const float *u = unknown + (static_cast<size_t>(b) * n + j) * 3;
+    const Nn3 r = nn_grid_query(__ldg(u), __ldg(u + 1), __ldg(u + 2), g, recs, cell_start);
+    const float r1 = __frcp_rn(__fadd_rn(__fsqrt_rn(r.d1), 1e-8f));
+    const float r2 = __frcp_rn(__fadd_rn(__fsqrt_rn(r.d2), 1e-8f));
+    const float r3 = __frcp_rn(__fadd_rn(__fsqrt_rn(r.d3), 1e-8f));
+    const float s = __fadd_rn(__fadd_rn(r1, r2), r3);
+    const size_t o = (static_cast<size_t>(b) * n + j) * 3;
+    weight[o] = __fdiv_rn(r1, s); weight[o + 1] = __fdiv_rn(r2, s); weight[o + 2] = __fdiv_rn(r3, s);
+    idx[o] = r.i1; idx[o + 1] = r.i2; idx[o + 2] = r.i3;
   }
 }
 
@@ -265,6 +296,9 @@ __global__ void rng_set_kernel(unsigned long long *state, unsigned long long see
 
 // One thread per (4 consecutive rows, 32-channel word).  Element (b, c, n) of the channel-major tensor has linear
 // index e = (b*C + c)*N + n; torch's thread (e/4) % T draws it in iteration (e/4) / T as component e % 4.
+// FAST: N % 4 == 0 and fewer than 2^32 elements -- the four rows of a thread share one Philox block per channel
+// and all index arithmetic is 32-bit (the division by T through a float estimate with an exact fix-up).
+template <bool FAST>
 __global__ void __launch_bounds__(kGlueThreads)
 dropout_bits_kernel(const unsigned long long *__restrict__ state, int C, int N, long long rows, float keep,
                     unsigned int T, int words, uint32_t *__restrict__ bits) {
@@ -274,7 +308,42 @@ dropout_bits_kernel(const unsigned long long *__restrict__ state, int C, int N, 
   const long long r0 = quad * 4;
   if (r0 >= rows) return;
   const unsigned long long seed = state[0], off4 = state[1] >> 2;
-  const uint2 key = make_uint2(static_cast<unsigned int>(seed), static_cast<unsigned int>(seed >> 32));
+  // the key schedule is the same for every block: ten (x, y) pairs, computed once
+  uint2 ks[10];
+  ks[0] = make_uint2(static_cast<unsigned int>(seed), static_cast<unsigned int>(seed >> 32));
+#pragma unroll
+  for (int r = 1; r < 10; ++r) ks[r] = make_uint2(ks[r - 1].x + 0x9E3779B9u, ks[r - 1].y + 0xBB67AE85u);
+  auto philox = [&](unsigned long long ctr, unsigned int sub) {
+    uint4 c = make_uint4(static_cast<unsigned int>(ctr), static_cast<unsigned int>(ctr >> 32), sub, 0u);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) c = philox_round(c, ks[r]);
+    return c;
+  };
+  const int c_end = min(C, cw * 32 + 32);
+  uint32_t w[4] = {0u, 0u, 0u, 0u};
+  if (FAST) {
+    const unsigned int b = static_cast<unsigned int>(r0 / N);
+    const unsigned int q0 = (b * static_cast<unsigned int>(C) * static_cast<unsigned int>(N) +
+                             static_cast<unsigned int>(r0 - static_cast<long long>(b) * N)) >> 2;   // e/4 at channel 0
+    const unsigned int qstep = static_cast<unsigned int>(N) >> 2;
+    const float inv_t = 1.0f / static_cast<float>(T);
+    for (int c = cw * 32; c < c_end; ++c) {
+      const unsigned int q = q0 + static_cast<unsigned int>(c) * qstep;
+      unsigned int k = static_cast<unsigned int>(static_cast<float>(q) * inv_t);
+      int sub = static_cast<int>(q - k * T);
+      if (sub < 0) { sub += static_cast<int>(T); --k; }
+      else if (sub >= static_cast<int>(T)) { sub -= static_cast<int>(T); ++k; }
+      const uint4 o = philox(off4 + k, static_cast<unsigned int>(sub));
+      const unsigned int bit = 1u << (c & 31);
+      if (keep_bit(o.x, keep)) w[0] |= bit;
+      if (keep_bit(o.y, keep)) w[1] |= bit;
+      if (keep_bit(o.z, keep)) w[2] |= bit;
+      if (keep_bit(o.w, keep)) w[3] |= bit;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) bits[(r0 + i) * words + cw] = w[i];
+    return;
+  }
   unsigned long long base[4];
   int nr = 0;
 #pragma unroll
@@ -288,8 +357,6 @@ dropout_bits_kernel(const unsigned long long *__restrict__ state, int C, int N, 
       base[i] = 0;
     }
   }
-  uint32_t w[4] = {0u, 0u, 0u, 0u};
-  const int c_end = min(C, cw * 32 + 32);
   for (int c = cw * 32; c < c_end; ++c) {
     unsigned long long have = ~0ull;
     uint4 o = make_uint4(0u, 0u, 0u, 0u);
@@ -302,9 +369,7 @@ dropout_bits_kernel(const unsigned long long *__restrict__ state, int C, int N, 
           unsigned long long k;
           if ((q >> 32) == 0) k = static_cast<unsigned int>(q) / T;       // 32-bit division in the common case
           else k = q / T;
-          const unsigned long long sub = q - k * T, ctr = off4 + k;
-          o = philox4x32_10(make_uint4(static_cast<unsigned int>(ctr), static_cast<unsigned int>(ctr >> 32),
-                                       static_cast<unsigned int>(sub), 0u), key);
+          o = philox(off4 + k, static_cast<unsigned int>(q - k * T));
           have = q;
         }
         const int comp = static_cast<int>(e & 3);
@@ -373,8 +438,14 @@ extern "C" int cpfn_dropout_mask_bits(const unsigned long long *rng_state, int B
   const long long threads = ((rows + 3) / 4) * words;
   const long long grid = (threads + kGlueThreads - 1) / kGlueThreads;
   if (grid > 0x7FFFFFFFll) return CPFN_EINVAL;
-  dropout_bits_kernel<<<static_cast<unsigned>(grid), kGlueThreads, 0, as_stream(stream)>>>(
-      rng_state, C, N, rows, keep_prob, static_cast<unsigned int>(torch_threads), words, bits);
+  const bool fast = (N % 4) == 0 && rows * C < 0xFFFFFFFFll && torch_threads < 0x7FFFFFFFll &&
+                    rows * C / 4 < (1ll << 24) * 64;   // float estimate of q / T stays within one of the quotient
+  if (fast)
+    dropout_bits_kernel<true><<<static_cast<unsigned>(grid), kGlueThreads, 0, as_stream(stream)>>>(
+        rng_state, C, N, rows, keep_prob, static_cast<unsigned int>(torch_threads), words, bits);
+  else
+    dropout_bits_kernel<false><<<static_cast<unsigned>(grid), kGlueThreads, 0, as_stream(stream)>>>(
+        rng_state, C, N, rows, keep_prob, static_cast<unsigned int>(torch_threads), words, bits);
   return check_launch();
 }
 
@@ -384,6 +455,14 @@ extern "C" int cpfn_three_nn_weights(const float *unknown, const float *known, i
   if (B < 0 || n < 0 || m < 0) return CPFN_EINVAL;
   if (B == 0 || n == 0) return CPFN_OK;
   if (!unknown || !weight || !idx || (m > 0 && !known) || B > 65535) return CPFN_EINVAL;
+  if (m >= 32 && m <= kNnGridMax && getenv("CPFN_NN_NO_GRID") == nullptr) {
+    const size_t gsmem = nn_grid_smem_bytes(m);
+    if (gsmem > 48 * 1024)
+      CPFN_CUDA_TRY(cudaFuncSetAttribute(three_nn_weights_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(gsmem)));
+    dim3 ggrid((n + kGlueThreads * kNnGridQ - 1) / (kGlueThreads * kNnGridQ), B);
+    three_nn_weights_grid_kernel<<<ggrid, kGlueThreads, gsmem, as_stream(stream)>>>(unknown, known, n, m, weight, idx);
+    return check_launch();
+  }
   dim3 grid((n + kGlueThreads - 1) / kGlueThreads, B);
   const size_t smem = sizeof(float4) * static_cast<size_t>(m < kNnTile ? (m > 0 ? m : 1) : kNnTile);
   three_nn_weights_kernel<<<grid, kGlueThreads, smem, as_stream(stream)>>>(unknown, known, n, m, weight, idx);

@@ -18,8 +18,10 @@
 //   * gradients: scatter-add with fire-and-forget fp32 RED (atomicAdd without
 //     a return value), destination zeroed on the same stream first.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
+#include "nn_grid.cuh"
 
 namespace cpfn {
 namespace {
@@ -69,6 +71,31 @@ three_nn_kernel(const float *__restrict__ unknown, const float *__restrict__ kno
     const size_t o = (static_cast<size_t>(b) * n + j) * 3;
     dist2[o] = b1; dist2[o + 1] = b2; dist2[o + 2] = b3;
     idx[o] = i1; idx[o + 1] = i2; idx[o + 2] = i3;
+  }
+}
+
+// Grid form (nn_grid.cuh) for known clouds of <= kNnGridMax points: same indices and distances, ~10x fewer
+// candidates per query.
+constexpr int kNnGridQ = 2;
+
+__global__ void __launch_bounds__(kNnThreads)
+three_nn_grid_kernel(const float *__restrict__ unknown, const float *__restrict__ known, int n, int m,
+                     float *__restrict__ dist2, int32_t *__restrict__ idx) {
+  extern __shared__ __align__(16) unsigned char s_grid_raw[];
+  const int b = blockIdx.y;
+  NnGrid g;
+  float4 *recs;
+  int *cell_start;
+  nn_grid_build(known + static_cast<size_t>(b) * m * 3, m, s_grid_raw, g, recs, cell_start);
+#pragma unroll 1
+  for (int q = 0; q < kNnGridQ; ++q) {
+    const int j = (blockIdx.x * kNnGridQ + q) * kNnThreads + threadIdx.x;
+    if (j >= n) continue;
+    const float *u = unknown + (static_cast<size_t>(b) * n + j) * 3;
+    const Nn3 r = nn_grid_query(__ldg(u), __ldg(u + 1), __ldg(u + 2), g, recs, cell_start);
+    const size_t o = (static_cast<size_t>(b) * n + j) * 3;
+    dist2[o] = r.d1; dist2[o + 1] = r.d2; dist2[o + 2] = r.d3;
+    idx[o] = r.i1; idx[o + 1] = r.i2; idx[o + 2] = r.i3;
   }
 }
 
@@ -183,6 +210,14 @@ extern "C" int cpfn_three_nn(const float *unknown, const float *known, int B, in
   if (B < 0 || n < 0 || m < 0) return CPFN_EINVAL;
   if (B == 0 || n == 0) return CPFN_OK;
   if (!unknown || !dist2 || !idx || (m > 0 && !known) || B > 65535) return CPFN_EINVAL;
+  if (m >= 32 && m <= kNnGridMax && getenv("CPFN_NN_NO_GRID") == nullptr) {
+    const size_t gsmem = nn_grid_smem_bytes(m);
+    if (gsmem > 48 * 1024)
+      CPFN_CUDA_TRY(cudaFuncSetAttribute(three_nn_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(gsmem)));
+    dim3 ggrid((n + kNnThreads * kNnGridQ - 1) / (kNnThreads * kNnGridQ), B);
+    three_nn_grid_kernel<<<ggrid, kNnThreads, gsmem, as_stream(stream)>>>(unknown, known, n, m, dist2, idx);
+    return check_launch();
+  }
   dim3 grid((n + kNnThreads - 1) / kNnThreads, B);
   const size_t smem = sizeof(float4) * static_cast<size_t>(m < kNnTile ? (m > 0 ? m : 1) : kNnTile);
   three_nn_kernel<<<grid, kNnThreads, smem, as_stream(stream)>>>(unknown, known, n, m, dist2, idx);

@@ -246,3 +246,42 @@ def test_fps_writes_the_centroids(B, N, m, cuda_dev):
     assert torch.equal(idx, idx2) and cen.shape == (B, m, 3)
     want = torch.gather(P, 1, idx.long().unsqueeze(2).expand(B, m, 3))
     assert torch.equal(cen, want)
+
+
+@pytest.mark.parametrize("name", ["shape", "lattice", "outside", "clustered", "m2048"])
+def test_three_nn_grid_equals_scan(cuda_dev, oracle_ops, name):
+    """The shared-memory grid search (csrc/nn_grid.cuh) against the exhaustive scan and the C oracle: indices and
+    squared distances bit for bit -- lattice clouds with many exactly equal distances (the smaller index must win),
+    queries far outside the known cloud's bounding box, known points piled up in a few cells."""
+    import os
+    from cpfn_b200 import cuda_ops, fused, synth
+    rng = np.random.default_rng(5)
+    if name == "shape":
+        u = synth.shape_batch(3, 8192, seed=3)[0]
+        k = u[:, :512].copy()
+    elif name == "lattice":
+        u = synth.lattice_cloud(2, 3000, seed=4, pitch=6)
+        k = u[:, :200].copy()
+    elif name == "outside":
+        k = synth.uniform_cloud(2, 300, seed=5) * np.float32(0.2)
+        u = synth.uniform_cloud(2, 2000, seed=6) * np.float32(3.0)
+    elif name == "clustered":
+        k = (rng.normal(size=(2, 400, 3)) * 0.01).astype(np.float32)
+        k[:, :5] += 1.0
+        u = synth.uniform_cloud(2, 1500, seed=7)
+    else:
+        u = synth.uniform_cloud(1, 5000, seed=8)
+        k = synth.uniform_cloud(1, 2048, seed=9)
+    U, Kn = torch.from_numpy(u).to(cuda_dev), torch.from_numpy(k).to(cuda_dev)
+    d_grid, i_grid = cuda_ops.three_nn(U, Kn)
+    w_grid, iw_grid = fused.three_nn_weights(U, Kn)
+    os.environ["CPFN_NN_NO_GRID"] = "1"
+    try:
+        d_scan, i_scan = cuda_ops.three_nn(U, Kn)
+        w_scan, iw_scan = fused.three_nn_weights(U, Kn)
+    finally:
+        os.environ.pop("CPFN_NN_NO_GRID")
+    assert torch.equal(i_grid, i_scan) and torch.equal(d_grid, d_scan)
+    assert torch.equal(iw_grid, iw_scan) and torch.equal(w_grid, w_scan)
+    d_ref, i_ref = oracle_ops.three_nn(u, k)
+    assert np.array_equal(i_grid.cpu().numpy(), i_ref) and np.array_equal(d_grid.cpu().numpy(), d_ref)
