@@ -210,7 +210,7 @@ extern "C" int cpfn_three_nn(const float *unknown, const float *known, int B, in
   if (B < 0 || n < 0 || m < 0) return CPFN_EINVAL;
   if (B == 0 || n == 0) return CPFN_OK;
   if (!unknown || !dist2 || !idx || (m > 0 && !known) || B > 65535) return CPFN_EINVAL;
-  if (m >= 32 && m <= kNnGridMax && getenv("CPFN_NN_NO_GRID") == nullptr) {
+  if (m >= kNnGridMin && m <= kNnGridMax && getenv("CPFN_NN_NO_GRID") == nullptr) {
     const size_t gsmem = nn_grid_smem_bytes(m);
     if (gsmem > 48 * 1024)
       CPFN_CUDA_TRY(cudaFuncSetAttribute(three_nn_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(gsmem)));

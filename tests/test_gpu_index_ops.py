@@ -261,12 +261,12 @@ def test_three_nn_grid_equals_scan(cuda_dev, oracle_ops, name):
         k = u[:, :512].copy()
     elif name == "lattice":
         u = synth.lattice_cloud(2, 3000, seed=4, pitch=6)
-        k = u[:, :200].copy()
+        k = u[:, :500].copy()
     elif name == "outside":
-        k = synth.uniform_cloud(2, 300, seed=5) * np.float32(0.2)
+        k = synth.uniform_cloud(2, 600, seed=5) * np.float32(0.2)
         u = synth.uniform_cloud(2, 2000, seed=6) * np.float32(3.0)
     elif name == "clustered":
-        k = (rng.normal(size=(2, 400, 3)) * 0.01).astype(np.float32)
+        k = (rng.normal(size=(2, 450, 3)) * 0.01).astype(np.float32)
         k[:, :5] += 1.0
         u = synth.uniform_cloud(2, 1500, seed=7)
     else:
