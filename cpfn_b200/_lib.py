@@ -61,6 +61,11 @@ SIGNATURES = {
     "cpfn_linear_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "cpfn_gather_xyz": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "cpfn_normalise_patches": (c_int, [c_void_p, ctypes.c_longlong, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "cpfn_seg_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "cpfn_label_membership_sums": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                           c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "cpfn_hungarian_matching": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
+                                        c_void_p]),
     "cpfn_zero_fill": (c_int, [c_void_p, c_size_t, c_void_p]),
     "cpfn_rng_set": (c_int, [c_void_p, ctypes.c_ulonglong, ctypes.c_ulonglong, c_void_p]),
     "cpfn_dropout_mask_bits": (c_int, [c_void_p, c_int, c_int, c_int, c_float, ctypes.c_longlong, c_void_p, c_void_p]),

@@ -4,4 +4,4 @@ libcpfn_b200.so: plane_fitter / sphere_fitter / cylinder_fitter / cone_fitter
 from . import fit, fitter_factory, losses_implementation  # noqa: F401
 from . import plane_fitter, sphere_fitter, cylinder_fitter, cone_fitter  # noqa: F401
 from . import differentiable_tls, geometry_utils  # noqa: F401
-from . import metric_implementation, residues  # noqa: F401
+from . import metric_implementation, residues, seg  # noqa: F401

@@ -7,7 +7,7 @@ autograd.  Any other name of the reference module is forwarded to the reference'
 on sys.path (see _reference.py): those functions are not on the hot path."""
 import torch
 
-from . import _reference, fit, residues
+from . import _reference, fit, residues, seg
 from . import plane_fitter, sphere_fitter, cylinder_fitter, cone_fitter
 
 _CLASS_KEYS = {
@@ -82,10 +82,21 @@ def compute_residue_loss(parameters, matching_indices, points_per_instance, T_gt
     residue_loss = torch.gather(residue_losses, 2, T_gt.unsqueeze(2)).squeeze(2)
     return residue_loss, residue_per_point_array
 
+def hungarian_matching(W_pred, I_gt):
+    """SPFN/losses_implementation.py:11-30 on the device (spfn/seg.py): no host round trip, no scipy."""
+    return seg.hungarian_matching(W_pred, I_gt)
+
+
+def compute_miou_loss(W, I_gt, matching_indices, div_eps=1e-10):
+    """SPFN/losses_implementation.py:77-89 (spfn/seg.py)."""
+    return seg.compute_miou_loss(W, I_gt, matching_indices, div_eps)
+
 
 def __getattr__(name):
     ref = _reference.load("losses_implementation", {"compute_parameters": compute_parameters,
-                                                    "compute_residue_loss": compute_residue_loss})
+                                                    "compute_residue_loss": compute_residue_loss,
+                                                    "hungarian_matching": hungarian_matching,
+                                                    "compute_miou_loss": compute_miou_loss})
     if ref is not None and hasattr(ref, name):
         return getattr(ref, name)
     raise AttributeError("cpfn_b200.spfn.losses_implementation has no '%s' (not a hot-path function; put the "

@@ -3,7 +3,7 @@
 reference's own file when its checkout is on sys.path (_reference.py)."""
 import torch
 
-from . import _reference, losses_implementation, residues
+from . import _reference, losses_implementation, residues, seg
 
 
 _LUT = {}
@@ -36,10 +36,15 @@ def compute_P_coverage(P, T, matching_indices, predicted_parameters, epsilon, cl
     cov = residues.p_coverage(P, lut[prim_type], matching_indices, predicted_parameters, [epsilon] if single else epsilon)
     return cov[:, 0] if single else cov
 
+def hungarian_matching(W_pred, I_gt):
+    """SPFN/metric_implementation.py:9-30 on the device: (matching_indices int64 [B,K], mask bool [B,K])."""
+    return seg.hungarian_matching(W_pred, I_gt, with_mask=True)
+
 
 def __getattr__(name):
     ref = _reference.load("metric_implementation", {"get_residual_loss": get_residual_loss,
-                                                    "compute_P_coverage": compute_P_coverage})
+                                                    "compute_P_coverage": compute_P_coverage,
+                                                    "hungarian_matching": hungarian_matching})
     if ref is not None and hasattr(ref, name):
         return getattr(ref, name)
     raise AttributeError("cpfn_b200.spfn.metric_implementation has no '%s' (not a hot-path function; put the "

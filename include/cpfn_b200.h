@@ -282,6 +282,26 @@ CPFN_API int cpfn_gather_xyz(const float *xyz, const int32_t *idx, int B, int N,
 CPFN_API int cpfn_linear_rows(const float *x, const float *W, const float *bias, int rows, int cin,
                               int cout, int ldo, float *out, cpfn_stream_t stream);
 
+/* ---------------------------------------------------------------------------
+ * Segmentation glue of the losses / metrics.
+ * ------------------------------------------------------------------------- */
+
+/* One pass over the memberships: S[b,g,k] = sum over the points with label g of W[b,n,k] (g < G), colsum[b,k] = sum over
+ * ALL points, count[b,g] = number of points with label g, n_gt[b] = max label + 1 -- everything
+ * SPFN/losses_implementation.py:11-30 (hungarian_matching) and :77-89 (compute_miou_loss) need from W and I_gt
+ * ([B,N] int32 or int64, -1 = no label).  K, G <= 64.  Deterministic (no floating-point atomics). */
+CPFN_API size_t cpfn_seg_workspace_bytes(int B, int N, int K, int G);
+CPFN_API int cpfn_label_membership_sums(const float *W, const void *labels, int labels_are_int64, int B, int N, int K,
+                                        int G, float *S, float *colsum, float *count, int32_t *n_gt, void *workspace,
+                                        size_t workspace_bytes, cpfn_stream_t stream);
+
+/* hungarian_matching on the device: IoU cost S / clamp(count + colsum - S, 1e-10) for the n_gt[b] ground-truth rows,
+ * maximum-weight assignment with scipy.optimize.linear_sum_assignment's algorithm and tie-breaking (one warp per
+ * sample, K <= 32).  matching int64 [B,K] (entries >= n_gt[b] are 0, as in the reference), mask u8 [B,K] | NULL
+ * (metric_implementation's second result). */
+CPFN_API int cpfn_hungarian_matching(const float *S, const float *colsum, const float *count, const int32_t *n_gt, int B,
+                                     int K, int G, long long *matching, unsigned char *mask, cpfn_stream_t stream);
+
 /* Stream-ordered zero fill (cudaMemsetAsync): the pooled output of a set-abstraction chain that runs as several
  * column windows is cleared once by the caller (cpfn_mlp_chain_t.out_prezeroed). */
 CPFN_API int cpfn_zero_fill(void *dst, size_t bytes, cpfn_stream_t stream);

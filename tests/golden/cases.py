@@ -244,3 +244,30 @@ def lowres_cases():
     lat = np.concatenate([lat, lat[:100]])
     out["lattice"] = (lat, (np.arange(len(lat)) % 7).astype(np.int32), 150, 233)
     return out
+
+
+def seg_cases():
+    """name -> (W_pred float32 [B,N,K], I_gt int64 [B,N]) for hungarian_matching / compute_miou_loss.
+    'soft': soft-maxed memberships of shape clouds (generic costs, no ties); 'hard': one-hot predictions that are a
+    permutation of the ground truth plus unused slots and an absent ground-truth label (all-zero cost rows and exact
+    ties: the solver's tie-breaking decides); 'background': points labelled -1; 'few': two ground-truth labels."""
+    out = {}
+    P, X, W, I = synth.shape_batch(3, 2048, seed=61, k_slots=28)
+    out["soft"] = (W.astype(np.float32), I.astype(np.int64))
+    rng = np.random.RandomState(62)
+    B, N, K = 4, 1500, 12
+    I = rng.randint(0, 9, size=(B, N)).astype(np.int64)
+    I[I == 4] = 5                                                  # label 4 never occurs: an all-zero cost row
+    perm = np.stack([rng.permutation(K) for _ in range(B)])
+    hard = np.zeros((B, N, K), np.float32)
+    for b in range(B):
+        hard[b, np.arange(N), perm[b][I[b]]] = 1.0
+    out["hard"] = (hard, I)
+    W2 = rng.rand(2, 1000, 24).astype(np.float32)
+    W2 /= W2.sum(2, keepdims=True)
+    I2 = rng.randint(-1, 10, size=(2, 1000)).astype(np.int64)
+    out["background"] = (W2, I2)
+    W3 = rng.rand(5, 700, 28).astype(np.float32)
+    I3 = rng.randint(0, 2, size=(5, 700)).astype(np.int64)
+    out["few"] = (W3, I3)
+    return out
