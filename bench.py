@@ -346,12 +346,12 @@ def run_ours(args):
     seq_ms = sum(a.elapsed_time(b) for a, b in ev)
     dev_ms, pipelined_value = seq_ms, False
     if use_graph and not os.environ.get("CPFN_BENCH_NO_PIPELINE"):
-        # Throughput with two batches in flight (GlobalSPFN.stream_device): batch i+1's furthest point sampling -- a
-        # chain of dependent rounds on 64 SMs -- runs beside batch i's MLP chains and fitters.  The K timed steps cycle
+        # Throughput with several batches in flight (GlobalSPFN.stream_device, 6 graph lanes): a batch's furthest point
+        # sampling -- a chain of dependent rounds on 64 SMs -- runs beside the other batches' MLP chains and fitters.  The K timed steps cycle
         # through 96 distinct device-resident batches (151 MB > the 126 MB L2), so every step reads its input from HBM.
         g = torch.Generator(device=dev).manual_seed(17)
         big = [dev_inputs[j % n_in][:, torch.randperm(N_POINTS, device=dev, generator=g)].contiguous() for j in range(96)]
-        for _ in eng.stream_device(big[i % 96] for i in range(max(4, args.warmup))):
+        for _ in eng.stream_device(big[i % 96] for i in range(max(12, args.warmup))):
             pass
         barrier()
         launches0 = cuda_ops.LAUNCHES
@@ -406,7 +406,7 @@ def run_ours(args):
     lat_s = time.perf_counter() - t0
     e2e_s, pipelined = lat_s, False
     if use_graph:
-        for _ in eng.stream_host(host_inputs[i % n_in] for i in range(max(5, args.warmup))):
+        for _ in eng.stream_host(host_inputs[i % n_in] for i in range(max(12, args.warmup))):
             pass
         barrier()
         t0 = time.perf_counter()
@@ -471,14 +471,14 @@ def run_ours(args):
                    "heads": [3, 4, K_SLOTS],
                    "l2": ("inputs larger than L2: the timed steps cycle through 96 distinct device-resident batches (151 MB)"
                           if pipelined_value else "flushed between timed iterations (512 MB memset outside the event pairs)"),
-                   "pipeline": ("two batches in flight (GlobalSPFN.stream_device): every batch runs the full forward + fit; "
+                   "pipeline": ("several batches in flight (GlobalSPFN.stream_device, CPFN_LANES graph lanes, default 6): every batch runs the full forward + fit; "
                                 "sequential_ms_per_step is one batch at a time with the L2 flushed in between"
                                 if pipelined_value else "one batch at a time"),
                    "sharding": "clouds sharded across ranks, no data-path collective", "fused_mlp": bool(fused.available()),
                    "cuda_graph": bool(use_graph)},
         "e2e": {"value": total_points / (e2e_ms * 1e-3 / args.steps), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
-                "api": "GlobalSPFN.stream_host (two batches in flight; every step does its full H2D, forward, fit, D2H)"
+                "api": "GlobalSPFN.stream_host (several batches in flight; every step does its full H2D, forward, fit, D2H)"
                        if pipelined else "GlobalSPFN.run_host",
                 "single_call_latency_ms": lat_ms / args.steps},
         "gpu_launches": launches, "sequential_ms_per_step": seq_ms / args.steps,

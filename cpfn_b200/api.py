@@ -6,6 +6,8 @@ reference PointNet2/pn2_network.py:38-73) -> X normalised, W soft-maxed
 (SPFN/losses_implementation.py:255-278).  ``run_host`` is the same call on HOST buffers
 (pinned staging, host<->device copies included) -- what bench.py reports as ``e2e``.
 """
+import os
+
 import torch
 
 from . import cuda_ops
@@ -166,44 +168,48 @@ class GlobalSPFN:
 
     @torch.no_grad()
     def stream_host(self, batches, dropout=True):
-        """``run_host`` over a sequence of pinned host batches of ONE shape, two batches in flight: while batch i
-        is on the SMs, batch i+1's clouds are already crossing PCIe into a second set of graph buffers, and batch
-        i's per-point results travel back under its own fitters.  Every batch still does its full H2D, forward,
-        fit and D2H; only their overlap changes.  Yields (results, h2d_bytes, d2h_bytes) in order; the result
-        tensors of a batch are pinned buffers that are reused two batches later."""
+        """``run_host`` over a sequence of pinned host batches of ONE shape with several batches in flight (see
+        ``_stream``): while a batch is on the SMs, the next ones' clouds are already crossing PCIe into their own
+        graph buffers, and its per-point results travel back under its own fitters.  Every batch still does its full
+        H2D, forward, fit and D2H; only their overlap changes.  Yields (results, h2d_bytes, d2h_bytes) in order; the
+        result tensors of a batch are pinned buffers that are reused CPFN_LANES batches later."""
         yield from self._stream(batches, dropout, host=True)
 
     @torch.no_grad()
     def stream_device(self, batches, dropout=True):
         """The same pipeline for batches that already live on the device: yields (forward dictionary incl.
         ``parameters``, 0, 0) per batch.  The tensors are the static buffers of the batch's graph slot: valid until
-        the batch after next is submitted."""
+        CPFN_LANES further batches have been submitted."""
         yield from self._stream(batches, dropout, host=False)
 
     def _stream(self, batches, dropout, host):
-        """Two graph slots, each with its own stream, input / output buffers and RNG state.  Consecutive batches
-        alternate between the slots, so batch i+1's sampling -- a chain of dependent rounds that keeps 64 of the 148
-        SMs busy -- runs beside batch i's MLP chains and fitters instead of in front of them (the GPU interleaves
-        the two graphs; each graph is unchanged and so are its results)."""
+        """Several graph slots ("lanes", 6 by default, CPFN_LANES), each with its own stream, input / output buffers
+        and RNG state.  Consecutive batches rotate through the lanes, so a batch's sampling -- a chain of dependent
+        rounds that keeps 64 of the 148 SMs busy -- and the latency-bound hand-offs inside its MLP chains run beside
+        the other batches' work instead of in front of it (the GPU interleaves the graphs; each graph is unchanged
+        and so are its results)."""
         from . import fused
         dev = self.device
         caller = torch.cuda.current_stream(dev)
-        lanes = self.__dict__.setdefault("_lanes", [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)])
+        n_lanes = max(1, int(os.environ.get("CPFN_LANES", "6")))       # measured: 2 -> 0.734, 4 -> 0.632, 6 -> 0.611, 8 -> 0.617 ms
+        if len(self.__dict__.get("_lanes", ())) != n_lanes:
+            self._lanes = [torch.cuda.Stream(device=dev) for _ in range(n_lanes)]
+        lanes = self._lanes
         copy_in = self.__dict__.setdefault("_copy_in", torch.cuda.Stream(device=dev))
         copier = fused._side_stream(dev)
-        free = [None, None]                                   # slot's input may be overwritten after this event
-        sent = [None, None]                                   # slot's per-point outputs have left the device
+        free = [None] * n_lanes                               # slot's input may be overwritten after this event
+        sent = [None] * n_lanes                               # slot's per-point outputs have left the device
+        inflight = []
         start = torch.cuda.Event()
         start.record(caller)
         for lane in lanes:
             lane.wait_event(start)                            # whatever the caller enqueued before comes first
-        pending = None
         for i, P_in in enumerate(batches):
             if host and not P_in.is_pinned():
                 raise RuntimeError("stream_host needs pinned host tensors (torch.Tensor.pin_memory())")
             if not host and not P_in.is_cuda:
                 raise RuntimeError("stream_device needs CUDA tensors")
-            slot = i & 1
+            slot = i % n_lanes
             lane = lanes[slot]
             graph, static_in, out, n_launch = self._net_graph(P_in, dropout, False, slot)
             if "instance" not in out or self.classes != ['plane', 'sphere', 'cylinder', 'cone']:
@@ -254,13 +260,14 @@ class GlobalSPFN:
             h2d = P_in.numel() * 4 if host else 0
             d2h = (packed.numel() * 4 + sum(res[k].numel() * res[k].element_size() for k in ("normals", "instance", "type"))
                    if host else 0)
-            if pending is not None:                           # hand out the previous batch while this one runs
-                pending[1].synchronize(); pending[2].synchronize()
-                yield pending[0], pending[3], pending[4]
-            pending = (res, done, copied, h2d, d2h)
-        if pending is not None:
-            pending[1].synchronize(); pending[2].synchronize()
-            yield pending[0], pending[3], pending[4]
+            inflight.append((res, done, copied, h2d, d2h))
+            if len(inflight) >= n_lanes:                      # hand out the oldest batch while the newer ones run
+                r = inflight.pop(0)
+                r[1].synchronize(); r[2].synchronize()
+                yield r[0], r[3], r[4]
+        for r in inflight:
+            r[1].synchronize(); r[2].synchronize()
+            yield r[0], r[3], r[4]
         for lane in lanes:
             caller.wait_stream(lane)
 

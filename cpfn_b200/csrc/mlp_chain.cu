@@ -105,6 +105,7 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
 // try_wait parks the thread in hardware until the phase completes or the suspend-time hint expires; with the default
 // (short) hint the producer, the MMA thread and 256 epilogue threads re-issue it continuously and took ~24 % of all
 // issue slots of the chain kernels (ncu source counters, round 1).
+__device__ uint32_t g_wait_hint = 0x989680u;      // suspend-time hint (ns) of the mbarrier waits; tuning knob
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
@@ -114,7 +115,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
       "@P1 bra DONE;\n\t"
       "bra WAIT_LOOP;\n\t"
       "DONE:\n\t"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(g_wait_hint) : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -1184,6 +1185,14 @@ extern "C" int cpfn_mlp_pack_weights_host(const float *W, int cout, int cin, voi
 
 extern "C" int cpfn_mlp_chain(const cpfn_mlp_chain_t *c, cpfn_stream_t stream) {
   using namespace cpfn;
+  static bool hint_set = false;
+  if (!hint_set) {
+    hint_set = true;
+    if (const char *e = getenv("CPFN_CHAIN_WAIT_HINT")) {
+      const uint32_t h = static_cast<uint32_t>(strtoul(e, nullptr, 0));
+      cudaMemcpyToSymbol(g_wait_hint, &h, sizeof(h));
+    }
+  }
   if (!c || c->n_layers <= 0 || c->n_layers > kMaxLayers || c->B < 0 || c->cols_per_cloud < 0) return CPFN_EINVAL;
   if (c->B == 0 || c->cols_per_cloud == 0) return CPFN_OK;
   if (!c->weights || !c->out) return CPFN_EINVAL;
