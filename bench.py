@@ -267,6 +267,62 @@ def cascade_bench(dev, rank, world, steps=10, warmup=3):
     return records
 
 
+def training_bench(dev, rank, world, steps=4, warmup=2):
+    """BASELINE configs[3]: one LocalSPFN optimisation step (forward, the reference's Local loss configuration,
+    backward, gradient all-reduce, Adam) on a batch of 32 patches x 8192 points, K = 21, the patches sharded over the
+    ranks (cpfn_b200/train.py).  The loss glue is the reference's own code (baseline/_ref), the ops are this package's
+    kernels with their scatter-add backward, the shared MLPs are torch's convolution / batch-norm modules."""
+    try:
+        ref_dir = os.path.join(ROOT, "baseline", "_ref")
+        for root in (ref_dir, "/root/reference"):
+            if os.path.isfile(os.path.join(root, "SPFN", "losses_implementation.py")):
+                if root not in sys.path:
+                    sys.path.insert(0, root)
+                break
+        else:
+            return {"unavailable": "the loss glue (reference SPFN/losses_implementation.py) is not staged"}
+        import warnings
+        warnings.filterwarnings("ignore")
+        from cpfn_b200 import synth, train
+        from cpfn_b200.pn2_network import PointNet2
+        model = PointNet2(dim_input=3, dim_pos=3, output_sizes=[3, 4, 21]).to(dev)
+        model.load_state_dict(model_state(model.state_dict()))
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+        B = 32
+        full = synth.training_batch(B, N_POINTS, seed=77, k_slots=21)
+        t = lambda a: torch.from_numpy(a).to(dev)
+        batch = {k: t(v) for k, v in full.items() if k != "gt_parameters"}
+        batch["gt_parameters"] = {k: t(v) for k, v in full["gt_parameters"].items()}
+        mine = train.shard_batch(batch, rank, world)
+        del batch
+        wall, stages = [], []
+        for i in range(warmup + steps):
+            if world > 1:
+                import torch.distributed as dist
+                dist.barrier()
+            torch.cuda.synchronize()
+            tm = {}
+            t0 = time.perf_counter()
+            train.train_step(model, opt, mine, train.LOCAL_MULTIPLIERS, timings=tm)
+            torch.cuda.synchronize()
+            wall.append((time.perf_counter() - t0) * 1e3)
+            names = ("start", "forward", "backward", "all_reduce", "step")
+            stages.append([tm[a].elapsed_time(tm[b]) for a, b in zip(names[:-1], names[1:])])
+        ms = torch.tensor([float(np.mean(wall[warmup:]))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        st = np.mean(np.array(stages[warmup:]), axis=0)
+        del model, opt, mine
+        torch.cuda.empty_cache()
+        return {"workload": "LocalSPFN training step, 32 patches x 8192 points, K = 21, Local loss configuration, Adam",
+                "n_gpus": world, "patches_per_rank": B // world, "ms_per_step": float(ms[0]),
+                "patches_per_s": B / (float(ms[0]) * 1e-3),
+                "stages_ms_rank0": {"forward+losses": float(st[0]), "backward": float(st[1]),
+                                    "gradient_all_reduce": float(st[2]), "optimizer": float(st[3])}}
+    except Exception as e:                                   # evidence only: never fails the bench
+        return {"unavailable": "%s: %s" % (type(e).__name__, e)}
+
+
 class OpTimer:
     """Per-op CUDA-event timing on the launching stream (used in a separate profiling pass
     after the timed region, so it does not perturb the headline number)."""
@@ -420,6 +476,8 @@ def run_ours(args):
     barrier()
     cascade = cascade_bench(dev, rank, world) if not os.environ.get("CPFN_BENCH_NO_CASCADE") else []
     barrier()
+    training = training_bench(dev, rank, world) if not os.environ.get("CPFN_BENCH_NO_TRAIN") else {"unavailable": "skipped"}
+    barrier()
     t = torch.tensor([dev_ms, e2e_s * 1e3, lat_s * 1e3, seq_ms], dtype=torch.float64, device=dev)
     if world > 1:
         import torch.distributed as dist
@@ -486,7 +544,7 @@ def run_ours(args):
         "fits_per_s": 4 * world * B_PER_GPU * K_SLOTS / (ms_per_step * 1e-3),
         "breakdown_us": breakdown, "roofline": roofline,
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
-        "gpu_reference": g_ref, "module_api": mod_api, "cascade": cascade,
+        "gpu_reference": g_ref, "module_api": mod_api, "cascade": cascade, "training": training,
         "clocks": clocks,
     }
     _emit(line)

@@ -137,3 +137,30 @@ def network_state(template, seed=7):
             fan_in = shape[1]
             out[name] = (rng.normal(size=shape) * np.sqrt(2.0 / fan_in)).astype(np.float32)
     return out
+
+
+def training_batch(batch, n_points, seed, k_slots=21, n_gt_points=512):
+    """Synthetic supervised batch in the layout of Utils/training_utils.py:119-131: P, X_gt [B,N,3], I_gt int64 [B,N]
+    (12 ground-truth primitives per cloud), T_gt int64 [B,K] (type ids in the order sphere=0, plane=1, cylinder=2,
+    cone=3 of the reference's configuration), points_per_instance [B,K,n_gt_points,3] (points of every ground-truth
+    primitive, zeros for the unused slots) and the ground-truth axes plane_normal / cylinder_axis / cone_axis [B,K,3]
+    (taken from the analytic normals: exact for planes, a per-primitive mean direction otherwise -- the losses only
+    need plausible unit vectors)."""
+    P, X, _, I = shape_batch(batch, n_points, seed, k_slots=k_slots)
+    rng = np.random.default_rng(seed + 999)
+    type_of = np.array([1, 1, 1, 0, 0, 0, 2, 2, 2, 3, 3, 3], dtype=np.int64)      # shape_cloud: 3 planes, 3 spheres, ...
+    T_gt = np.zeros((batch, k_slots), np.int64)
+    T_gt[:, :12] = type_of
+    ppi = np.zeros((batch, k_slots, n_gt_points, 3), np.float32)
+    axes = np.zeros((batch, k_slots, 3), np.float32)
+    axes[..., 2] = 1.0
+    for b in range(batch):
+        for g in range(12):
+            ids = np.flatnonzero(I[b] == g)
+            if len(ids):
+                ppi[b, g] = P[b, rng.choice(ids, n_gt_points, replace=len(ids) < n_gt_points)]
+                m = X[b, ids].mean(0)
+                axes[b, g] = m / max(np.linalg.norm(m), 1e-6)
+    return {"P": P.astype(np.float32), "X_gt": X.astype(np.float32), "I_gt": I.astype(np.int64), "T_gt": T_gt,
+            "points_per_instance": ppi,
+            "gt_parameters": {"plane_normal": axes.copy(), "cylinder_axis": axes.copy(), "cone_axis": axes.copy()}}
