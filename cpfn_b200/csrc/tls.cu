@@ -79,8 +79,7 @@ template <int PASS>
 __global__ void __launch_bounds__(kTlsThreads, 2)
 tls_pass_kernel(const float *__restrict__ P, const float *__restrict__ X,
                 const float *__restrict__ W, const double *__restrict__ state,
-                double *__restrict__ part, int N, int K, int G, int CP, int iters, int chunks,
-                double *__restrict__ pivots) {
+                double *__restrict__ part, int N, int K, int G, int CP, int iters, int chunks) {
   constexpr int F = NFeat<PASS>::F;
   __shared__ float s_piv[4];                 // PASS 1: the CTA's pivot for the first and second normal moments
   extern __shared__ float4 s_pts[];          // [CP] positions (+ |p|^2), [CP] normals (+ p.x)
@@ -135,7 +134,7 @@ tls_pass_kernel(const float *__restrict__ P, const float *__restrict__ X,
     __syncthreads();
     if (PASS == 1 && it == 0) {
       // Pivot of this CTA's normal moments: the plain mean of the normals it staged first.  sum w x and sum w x x^T
-      // are accumulated about it and shifted back to the origin in fp64 by solve1 (exact algebra per CTA): when the
+      // are accumulated about it and shifted back to the origin in fp64 when the CTA writes its partials: when the
       // normals a slot weights are concentrated around the cloud's mean normal -- near-uniform memberships -- the
       // fp32 terms are small and the scatter about the slot mean, which the cone axis comes from, keeps its digits.
       float a = 0.f, bq = 0.f, c = 0.f;
@@ -255,9 +254,26 @@ tls_pass_kernel(const float *__restrict__ P, const float *__restrict__ X,
   }
   __syncthreads();
   double *out = part + (static_cast<size_t>(b) * chunks + chunk) * K * kFP;
-  for (int o = t; o < K * kFP; o += kTlsThreads)
-    if ((o & (kFP - 1)) < F) out[o] = tot[o];
-  if (PASS == 1 && t < 3) pivots[(static_cast<size_t>(b) * chunks + chunk) * 4 + t] = static_cast<double>(s_piv[t]);
+  for (int o = t; o < K * kFP; o += kTlsThreads) {
+    const int f = o & (kFP - 1);
+    if (f >= F) continue;
+    double v = tot[o];
+    if (PASS == 1 && f >= 5 && f <= 13) {
+      // features 5-13 were accumulated about the CTA's pivot c: back to the origin, in fp64 (exact algebra):
+      //   sum w x = s + Sw c,   sum w x_i x_j = M_ij + c_i s_j + s_i c_j + Sw c_i c_j
+      const double *row = tot + (o - f);
+      const double sw = row[0];
+      const double c[3] = {static_cast<double>(s_piv[0]), static_cast<double>(s_piv[1]), static_cast<double>(s_piv[2])};
+      if (f < 8) {
+        v += sw * c[f - 5];
+      } else {
+        const int ij[6][2] = {{0, 0}, {0, 1}, {0, 2}, {1, 1}, {1, 2}, {2, 2}};
+        const int i = ij[f - 8][0], j = ij[f - 8][1];
+        v += c[i] * row[5 + j] + row[5 + i] * c[j] + sw * c[i] * c[j];
+      }
+    }
+    out[o] = v;
+  }
 }
 
 // ---- small dense algebra in registers (fp64) -------------------------------------------------
@@ -387,30 +403,13 @@ __device__ __forceinline__ double sum_partials(const double *part, int b, int k,
 constexpr int kSolveWarps = 4;
 
 __global__ void __launch_bounds__(kSolveWarps * 32)
-tls_solve1_kernel(const double *__restrict__ part, const double *__restrict__ pivots, double *__restrict__ state,
-                  int BK, int K, int chunks) {
+tls_solve1_kernel(const double *__restrict__ part, double *__restrict__ state, int BK, int K, int chunks) {
   __shared__ double sm[kSolveWarps][kFP];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bk = blockIdx.x * kSolveWarps + warp;
   if (bk >= BK) return;
   const int b = bk / K, k = bk - b * K;
-  double v = 0.0;
-  if (lane < kF1 && (lane < 5 || lane > 13)) {
-    v = sum_partials(part, b, k, K, chunks, lane);
-  } else if (lane < kF1) {
-    // features 5-13 were accumulated about each CTA's pivot c: back to the origin, chunk by chunk, in fp64:
-    //   sum w x = s + Sw c,   sum w x_i x_j = M_ij + c_i s_j + s_i c_j + Sw c_i c_j
-    const int ij[9][2] = {{0, 0}, {1, 1}, {2, 2}, {0, 0}, {0, 1}, {0, 2}, {1, 1}, {1, 2}, {2, 2}};
-    const int i = ij[lane - 5][0], j = ij[lane - 5][1];
-    for (int c = 0; c < chunks; ++c) {
-      const double *p = part + ((static_cast<size_t>(b) * chunks + c) * K + k) * kFP;
-      const double *pv = pivots + (static_cast<size_t>(b) * chunks + c) * 4;
-      const double sw = p[0];
-      if (lane < 8) v += p[lane] + sw * pv[i];
-      else v += p[lane] + pv[i] * p[5 + j] + p[5 + i] * pv[j] + sw * pv[i] * pv[j];
-    }
-  }
-  sm[warp][lane] = v;
+  sm[warp][lane] = lane < kF1 ? sum_partials(part, b, k, K, chunks, lane) : 0.0;
   __syncwarp();
   const double *m = sm[warp];
   double *st = state + static_cast<size_t>(bk) * kState;
@@ -680,7 +679,7 @@ moments_grad_x_kernel(const float *__restrict__ P, const float *__restrict__ X, 
 }
 
 struct TlsWs {
-  double *state, *part, *pivots;
+  double *state, *part;
   size_t bytes;
 };
 
@@ -688,11 +687,9 @@ TlsWs tls_carve(void *ws, int B, int K, const TlsGeom &g) {
   TlsWs w;
   const size_t n_state = static_cast<size_t>(B) * K * kState;
   const size_t n_part = static_cast<size_t>(B) * g.chunks * K * kFP;
-  const size_t n_piv = static_cast<size_t>(B) * g.chunks * 4;
   w.state = static_cast<double *>(ws);
   w.part = w.state + n_state;
-  w.pivots = w.part + n_part;
-  w.bytes = (n_state + n_part + n_piv) * sizeof(double);
+  w.bytes = (n_state + n_part) * sizeof(double);
   return w;
 }
 
@@ -729,10 +726,10 @@ extern "C" int cpfn_fit_primitives(const float *P, const float *W, const float *
   const int BK = B * K;
   const int sgrid = (BK + kSolveWarps - 1) / kSolveWarps;
   tls_pass_kernel<1><<<grid, kTlsThreads, smem, st>>>(P, X, W, ws.state, ws.part, N, K, g.G, g.CP,
-                                                      g.iters, g.chunks, ws.pivots);
-  tls_solve1_kernel<<<sgrid, kSolveWarps * 32, 0, st>>>(ws.part, ws.pivots, ws.state, BK, K, g.chunks);
+                                                      g.iters, g.chunks);
+  tls_solve1_kernel<<<sgrid, kSolveWarps * 32, 0, st>>>(ws.part, ws.state, BK, K, g.chunks);
   tls_pass_kernel<2><<<grid, kTlsThreads, smem, st>>>(P, nullptr, W, ws.state, ws.part, N, K, g.G, g.CP,
-                                                      g.iters, g.chunks, nullptr);     // pass 2 reads no normals
+                                                      g.iters, g.chunks);              // pass 2 reads no normals
   tls_solve2_kernel<<<sgrid, kSolveWarps * 32, 0, st>>>(ws.part, ws.state, out, BK, K, g.chunks);
   return check_launch();
 }
@@ -755,7 +752,7 @@ extern "C" int cpfn_weighted_moments(const float *P, const float *X, const float
   if (smem > 48 * 1024)
     CPFN_CUDA_TRY(cudaFuncSetAttribute(tls_pass_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   tls_pass_kernel<4><<<dim3(g.chunks, B), kTlsThreads, smem, st>>>(P, X, Wt, ws.state, ws.part, N, K, g.G, g.CP, g.iters,
-                                                               g.chunks, nullptr);
+                                                               g.chunks);
   const int BK = B * K;
   tls_sum_partials_kernel<<<(BK + kSolveWarps - 1) / kSolveWarps, kSolveWarps * 32, 0, st>>>(ws.part, M, BK, K, g.chunks);
   return check_launch();
