@@ -503,7 +503,9 @@ def run_ours(args):
     fps_t = float(np.mean(fps_big)) * 1e-6 if fps_big else float("nan")
     achieved = fps_bytes / fps_t / 1e9
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")        # dram bytes per launch from the committed ncu capture
+    tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")        # dram bytes per launch from the committed ncu capture
+    if not os.path.exists(tpath):                                    # (gpurun_out/r2_step.ncu-rep, `ncu --set full`)
+        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
             for k, v in json.load(f).items():
