@@ -27,6 +27,7 @@ SIGNATURES = {
     "cpfn_last_cuda_error": (ctypes.c_char_p, []),
     "cpfn_sm_count": (c_int, []),
     "cpfn_debug_fps_profile": (c_int, [c_void_p]),
+    "cpfn_debug_chain_profile": (c_int, [c_void_p, c_int, c_int]),
     "cpfn_fps_rounds_supported": (c_int, [c_int, c_int]),
     "cpfn_furthest_point_sampling_rounds": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                                     c_size_t, c_size_t, c_void_p]),

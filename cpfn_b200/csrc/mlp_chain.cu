@@ -48,7 +48,7 @@ constexpr int kWorkers = 256;
 constexpr int kStageBytes = 16384;   // one weight block: 128 rows x 128 B (64 bf16)
 constexpr int kMaxLayers = CPFN_MLP_MAX_LAYERS;
 constexpr int kMaxStages = 8;
-constexpr int kMiscBytes = 8192;     // barriers, TMEM slot, per-row loader scratch
+constexpr int kMiscBytes = 10240;    // barriers, TMEM slot, per-row loader scratch (2 x 1152 words in the two-sub-tile kernel)
 
 struct LayerP {
   int cin_atoms, ksteps, cout_chunks, cout, relu, bias_per_cloud, next_k16;
@@ -76,7 +76,31 @@ struct ChainP {
   const float *l0_w, *l0_b; int l0_cout;   // GROUP mode without features: first layer (3 -> l0_cout) on CUDA cores
   const float *in_bias;                    // INTERP mode: relu(interpolated + in_bias) enters layer 0
   int win_cols, win_off;                   // column window: win_cols columns of every cloud, from column win_off (0: all)
+  int pool_fast;                           // points-as-M max-pool without atomics (see mlp_chain_pm_kernel)
   int act_bytes0, act_bytes1, nstage, tmem_cols;
+  unsigned long long *prof;                // phase profile of this launch (kProfSlots sums), or nullptr
+  uint32_t wait_hint;                      // suspend-time hint (ns) of the mbarrier waits (CPFN_CHAIN_WAIT_HINT)
+};
+
+// Phase profile (CPFN_CHAIN_PROFILE=1, read back with cpfn_debug_chain_profile): clock64 sums over the CTAs of a launch.
+//   0 MMA thread waiting for the operand tile   1 MMA thread waiting for weight blocks   2 MMA thread, whole loop
+//   3 weight producer waiting for a free stage  4 weight producer, whole loop
+//   5 first worker warp building the input tile 6 ... waiting for the accumulators       7 ... whole loop
+//   8 CTAs                                      9 tiles (sub-tiles) processed by the profiled worker warps
+constexpr int kProfSlots = 16;
+constexpr int kProfLaunches = 64;
+struct Prof {
+  bool on;
+  long long t0, acc[3];
+  __device__ __forceinline__ explicit Prof(const ChainP &p) : on(p.prof != nullptr), t0(0), acc{0, 0, 0} {}
+  __device__ __forceinline__ long long now() const { return on ? clock64() : 0; }
+  __device__ __forceinline__ void start() { t0 = now(); }
+  __device__ __forceinline__ void stop(int k) { if (on) acc[k] += clock64() - t0; }
+  __device__ __forceinline__ void flush(const ChainP &p, int slot0, int n, long long total) {
+    if (!on) return;
+    for (int k = 0; k < n; ++k) atomicAdd(p.prof + slot0 + k, static_cast<unsigned long long>(acc[k]));
+    atomicAdd(p.prof + slot0 + n, static_cast<unsigned long long>(total));
+  }
 };
 
 // First column of tile `tile`.  With a column window the launch covers columns [win_off, win_off + win_cols) of every
@@ -105,8 +129,7 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
 // try_wait parks the thread in hardware until the phase completes or the suspend-time hint expires; with the default
 // (short) hint the producer, the MMA thread and 256 epilogue threads re-issue it continuously and took ~24 % of all
 // issue slots of the chain kernels (ncu source counters, round 1).
-__device__ uint32_t g_wait_hint = 0x989680u;      // suspend-time hint (ns) of the mbarrier waits; tuning knob
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, uint32_t hint) {
   asm volatile(
       "{\n\t"
       ".reg .pred P1;\n\t"
@@ -115,7 +138,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
       "@P1 bra DONE;\n\t"
       "bra WAIT_LOOP;\n\t"
       "DONE:\n\t"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(g_wait_hint) : "memory");
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(hint) : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -132,16 +155,37 @@ __device__ __forceinline__ void tmem_alloc(uint32_t *slot, uint32_t cols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+// The MMA warp runs its loops warp-uniformly (all 32 lanes take the same path, so the compiler keeps descriptors and
+// addresses in uniform registers) and only the tcgen05 instructions themselves are predicated on the elected lane:
+// with the loops inside `if (lane == 0)` ptxas wrapped every UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop and
+// a dependent descriptor chain, ~200 cycles per MMA issued against 32-64 cycles of tensor time (phase profile, r2).
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
   asm volatile(
       "{\n\t"
-      ".reg .pred p;\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n" : "=r"(pred));
+  return pred;
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar, uint32_t leader) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}\n" ::"r"(smem_u32(bar)), "r"(leader) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc,
+                                          uint32_t leader) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(leader) : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
@@ -270,8 +314,8 @@ __device__ void load_tile(const ChainP &p, uint32_t buf, long long col0, int w8,
     } else if (p.in_mode == CPFN_MLP_IN_INTERP) {
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
-        s_brow[t * 3 + q] = static_cast<int>(cloud * p.b_rows + __ldg(p.idx + c * 3 + q));
-        s_w[t * 3 + q] = __ldg(p.nn_w + c * 3 + q);
+        s_brow[t * 4 + q] = valid ? static_cast<int>(cloud * p.b_rows + __ldg(p.idx + c * 3 + q)) : 0;
+        s_w[t * 4 + q] = valid ? __ldg(p.nn_w + c * 3 + q) : 0.f;
       }
     }
     s_arow[t] = valid ? arow : -1;
@@ -297,7 +341,50 @@ __device__ void load_tile(const ChainP &p, uint32_t buf, long long col0, int w8,
       }
     }
   }
-  if (p.in_mode == CPFN_MLP_IN_INTERP) {
+  if (p.in_mode == CPFN_MLP_IN_INTERP && NT == 128 && NW == 8 && p.a_ch == 0 && p.b_ch == 128) {
+    // Interpolation-only input of 128 channels (the FP3 + heads chain): lane = 4 channels of rows w8, w8 + 8, ... --
+    // all of them have (row & 7) == w8, so the swizzled store offset is one constant plus 1024 bytes per row step, and
+    // the per-row source rows / weights come as two 16-byte shared-memory records.  Rows past the end of the data
+    // read row 0 with zero weights (finite values; a garbage row only affects its own, never stored, output row).
+    constexpr int RI = 4;
+    const float4 *src = reinterpret_cast<const float4 *>(p.b_src) + lane;
+    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.in_bias != nullptr) bb = __ldg(reinterpret_cast<const float4 *>(p.in_bias) + lane);
+    const bool act_in = p.in_bias != nullptr;
+    const uint32_t o_hi = buf + part_base<NT>(lane >> 4, 0) + static_cast<uint32_t>(w8 * 128) +
+                          static_cast<uint32_t>(((((lane & 15) >> 1) ^ w8) << 4) | ((lane & 1) << 3));
+#pragma unroll 1
+    for (int j0 = 0; j0 < NT / 8; j0 += RI) {
+      float4 f[RI][3], w[RI];
+#pragma unroll
+      for (int u = 0; u < RI; ++u) {
+        const int r = w8 + 8 * (j0 + u);
+        const int4 rows = *reinterpret_cast<const int4 *>(s_brow + r * 4);
+        w[u] = *reinterpret_cast<const float4 *>(s_w + r * 4);
+        f[u][0] = __ldg(src + static_cast<size_t>(static_cast<unsigned>(rows.x)) * 32);
+        f[u][1] = __ldg(src + static_cast<size_t>(static_cast<unsigned>(rows.y)) * 32);
+        f[u][2] = __ldg(src + static_cast<size_t>(static_cast<unsigned>(rows.z)) * 32);
+      }
+#pragma unroll
+      for (int u = 0; u < RI; ++u) {
+        float4 o;
+        o.x = __fmaf_rn(f[u][2].x, w[u].z, __fmaf_rn(f[u][0].x, w[u].x, __fmul_rn(f[u][1].x, w[u].y)));
+        o.y = __fmaf_rn(f[u][2].y, w[u].z, __fmaf_rn(f[u][0].y, w[u].x, __fmul_rn(f[u][1].y, w[u].y)));
+        o.z = __fmaf_rn(f[u][2].z, w[u].z, __fmaf_rn(f[u][0].z, w[u].x, __fmul_rn(f[u][1].z, w[u].y)));
+        o.w = __fmaf_rn(f[u][2].w, w[u].z, __fmaf_rn(f[u][0].w, w[u].x, __fmul_rn(f[u][1].w, w[u].y)));
+        if (act_in) {
+          o.x = fmaxf(o.x + bb.x, 0.f); o.y = fmaxf(o.y + bb.y, 0.f);
+          o.z = fmaxf(o.z + bb.z, 0.f); o.w = fmaxf(o.w + bb.w, 0.f);
+        }
+        uint32_t H01, L01, H23, L23;
+        split2(o.x, o.y, H01, L01);
+        split2(o.z, o.w, H23, L23);
+        const uint32_t a = o_hi + static_cast<uint32_t>(j0 + u) * 1024;
+        st_shared_v2(a, H01, H23);
+        st_shared_v2(a + NT * 128, L01, L23);
+      }
+    }
+  } else if (p.in_mode == CPFN_MLP_IN_INTERP) {
     // three_weighted_sum (interpolate_gpu.cu:98-99 as compiled): fma(p3,w3, fma(p1,w1, p2*w2))
     constexpr int RI = 4;
     const int nB4 = p.b_ch >> 2, a4 = p.a_ch >> 2;
@@ -312,8 +399,8 @@ __device__ void load_tile(const ChainP &p, uint32_t buf, long long col0, int w8,
           ok[u] = r < NT && s_arow[r < NT ? r : 0] >= 0;
 #pragma unroll
           for (int q = 0; q < 3; ++q) {
-            w[u][q] = ok[u] ? s_w[r * 3 + q] : 0.f;
-            f[u][q] = ok[u] ? __ldg(reinterpret_cast<const float4 *>(p.b_src + static_cast<long long>(s_brow[r * 3 + q]) * p.b_ch) + c4)
+            w[u][q] = ok[u] ? s_w[r * 4 + q] : 0.f;
+            f[u][q] = ok[u] ? __ldg(reinterpret_cast<const float4 *>(p.b_src + static_cast<long long>(s_brow[r * 4 + q]) * p.b_ch) + c4)
                             : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
@@ -351,8 +438,8 @@ mlp_chain_kernel(const __grid_constant__ ChainP p) {
            *acc_full = bars + 2 * kMaxStages + 1;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kMaxStages + 2);
   int *s_arow = reinterpret_cast<int *>(bars + 32);          // [128]
-  int *s_brow = s_arow + 128;                                // [128][3]
-  float *s_w = reinterpret_cast<float *>(s_brow + 384);      // [128][3]
+  int *s_brow = s_arow + 128;                                // [128][4] (16-byte records: three source rows)
+  float *s_w = reinterpret_cast<float *>(s_brow + 512);      // [128][4] (three weights)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -365,31 +452,39 @@ mlp_chain_kernel(const __grid_constant__ ChainP p) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform for the compiler
   const int wave_max = p.tmem_cols / NT;
 
   if (warp == 0) {
     // ===== weight producer: the packed blob is consumed strictly in order, once per tile =====
     if (lane == 0) {
+      Prof pf(p);
+      const long long pf_begin = pf.now();
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const int nblk = p.split_cout ? p.L[0].cin_atoms * 2 : p.total_blocks;
         const size_t blk0 = p.split_cout ? static_cast<size_t>(blockIdx.y) * nblk : 0;
         for (int blk = 0; blk < nblk; ++blk) {
-          mbar_wait(empty + stage, phase ^ 1);
+          pf.start();
+          mbar_wait(empty + stage, phase ^ 1, p.wait_hint);
+          pf.stop(0);
           mbar_arrive_expect_tx(full + stage, kStageBytes);
           bulk_g2s(ring + stage * kStageBytes, p.weights + (blk0 + blk) * kStageBytes, kStageBytes,
                    full + stage);
           if (++stage == p.nstage) { stage = 0; phase ^= 1; }
         }
       }
+      pf.flush(p, 3, 1, pf.now() - pf_begin);
     }
   } else if (warp == 1) {
     // ===== MMA issuer (one thread): per K-atom  D += Whi*Ahi + Whi*Alo  then  D += Wlo*Ahi =====
-    if (lane == 0) {
+    {
+      const uint32_t leader = elect_one();
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(NT >> 3) << 17) |
                                  (static_cast<uint32_t>(128 >> 4) << 24);
+      Prof pf(p);
+      const long long pf_begin = pf.now();
       int stage = 0;
       uint32_t phase = 0, act_phase = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
@@ -399,7 +494,9 @@ mlp_chain_kernel(const __grid_constant__ ChainP p) {
           const int n_chunks = p.split_cout ? 1 : L.cout_chunks;
           for (int m0 = 0; m0 < n_chunks; m0 += wave_max) {
             const int mc = min(wave_max, n_chunks - m0);
-            mbar_wait(act_ready, act_phase);
+            pf.start();
+            mbar_wait(act_ready, act_phase, p.wait_hint);
+            pf.stop(0);
             act_phase ^= 1;
             tc_fence_after();
             for (int m = 0; m < mc; ++m) {
@@ -407,28 +504,33 @@ mlp_chain_kernel(const __grid_constant__ ChainP p) {
               for (int j = 0; j < L.cin_atoms; ++j) {
                 const int ks = min(4, L.ksteps - 4 * j);
                 const uint32_t a_hi = in_buf + part_base<NT>(j, 0), a_lo = a_hi + NT * 128;
-                mbar_wait(full + stage, phase);            // W_hi block
+                pf.start();
+                mbar_wait(full + stage, phase, p.wait_hint);            // W_hi block
+                pf.stop(1);
                 tc_fence_after();
                 uint32_t w_base = smem_u32(ring + stage * kStageBytes);
                 for (int kk = 0; kk < ks; ++kk) {
-                  umma_bf16(d_tmem, make_desc(w_base + kk * 32), make_desc(a_hi + kk * 32), idesc, (j | kk) != 0 ? 1u : 0u);
-                  umma_bf16(d_tmem, make_desc(w_base + kk * 32), make_desc(a_lo + kk * 32), idesc, 1u);
+                  umma_bf16(d_tmem, make_desc(w_base + kk * 32), make_desc(a_hi + kk * 32), idesc, (j | kk) != 0 ? 1u : 0u, leader);
+                  umma_bf16(d_tmem, make_desc(w_base + kk * 32), make_desc(a_lo + kk * 32), idesc, 1u, leader);
                 }
-                umma_commit(empty + stage);                // frees the stage when these MMAs retire
+                umma_commit(empty + stage, leader);                // frees the stage when these MMAs retire
                 if (++stage == p.nstage) { stage = 0; phase ^= 1; }
-                mbar_wait(full + stage, phase);            // W_lo block
+                pf.start();
+                mbar_wait(full + stage, phase, p.wait_hint);            // W_lo block
+                pf.stop(1);
                 tc_fence_after();
                 w_base = smem_u32(ring + stage * kStageBytes);
                 for (int kk = 0; kk < ks; ++kk)
-                  umma_bf16(d_tmem, make_desc(w_base + kk * 32), make_desc(a_hi + kk * 32), idesc, 1u);
-                umma_commit(empty + stage);
+                  umma_bf16(d_tmem, make_desc(w_base + kk * 32), make_desc(a_hi + kk * 32), idesc, 1u, leader);
+                umma_commit(empty + stage, leader);
                 if (++stage == p.nstage) { stage = 0; phase ^= 1; }
               }
             }
-            umma_commit(acc_full);                         // accumulators of this wave complete
+            umma_commit(acc_full, leader);                         // accumulators of this wave complete
           }
         }
       }
+      if (leader) pf.flush(p, 0, 2, pf.now() - pf_begin);
     }
   } else {
     // ===== workers: build the input tile, then the epilogue of every layer =====
@@ -444,13 +546,19 @@ mlp_chain_kernel(const __grid_constant__ ChainP p) {
     const uint32_t sel_send = par ? 0x5410u : 0x7632u, sel_keep = par ? 0x7632u : 0x5410u;
     constexpr int HC = NT / 2;                        // columns per worker warp
     uint32_t acc_phase = 0;
+    Prof pf(p);
+    pf.on = pf.on && threadIdx.x == 64;
+    const long long pf_begin = pf.now();
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const long long col0 = tile_col0<NT>(p, tile);
       const long long cloud = col0 / p.cols_per_cloud;
       const long long n_in_cloud = col0 - cloud * p.cols_per_cloud;
+      pf.start();
       load_tile<NT, 8>(p, smem_u32(act0), col0, w8, lane, s_arow, s_brow, s_w, 1);
       fence_proxy_async();
       mbar_arrive(act_ready);
+      pf.stop(0);
+      pf.acc[2] += 1;
       for (int l = 0; l < p.n_layers; ++l) {
         const LayerP &L = p.L[l];
         const bool last = (l == p.n_layers - 1);
@@ -461,7 +569,9 @@ mlp_chain_kernel(const __grid_constant__ ChainP p) {
         const int chunk_base = p.split_cout ? static_cast<int>(blockIdx.y) : 0;
         for (int m0 = 0; m0 < n_chunks; m0 += wave_max) {
           const int mc = min(wave_max, n_chunks - m0);
-          mbar_wait(acc_full, acc_phase);
+          pf.start();
+          mbar_wait(acc_full, acc_phase, p.wait_hint);
+          pf.stop(1);
           acc_phase ^= 1;
           tc_fence_after();
           for (int m = 0; m < mc; ++m) {
@@ -471,12 +581,30 @@ mlp_chain_kernel(const __grid_constant__ ChainP p) {
             const bool to_smem = !last && (ch & ~1) < L.next_k16;
             const uint32_t o_hi = out_buf + part_base<NT>(ch >> 6, 0);
             const size_t cm_base = (static_cast<size_t>(cloud) * L.cout + ch) * p.cols_per_cloud + n_in_cloud;
-            float pool = 0.f;                          // post-ReLU values are >= 0
+            // Max-pool of the last layer: bias and ReLU are monotone and per channel, so the raw accumulators are pooled and
+            // relu(max + bias) is formed once per group (identical bits, a quarter of the instructions per element).
+            const bool pool_last = last && p.out_mode == CPFN_MLP_OUT_POOL;
+            const bool tile_full = col0 + NT <= p.cols;
+            float pool = -INFINITY;
 #pragma unroll 1
             for (int cb = 0; cb < HC; cb += 16) {
               const int c = half * HC + cb;            // first column of this batch inside the tile
               uint32_t r[16];
               tmem_ld16(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + m * NT + c, r);
+              if (pool_last) {
+                if (tile_full) {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) pool = fmaxf(pool, __uint_as_float(r[i]));
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) pool = fmaxf(pool, (col0 + c + i < p.cols) ? __uint_as_float(r[i]) : -INFINITY);
+                }
+                if (p.pool_g <= HC && ((c + 16) % p.pool_g) == 0) {
+                  if (ch_real && col0 + c + 16 - p.pool_g < p.cols) p.out[((col0 + c) / p.pool_g) * p.ldo + ch] = fmaxf(pool + bias, 0.f);
+                  pool = -INFINITY;
+                }
+                continue;
+              }
               float v[16];
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
@@ -522,17 +650,11 @@ mlp_chain_kernel(const __grid_constant__ ChainP p) {
                   for (int i = 0; i < 16; ++i)
                     if (col0 + c + i < p.cols) p.out[(col0 + c + i) * p.ldo + ch] = v[i];
                 }
-              } else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) pool = fmaxf(pool, (col0 + c + i < p.cols) ? v[i] : 0.f);
-                if (p.pool_g <= HC && ((c + 16) % p.pool_g) == 0) {
-                  if (ch_real && col0 + c + 16 - p.pool_g < p.cols) p.out[((col0 + c) / p.pool_g) * p.ldo + ch] = pool;
-                  pool = 0.f;
-                }
               }
             }
-            if (last && p.out_mode == CPFN_MLP_OUT_POOL && p.pool_g > HC && ch_real && col0 + half * HC < p.cols)
-              atomicMax(reinterpret_cast<int *>(p.out + ((col0 + half * HC) / p.pool_g) * p.ldo + ch), __float_as_int(pool));
+            if (pool_last && p.pool_g > HC && ch_real && col0 + half * HC < p.cols)
+              atomicMax(reinterpret_cast<int *>(p.out + ((col0 + half * HC) / p.pool_g) * p.ldo + ch),
+                        __float_as_int(fmaxf(pool + bias, 0.f)));
           }
           tc_fence_before();
           const bool final_wave = last && (m0 + wave_max >= n_chunks);
@@ -542,6 +664,12 @@ mlp_chain_kernel(const __grid_constant__ ChainP p) {
           }
         }
       }
+    }
+    if (pf.on) {
+      const long long tiles = pf.acc[2];
+      pf.flush(p, 5, 2, pf.now() - pf_begin);
+      atomicAdd(p.prof + 8, 1ull);
+      atomicAdd(p.prof + 9, static_cast<unsigned long long>(tiles));
     }
   }
   tc_fence_before();
@@ -561,6 +689,12 @@ mlp_chain_kernel(const __grid_constant__ ChainP p) {
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+// max over the warp's 32 lanes of a (signed) float: CREDUX.MAX.F32, result in a uniform register
+__device__ __forceinline__ float warp_max_f32(float v) {
+  float r;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
+}
 
 // Single-tile form of the points-as-M kernel (8 epilogue warps, each lane quarter's two warps share a
 // chunk's channels): used when one 128-column tile per CTA lets two CTAs share an SM but two sub-tiles
@@ -579,7 +713,7 @@ mlp_chain_pm1_kernel(const __grid_constant__ ChainP p) {
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kMaxStages + 2);
   int *s_arow = reinterpret_cast<int *>(bars + 32);
   int *s_brow = s_arow + 128;
-  float *s_w = reinterpret_cast<float *>(s_brow + 384);
+  float *s_w = reinterpret_cast<float *>(s_brow + 512);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -592,26 +726,34 @@ mlp_chain_pm1_kernel(const __grid_constant__ ChainP p) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform for the compiler
   const int wave_max = p.tmem_cols / 128;
 
   if (warp == 0) {
     if (lane == 0) {
+      Prof pf(p);
+      const long long pf_begin = pf.now();
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         for (int blk = 0; blk < p.total_blocks; ++blk) {
-          mbar_wait(empty + stage, phase ^ 1);
+          pf.start();
+          mbar_wait(empty + stage, phase ^ 1, p.wait_hint);
+          pf.stop(0);
           mbar_arrive_expect_tx(full + stage, kStageBytes);
           bulk_g2s(ring + stage * kStageBytes, p.weights + static_cast<size_t>(blk) * kStageBytes, kStageBytes,
                    full + stage);
           if (++stage == p.nstage) { stage = 0; phase ^= 1; }
         }
       }
+      pf.flush(p, 3, 1, pf.now() - pf_begin);
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      const uint32_t leader = elect_one();
       constexpr uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(128 >> 4) << 24);
+      Prof pf(p);
+      const long long pf_begin = pf.now();
       int stage = 0;
       uint32_t phase = 0, act_phase = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
@@ -621,7 +763,9 @@ mlp_chain_pm1_kernel(const __grid_constant__ ChainP p) {
           const int cout16 = (L.cout + 15) & ~15;
           for (int m0 = 0; m0 < L.cout_chunks; m0 += wave_max) {
             const int mc = min(wave_max, L.cout_chunks - m0);
-            mbar_wait(act_ready, act_phase);
+            pf.start();
+            mbar_wait(act_ready, act_phase, p.wait_hint);
+            pf.stop(0);
             act_phase ^= 1;
             tc_fence_after();
             for (int m = 0; m < mc; ++m) {
@@ -631,28 +775,33 @@ mlp_chain_pm1_kernel(const __grid_constant__ ChainP p) {
               for (int j = 0; j < L.cin_atoms; ++j) {
                 const int ks = min(4, L.ksteps - 4 * j);
                 const uint32_t a_hi = in_buf + part_base<NT>(j, 0), a_lo = a_hi + NT * 128;
-                mbar_wait(full + stage, phase);            // W_hi block
+                pf.start();
+                mbar_wait(full + stage, phase, p.wait_hint);            // W_hi block
+                pf.stop(1);
                 tc_fence_after();
                 uint32_t w_base = smem_u32(ring + stage * kStageBytes);
                 for (int kk = 0; kk < ks; ++kk) {
-                  umma_bf16(d_tmem, make_desc(a_hi + kk * 32), make_desc(w_base + kk * 32), idesc, (j | kk) != 0 ? 1u : 0u);
-                  umma_bf16(d_tmem, make_desc(a_lo + kk * 32), make_desc(w_base + kk * 32), idesc, 1u);
+                  umma_bf16(d_tmem, make_desc(a_hi + kk * 32), make_desc(w_base + kk * 32), idesc, (j | kk) != 0 ? 1u : 0u, leader);
+                  umma_bf16(d_tmem, make_desc(a_lo + kk * 32), make_desc(w_base + kk * 32), idesc, 1u, leader);
                 }
-                umma_commit(empty + stage);
+                umma_commit(empty + stage, leader);
                 if (++stage == p.nstage) { stage = 0; phase ^= 1; }
-                mbar_wait(full + stage, phase);            // W_lo block
+                pf.start();
+                mbar_wait(full + stage, phase, p.wait_hint);            // W_lo block
+                pf.stop(1);
                 tc_fence_after();
                 w_base = smem_u32(ring + stage * kStageBytes);
                 for (int kk = 0; kk < ks; ++kk)
-                  umma_bf16(d_tmem, make_desc(a_hi + kk * 32), make_desc(w_base + kk * 32), idesc, 1u);
-                umma_commit(empty + stage);
+                  umma_bf16(d_tmem, make_desc(a_hi + kk * 32), make_desc(w_base + kk * 32), idesc, 1u, leader);
+                umma_commit(empty + stage, leader);
                 if (++stage == p.nstage) { stage = 0; phase ^= 1; }
               }
             }
-            umma_commit(acc_full);
+            umma_commit(acc_full, leader);
           }
         }
       }
+      if (leader) pf.flush(p, 0, 2, pf.now() - pf_begin);
     }
   } else {
     const int w8 = warp - 2;
@@ -662,6 +811,9 @@ mlp_chain_pm1_kernel(const __grid_constant__ ChainP p) {
     const uint32_t row_base = static_cast<uint32_t>((row >> 3) * 1024 + (row & 7) * 128);
     const int r7 = row & 7;
     uint32_t acc_phase = 0;
+    Prof pf(p);
+    pf.on = pf.on && threadIdx.x == 64;
+    const long long pf_begin = pf.now();
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const long long col0 = tile_col0<NT>(p, tile);
       const long long col = col0 + row;
@@ -669,9 +821,12 @@ mlp_chain_pm1_kernel(const __grid_constant__ ChainP p) {
       // thread = point: the cloud of THIS row (a tile may straddle two clouds when N is not a multiple of 128)
       const long long cloud = (row_ok ? col : col0) / p.cols_per_cloud;
       const long long n_in_cloud = (row_ok ? col : col0) - cloud * p.cols_per_cloud - row;
+      pf.start();
       load_tile<NT, 8>(p, smem_u32(act0), col0, w8, lane, s_arow, s_brow, s_w, 1);
       fence_proxy_async();
       mbar_arrive(act_ready);
+      pf.stop(0);
+      pf.acc[2] += 1;
       for (int l = 0; l < p.n_layers; ++l) {
         const LayerP &L = p.L[l];
         const bool last = (l == p.n_layers - 1);
@@ -689,7 +844,9 @@ mlp_chain_pm1_kernel(const __grid_constant__ ChainP p) {
         }
         for (int m0 = 0; m0 < L.cout_chunks; m0 += wave_max) {
           const int mc = min(wave_max, L.cout_chunks - m0);
-          mbar_wait(acc_full, acc_phase);
+          pf.start();
+          mbar_wait(acc_full, acc_phase, p.wait_hint);
+          pf.stop(1);
           acc_phase ^= 1;
           tc_fence_after();
           for (int m = 0; m < mc; ++m) {
@@ -773,6 +930,12 @@ mlp_chain_pm1_kernel(const __grid_constant__ ChainP p) {
         }
       }
     }
+    if (pf.on) {
+      const long long tiles = pf.acc[2];
+      pf.flush(p, 5, 2, pf.now() - pf_begin);
+      atomicAdd(p.prof + 8, 1ull);
+      atomicAdd(p.prof + 9, static_cast<unsigned long long>(tiles));
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -793,7 +956,7 @@ mlp_chain_pm_kernel(const __grid_constant__ ChainP p) {
   uint64_t *full = bars, *empty = bars + kMaxStages, *act_ready = bars + 2 * kMaxStages,   // [2]
            *acc_full = bars + 2 * kMaxStages + 2;                                          // [2]
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kMaxStages + 4);
-  int *s_scratch = reinterpret_cast<int *>(bars + 32);                // per group: arow[128], brow[384], w[384]
+  int *s_scratch = reinterpret_cast<int *>(bars + 32);                // per group: arow[128], brow[128][4], w[128][4]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -805,13 +968,15 @@ mlp_chain_pm_kernel(const __grid_constant__ ChainP p) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform for the compiler
   const int sub_cols = p.tmem_cols / 2;                               // TMEM columns of one sub-tile
   const int n_pairs = (p.n_tiles + 1) / 2;
 
   if (warp == 0) {
     // ===== weight producer: layer by layer, once per valid sub-tile =====
     if (lane == 0) {
+      Prof pf(p);
+      const long long pf_begin = pf.now();
       int stage = 0;
       uint32_t phase = 0;
       for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
@@ -821,7 +986,9 @@ mlp_chain_pm_kernel(const __grid_constant__ ChainP p) {
           const int nblk = p.L[l].cout_chunks * p.L[l].cin_atoms * 2;
           for (int g = 0; g < nsub; ++g)
             for (int blk = 0; blk < nblk; ++blk) {
-              mbar_wait(empty + stage, phase ^ 1);
+              pf.start();
+              mbar_wait(empty + stage, phase ^ 1, p.wait_hint);
+              pf.stop(0);
               mbar_arrive_expect_tx(full + stage, kStageBytes);
               bulk_g2s(ring + stage * kStageBytes, p.weights + static_cast<size_t>(blk0 + blk) * kStageBytes,
                        kStageBytes, full + stage);
@@ -830,11 +997,15 @@ mlp_chain_pm_kernel(const __grid_constant__ ChainP p) {
           blk0 += nblk;
         }
       }
+      pf.flush(p, 3, 1, pf.now() - pf_begin);
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
+    {
+      const uint32_t leader = elect_one();
       constexpr uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(128 >> 4) << 24);
+      Prof pf(p);
+      const long long pf_begin = pf.now();
       int stage = 0;
       uint32_t phase = 0, act_phase[2] = {0, 0};
       for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
@@ -844,7 +1015,9 @@ mlp_chain_pm_kernel(const __grid_constant__ ChainP p) {
           const int cout16 = (L.cout + 15) & ~15;
           for (int g = 0; g < nsub; ++g) {
             const uint32_t in_buf = smem_u32(act + g * p.act_bytes0);
-            mbar_wait(act_ready + g, act_phase[g]);
+            pf.start();
+            mbar_wait(act_ready + g, act_phase[g], p.wait_hint);
+            pf.stop(0);
             act_phase[g] ^= 1;
             tc_fence_after();
             for (int m = 0; m < L.cout_chunks; ++m) {
@@ -854,28 +1027,33 @@ mlp_chain_pm_kernel(const __grid_constant__ ChainP p) {
               for (int j = 0; j < L.cin_atoms; ++j) {
                 const int ks = min(4, L.ksteps - 4 * j);
                 const uint32_t a_hi = in_buf + part_base<NT>(j, 0), a_lo = a_hi + NT * 128;
-                mbar_wait(full + stage, phase);            // W_hi block
+                pf.start();
+                mbar_wait(full + stage, phase, p.wait_hint);            // W_hi block
+                pf.stop(1);
                 tc_fence_after();
                 uint32_t w_base = smem_u32(ring + stage * kStageBytes);
                 for (int kk = 0; kk < ks; ++kk) {
-                  umma_bf16(d_tmem, make_desc(a_hi + kk * 32), make_desc(w_base + kk * 32), idesc, (j | kk) != 0 ? 1u : 0u);
-                  umma_bf16(d_tmem, make_desc(a_lo + kk * 32), make_desc(w_base + kk * 32), idesc, 1u);
+                  umma_bf16(d_tmem, make_desc(a_hi + kk * 32), make_desc(w_base + kk * 32), idesc, (j | kk) != 0 ? 1u : 0u, leader);
+                  umma_bf16(d_tmem, make_desc(a_lo + kk * 32), make_desc(w_base + kk * 32), idesc, 1u, leader);
                 }
-                umma_commit(empty + stage);
+                umma_commit(empty + stage, leader);
                 if (++stage == p.nstage) { stage = 0; phase ^= 1; }
-                mbar_wait(full + stage, phase);            // W_lo block
+                pf.start();
+                mbar_wait(full + stage, phase, p.wait_hint);            // W_lo block
+                pf.stop(1);
                 tc_fence_after();
                 w_base = smem_u32(ring + stage * kStageBytes);
                 for (int kk = 0; kk < ks; ++kk)
-                  umma_bf16(d_tmem, make_desc(a_hi + kk * 32), make_desc(w_base + kk * 32), idesc, 1u);
-                umma_commit(empty + stage);
+                  umma_bf16(d_tmem, make_desc(a_hi + kk * 32), make_desc(w_base + kk * 32), idesc, 1u, leader);
+                umma_commit(empty + stage, leader);
                 if (++stage == p.nstage) { stage = 0; phase ^= 1; }
               }
             }
-            umma_commit(acc_full + g);
+            umma_commit(acc_full + g, leader);
           }
         }
       }
+      if (leader) pf.flush(p, 0, 2, pf.now() - pf_begin);
     }
   } else {
     const int g = (warp - 2) >> 2;                    // worker group = sub-tile
@@ -885,9 +1063,12 @@ mlp_chain_pm_kernel(const __grid_constant__ ChainP p) {
     const uint32_t row_base = static_cast<uint32_t>((row >> 3) * 1024 + (row & 7) * 128);
     const int r7 = row & 7;
     const uint32_t my_act = smem_u32(act + g * p.act_bytes0);
-    int *s_arow = s_scratch + g * 896, *s_brow = s_arow + 128;
-    float *s_w = reinterpret_cast<float *>(s_brow + 384);
+    int *s_arow = s_scratch + g * 1152, *s_brow = s_arow + 128;
+    float *s_w = reinterpret_cast<float *>(s_brow + 512);
     uint32_t acc_phase = 0;
+    Prof pf(p);
+    pf.on = pf.on && threadIdx.x == 64;
+    const long long pf_begin = pf.now();
     for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
       const int tile = 2 * pair + g;
       if (tile >= p.n_tiles) continue;
@@ -897,9 +1078,12 @@ mlp_chain_pm_kernel(const __grid_constant__ ChainP p) {
       // thread = point: the cloud of THIS row (a tile may straddle two clouds when N is not a multiple of 128)
       const long long cloud = (row_ok ? col : col0) / p.cols_per_cloud;
       const long long n_in_cloud = (row_ok ? col : col0) - cloud * p.cols_per_cloud - row;
+      pf.start();
       load_tile<NT, 4>(p, my_act, col0, w4, lane, s_arow, s_brow, s_w, 1 + g);
       fence_proxy_async();
       mbar_arrive(act_ready + g);
+      pf.stop(0);
+      pf.acc[2] += 1;
       for (int l = 0; l < p.n_layers; ++l) {
         const LayerP &L = p.L[l];
         const bool last = (l == p.n_layers - 1);
@@ -914,9 +1098,46 @@ mlp_chain_pm_kernel(const __grid_constant__ ChainP p) {
           if (L.mask_words > 2) mbits.z = __ldg(mb + 2);
           if (L.mask_words > 3) mbits.w = __ldg(mb + 3);
         }
-        mbar_wait(acc_full + g, acc_phase);
+        pf.start();
+        mbar_wait(acc_full + g, acc_phase, p.wait_hint);
+        pf.stop(1);
         acc_phase ^= 1;
         tc_fence_after();
+        if (last && p.pool_fast) {
+          // Max-pool of the last layer without atomics and without touching bias / ReLU per element: both are
+          // monotone and the bias is per channel, so max_rows relu(acc + b) == relu(max_rows(acc) + b) exactly.  Every warp
+          // reduces its 32 rows per channel with one CREDUX on the raw accumulators, the four warps of the sub-tile meet in
+          // shared memory, and thread c finishes channel c of every pooling group of the tile with a plain store.
+          float *s_pool = reinterpret_cast<float *>(s_brow);                 // [4][cout16] (no interpolation rows here)
+#pragma unroll 1
+          for (int ch0 = 0; ch0 < cout16; ch0 += 16) {
+            uint32_t r[16];
+            tmem_ld16(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + g * sub_cols + ch0, r);
+            float m[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) m[i] = warp_max_f32(__uint_as_float(r[i]));
+            if (lane == 0) {
+              float4 *dst = reinterpret_cast<float4 *>(s_pool + wq * cout16 + ch0);
+#pragma unroll
+              for (int i4 = 0; i4 < 4; ++i4) dst[i4] = make_float4(m[i4 * 4], m[i4 * 4 + 1], m[i4 * 4 + 2], m[i4 * 4 + 3]);
+            }
+          }
+          tc_fence_before();
+          asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(128) : "memory");
+          const int wpg = p.pool_g >> 5, n_groups = 128 / p.pool_g;
+          const long long group0 = col0 / p.pool_g;
+          for (int c = row; c < L.cout; c += 128) {
+            for (int gi = 0; gi < n_groups; ++gi) {
+              float mx = s_pool[(gi * wpg) * cout16 + c];
+              for (int w = 1; w < wpg; ++w) mx = fmaxf(mx, s_pool[(gi * wpg + w) * cout16 + c]);
+              const long long gcloud = (col0 + static_cast<long long>(gi) * p.pool_g) / p.cols_per_cloud;
+              float v = mx + __ldg(L.bias + (L.bias_per_cloud ? gcloud * cout_pad : 0) + c);
+              if (L.relu) v = fmaxf(v, 0.f);
+              p.out[(group0 + gi) * p.ldo + c] = v;
+            }
+          }
+          continue;      // last layer: nothing to publish (the next tile's loader meets this sub-tile's warps at its barrier)
+        }
 #pragma unroll 1
         for (int ch0 = 0; ch0 < cout16; ch0 += 16) {
           uint32_t r[16];
@@ -990,11 +1211,21 @@ mlp_chain_pm_kernel(const __grid_constant__ ChainP p) {
         }
       }
     }
+    if (pf.on) {
+      const long long tiles = pf.acc[2];
+      pf.flush(p, 5, 2, pf.now() - pf_begin);
+      atomicAdd(p.prof + 8, 1ull);
+      atomicAdd(p.prof + 9, static_cast<unsigned long long>(tiles));
+    }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
 }
+
+uint32_t g_wait_hint = 0x989680u;
+unsigned long long *g_prof_buf = nullptr;     // [kProfLaunches][kProfSlots], CPFN_CHAIN_PROFILE=1
+int g_prof_launch = 0;
 
 int pow2_at_least(int x) {
   int p = 32;
@@ -1071,11 +1302,19 @@ int launch_chain(const cpfn_mlp_chain_t *c, cudaStream_t st) {
   if (p.cols >= 2147483647LL || static_cast<long long>(c->B) * c->a_rows >= 2147483647LL ||
       static_cast<long long>(c->B) * c->b_rows >= 2147483647LL) return CPFN_EINVAL;
   bool atomic_pool = false;
+  p.pool_fast = 0;
   if (c->out_mode == CPFN_MLP_OUT_POOL && NT == 128) {
-    // points-as-M kernel: every warp (32 rows) max-reduces and merges with atomicMax
+    // points-as-M kernel: every warp (32 rows) max-reduces and merges with atomicMax ...
     if (c->pool_g <= 0 || (c->pool_g % 32) != 0 || !c->layers[c->n_layers - 1].relu ||
         (c->cols_per_cloud % c->pool_g) != 0) return CPFN_EINVAL;
     atomic_pool = true;
+    // ... unless whole pooling groups sit inside full tiles: then the sub-tile's warps meet in shared memory (no atomics,
+    // no zero fill).  Decided after the kernel variant is known (two-sub-tile kernel only).
+    const cpfn_mlp_layer_t &last = c->layers[c->n_layers - 1];
+    const long long span = c->win_cols > 0 ? c->win_cols : c->cols_per_cloud;
+    if ((c->pool_g == 32 || c->pool_g == 64 || c->pool_g == 128) && (span % 128) == 0 && c->in_mode != CPFN_MLP_IN_INTERP &&
+        ((last.cout + 15) & ~15) <= 192 && !last.mask_bits && !last.out_cm)
+      p.pool_fast = 1;
   } else if (c->out_mode == CPFN_MLP_OUT_POOL) {
     if (c->pool_g <= 0 || (c->pool_g % 16) != 0 || !c->layers[c->n_layers - 1].relu) return CPFN_EINVAL;
     if (c->pool_g <= NT / 2) {
@@ -1120,6 +1359,8 @@ int launch_chain(const cpfn_mlp_chain_t *c, cudaStream_t st) {
   const size_t smem = fixed + static_cast<size_t>(nstage) * kStageBytes;
   void (*kern)(ChainP) = mlp_chain_kernel<NT>;
   if (NT == 128) kern = two_sub ? mlp_chain_pm_kernel : mlp_chain_pm1_kernel;
+  if (!(NT == 128 && two_sub)) p.pool_fast = 0;
+  if (p.pool_fast) atomic_pool = false;
   CPFN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const int sms = sm_count() > 0 ? sm_count() : 148;
   const int units = (NT == 128 && two_sub) ? (p.n_tiles + 1) / 2 : p.n_tiles;   // the ping-pong kernel takes tile pairs
@@ -1129,6 +1370,12 @@ int launch_chain(const cpfn_mlp_chain_t *c, cudaStream_t st) {
   if (atomic_pool && !c->out_prezeroed)
     CPFN_CUDA_TRY(cudaMemsetAsync(c->out, 0, sizeof(float) * static_cast<size_t>(p.cols / c->pool_g) * c->ldo, st));
   const dim3 grid2(grid, p.split_cout ? p.L[0].cout_chunks : 1);
+  p.wait_hint = g_wait_hint;
+  p.prof = nullptr;
+  if (g_prof_buf != nullptr) {
+    p.prof = g_prof_buf + static_cast<size_t>(g_prof_launch % kProfLaunches) * kProfSlots;
+    ++g_prof_launch;
+  }
   kern<<<grid2, kChainThreads, smem, st>>>(p);
   return check_launch();
 }
@@ -1183,14 +1430,34 @@ extern "C" int cpfn_mlp_pack_weights_host(const float *W, int cout, int cin, voi
   return CPFN_OK;
 }
 
+extern "C" int cpfn_debug_chain_profile(unsigned long long *out, int max_launches, int reset) {
+  using namespace cpfn;
+  if (g_prof_buf == nullptr) return CPFN_EINVAL;
+  CPFN_CUDA_TRY(cudaDeviceSynchronize());
+  int n = g_prof_launch < kProfLaunches ? g_prof_launch : kProfLaunches;
+  if (n > max_launches) n = max_launches;
+  if (out != nullptr && n > 0)
+    CPFN_CUDA_TRY(cudaMemcpy(out, g_prof_buf, sizeof(unsigned long long) * n * kProfSlots, cudaMemcpyDeviceToHost));
+  if (reset) {
+    CPFN_CUDA_TRY(cudaMemset(g_prof_buf, 0, sizeof(unsigned long long) * kProfLaunches * kProfSlots));
+    g_prof_launch = 0;
+  }
+  return n;
+}
+
 extern "C" int cpfn_mlp_chain(const cpfn_mlp_chain_t *c, cpfn_stream_t stream) {
   using namespace cpfn;
   static bool hint_set = false;
   if (!hint_set) {
     hint_set = true;
+    if (const char *e = getenv("CPFN_CHAIN_PROFILE")) {
+      if (e[0] == '1' && cudaMalloc(&g_prof_buf, sizeof(unsigned long long) * kProfLaunches * kProfSlots) == cudaSuccess)
+        cudaMemset(g_prof_buf, 0, sizeof(unsigned long long) * kProfLaunches * kProfSlots);
+      else
+        g_prof_buf = nullptr;
+    }
     if (const char *e = getenv("CPFN_CHAIN_WAIT_HINT")) {
-      const uint32_t h = static_cast<uint32_t>(strtoul(e, nullptr, 0));
-      cudaMemcpyToSymbol(g_wait_hint, &h, sizeof(h));
+      g_wait_hint = static_cast<uint32_t>(strtoul(e, nullptr, 0));
     }
   }
   if (!c || c->n_layers <= 0 || c->n_layers > kMaxLayers || c->B < 0 || c->cols_per_cloud < 0) return CPFN_EINVAL;

@@ -73,6 +73,12 @@ CPFN_API int cpfn_furthest_point_sampling_rounds(const float *xyz, int B, int N,
  * cluster arg-max, centroid look-up}; this copies the six sums of the last such launch to the host (synchronises). */
 CPFN_API int cpfn_debug_fps_profile(long long *cycles6);
 
+/* Diagnostic: with CPFN_CHAIN_PROFILE=1 every cpfn_mlp_chain launch sums, over its CTAs, the cycles its MMA thread,
+ * its weight producer and its first worker warp spend waiting / working (16 sums per launch, slot meaning in
+ * csrc/mlp_chain.cu); copies the sums of the launches since the last reset (at most 64, in launch order) to `out`
+ * (16 values each), optionally resets, returns the number of launches copied.  Synchronises the device. */
+CPFN_API int cpfn_debug_chain_profile(unsigned long long *out, int max_launches, int reset);
+
 /* Furthest point sampling.  Replaces farthest_point_sampling
  * (src/sampling.cpp:65-86, kernel src/sampling_gpu.cu:63-159).
  * xyz [B,N,3] f32 -> idx [B,nsamples] i32.  Bit-exact with the reference,

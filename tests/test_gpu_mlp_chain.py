@@ -57,10 +57,16 @@ def test_dense_rows(cuda_dev, dims, tile):
     assert _rel(out, ref) < TOL, _rel(out, ref)
 
 
-@pytest.mark.parametrize("feat_ch,K,tile", [(0, 64, 128), (64, 64, 128), (128, 64, 64), (128, 32, 64), (256, 128, 32)])
-def test_group_and_pool(cuda_dev, feat_ch, K, tile):
+@pytest.mark.parametrize("feat_ch,K,tile,S", [(0, 64, 128, 24), (64, 64, 128, 24), (128, 64, 64, 24), (128, 32, 64, 24),
+                                              (256, 128, 32, 24),
+                                              # points-as-M kernel: whole groups inside full tiles (pooled through shared
+                                              # memory, plain stores) with 4 / 2 / 1 groups per tile ...
+                                              (0, 32, 128, 24), (0, 128, 128, 24), (64, 64, 128, 26),
+                                              # ... and ragged clouds (last tile partly empty: atomicMax path)
+                                              (0, 32, 128, 25), (64, 64, 128, 25)])
+def test_group_and_pool(cuda_dev, feat_ch, K, tile, S):
     rng = np.random.default_rng(feat_ch + K)
-    B, N, S = 2, 500, 24
+    B, N = 2, 500
     dims = [feat_ch + 3, 64, 128]
     pc, layers = _chain(dims, rng, cuda_dev)
     xyz = torch.from_numpy(rng.normal(size=(B, N, 3)).astype(np.float32)).to(cuda_dev)
