@@ -491,9 +491,22 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # Dominant kernel of ours: SA1 furthest point sampling (one launch per step at N=8192, m=512).
-    fps_us = [t_ for t_ in per_op.get("farthest_point_sampling", [])]
-    fps_big = fps_us[0::2] if len(fps_us) >= 2 else fps_us       # calls alternate SA1 (8192->512), SA2 (512->128)
+    # Dominant kernel of ours: SA1 furthest point sampling (one launch per step at N=8192, m=512).  Timed live, one
+    # CUDA-event pair per launch on the launching stream, over the K steps' inputs, the call the step makes
+    # (centroids written by the kernel), L2 flushed before every launch.  The flush kernel is still running when the
+    # event and the launch are enqueued, so the pair brackets the kernel and not the host's launch latency (the per-op
+    # times of the eager profiling pass above do include it once the GPU outruns the Python launch path).
+    fps_big = []
+    for i in range(args.steps):
+        P = dev_inputs[i % len(dev_inputs)]
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        cuda_ops.farthest_point_sampling(P, 512, return_centroids=True)
+        b.record()
+        fps_big.append((a, b))
+    torch.cuda.synchronize()
+    fps_big = [a.elapsed_time(b) * 1e3 for a, b in fps_big]
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peak, peak_src = 6650.0, "fallback"
     if os.path.exists(peaks_path):

@@ -76,7 +76,8 @@ struct ChainP {
   const float *l0_w, *l0_b; int l0_cout;   // GROUP mode without features: first layer (3 -> l0_cout) on CUDA cores
   const float *in_bias;                    // INTERP mode: relu(interpolated + in_bias) enters layer 0
   int win_cols, win_off;                   // column window: win_cols columns of every cloud, from column win_off (0: all)
-  int pool_fast;                           // points-as-M max-pool without atomics (see mlp_chain_pm_kernel)
+  int pool_fast;                           // pooled last layer with swapped operand roles (see epi_pool_cols)
+  const float *xyz_w;                      // GROUP + features: layer 0's position columns as an epilogue term [cout_pad][4]
   int act_bytes0, act_bytes1, nstage, tmem_cols;
   unsigned long long *prof;                // phase profile of this launch (kProfSlots sums), or nullptr
   uint32_t wait_hint;                      // suspend-time hint (ns) of the mbarrier waits (CPFN_CHAIN_WAIT_HINT)
@@ -87,6 +88,7 @@ struct ChainP {
 //   3 weight producer waiting for a free stage  4 weight producer, whole loop
 //   5 first worker warp building the input tile 6 ... waiting for the accumulators       7 ... whole loop
 //   8 CTAs                                      9 tiles (sub-tiles) processed by the profiled worker warps
+//   10 + l: the profiled worker warp's epilogue of layer l (l <= 5)
 constexpr int kProfSlots = 16;
 constexpr int kProfLaunches = 64;
 struct Prof {
@@ -96,6 +98,9 @@ struct Prof {
   __device__ __forceinline__ long long now() const { return on ? clock64() : 0; }
   __device__ __forceinline__ void start() { t0 = now(); }
   __device__ __forceinline__ void stop(int k) { if (on) acc[k] += clock64() - t0; }
+  __device__ __forceinline__ void lap(const ChainP &p, int slot) {        // time since start(), straight to the sums
+    if (on) atomicAdd(p.prof + slot, static_cast<unsigned long long>(clock64() - t0));
+  }
   __device__ __forceinline__ void flush(const ChainP &p, int slot0, int n, long long total) {
     if (!on) return;
     for (int k = 0; k < n; ++k) atomicAdd(p.prof + slot0 + k, static_cast<unsigned long long>(acc[k]));
@@ -274,7 +279,8 @@ __device__ void load_tile(const ChainP &p, uint32_t buf, long long col0, int w8,
                           int *s_brow, float *s_w, int bar_id) {
   const int t = w8 * 32 + lane;
   const int cin = p.l0_w != nullptr ? p.l0_cout
-                                     : p.a_ch + (p.in_mode == CPFN_MLP_IN_GROUP ? 3 : (p.in_mode == CPFN_MLP_IN_INTERP ? p.b_ch : 0));
+                                     : p.a_ch + (p.in_mode == CPFN_MLP_IN_GROUP ? (p.xyz_w != nullptr ? 0 : 3)
+                                                                                : (p.in_mode == CPFN_MLP_IN_INTERP ? p.b_ch : 0));
   const int k16 = p.L[0].ksteps * 16;
   if (t < NT) {
     const long long col = col0 + t;
@@ -283,7 +289,9 @@ __device__ void load_tile(const ChainP &p, uint32_t buf, long long col0, int w8,
     const long long cloud = c / p.cols_per_cloud;
     int arow = static_cast<int>(c);
     int pad_from = cin;
-    if (p.in_mode == CPFN_MLP_IN_GROUP) {
+    if (p.in_mode == CPFN_MLP_IN_GROUP && p.xyz_w != nullptr) {
+      arow = static_cast<int>(cloud * p.a_rows + __ldg(p.idx + c));       // positions enter in layer 0's epilogue
+    } else if (p.in_mode == CPFN_MLP_IN_GROUP) {
       arow = static_cast<int>(cloud * p.a_rows + __ldg(p.idx + c));
       // recentred position (pointset_abstraction.py:62-63): xyz[idx] - centre
       const float *a = p.xyz + static_cast<long long>(arow) * 3;
@@ -508,20 +516,25 @@ mlp_chain_kernel(const __grid_constant__ ChainP p) {
                 mbar_wait(full + stage, phase, p.wait_hint);            // W_hi block
                 pf.stop(1);
                 tc_fence_after();
-                uint32_t w_base = smem_u32(ring + stage * kStageBytes);
-                for (int kk = 0; kk < ks; ++kk) {
-                  umma_bf16(d_tmem, make_desc(w_base + kk * 32), make_desc(a_hi + kk * 32), idesc, (j | kk) != 0 ? 1u : 0u, leader);
-                  umma_bf16(d_tmem, make_desc(w_base + kk * 32), make_desc(a_lo + kk * 32), idesc, 1u, leader);
-                }
+                // descriptors of K step kk = those of step 0 + 2 (32 bytes >> 4) in the 14-bit start-address field
+                const uint64_t d_ahi = make_desc(a_hi), d_alo = make_desc(a_lo);
+                uint64_t d_w = make_desc(smem_u32(ring + stage * kStageBytes));
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                  if (kk < ks) {
+                    umma_bf16(d_tmem, d_w + 2 * kk, d_ahi + 2 * kk, idesc, (j | kk) != 0 ? 1u : 0u, leader);
+                    umma_bf16(d_tmem, d_w + 2 * kk, d_alo + 2 * kk, idesc, 1u, leader);
+                  }
                 umma_commit(empty + stage, leader);                // frees the stage when these MMAs retire
                 if (++stage == p.nstage) { stage = 0; phase ^= 1; }
                 pf.start();
                 mbar_wait(full + stage, phase, p.wait_hint);            // W_lo block
                 pf.stop(1);
                 tc_fence_after();
-                w_base = smem_u32(ring + stage * kStageBytes);
-                for (int kk = 0; kk < ks; ++kk)
-                  umma_bf16(d_tmem, make_desc(w_base + kk * 32), make_desc(a_hi + kk * 32), idesc, 1u, leader);
+                d_w = make_desc(smem_u32(ring + stage * kStageBytes));
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                  if (kk < ks) umma_bf16(d_tmem, d_w + 2 * kk, d_ahi + 2 * kk, idesc, 1u, leader);
                 umma_commit(empty + stage, leader);
                 if (++stage == p.nstage) { stage = 0; phase ^= 1; }
               }
@@ -572,6 +585,7 @@ mlp_chain_kernel(const __grid_constant__ ChainP p) {
           pf.start();
           mbar_wait(acc_full, acc_phase, p.wait_hint);
           pf.stop(1);
+          pf.start();
           acc_phase ^= 1;
           tc_fence_after();
           for (int m = 0; m < mc; ++m) {
@@ -662,6 +676,7 @@ mlp_chain_kernel(const __grid_constant__ ChainP p) {
             fence_proxy_async();
             mbar_arrive(act_ready);
           }
+          pf.lap(p, 10 + min(l, 5));
         }
       }
     }
@@ -694,6 +709,143 @@ __device__ __forceinline__ float warp_max_f32(float v) {
   float r;
   asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
   return r;
+}
+
+// ---- specialised epilogue loops of the points-as-M kernels (thread = point) ---------------------------------
+// The generic per-chunk body below serves every combination of (ReLU, dropout bits, channel-major copy, rows / pooled /
+// next-layer output); each extra uniform branch in it costs every layer (the 128 -> 128 layers of the heads chain went
+// from 12.7 to 17 kilo-cycles per CTA as cases were added), so the combinations the network actually runs get their
+// own straight-line loops.  `taddr` = TMEM address of the thread's lane quarter at column 0 of the chunk's accumulator.
+
+// bias + (ReLU) + (hi, lo) split -> the next layer's operand tile, channels [chunk0 + cb0, chunk0 + cb1)
+template <bool RELU>
+__device__ __forceinline__ void epi_next(uint32_t taddr, const float *__restrict__ bias, int chunk0, int cb0, int cb1,
+                                         int next_k16, uint32_t out_buf, uint32_t row_base, int r7) {
+#pragma unroll 1
+  for (int cb = cb0; cb < cb1; cb += 16) {
+    const int ch0 = chunk0 + cb;
+    uint32_t r[16];
+    float4 b4[4];
+#pragma unroll
+    for (int i4 = 0; i4 < 4; ++i4) b4[i4] = __ldg(reinterpret_cast<const float4 *>(bias + ch0) + i4);
+    tmem_ld16(taddr + cb, r);
+    if (ch0 >= next_k16) continue;
+    float v[16];
+#pragma unroll
+    for (int i4 = 0; i4 < 4; ++i4) {
+      v[i4 * 4] = __uint_as_float(r[i4 * 4]) + b4[i4].x;
+      v[i4 * 4 + 1] = __uint_as_float(r[i4 * 4 + 1]) + b4[i4].y;
+      v[i4 * 4 + 2] = __uint_as_float(r[i4 * 4 + 2]) + b4[i4].z;
+      v[i4 * 4 + 3] = __uint_as_float(r[i4 * 4 + 3]) + b4[i4].w;
+    }
+    if (RELU) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
+    uint32_t H[8], Lo[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) split2(v[2 * i], v[2 * i + 1], H[i], Lo[i]);
+    const uint32_t base = out_buf + part_base<128>(ch0 >> 6, 0) + row_base;
+    const int c8 = (ch0 & 63) >> 3;
+    const uint32_t a0 = base + (((c8) ^ r7) << 4), a1 = base + (((c8 + 1) ^ r7) << 4);
+    st_shared_v4(a0, H[0], H[1], H[2], H[3]);
+    st_shared_v4(a1, H[4], H[5], H[6], H[7]);
+    st_shared_v4(a0 + 128 * 128, Lo[0], Lo[1], Lo[2], Lo[3]);
+    st_shared_v4(a1 + 128 * 128, Lo[4], Lo[5], Lo[6], Lo[7]);
+  }
+}
+
+// the same with layer 0's position term instead of a plain bias: rows (wx, wy, wz, bias) per channel
+template <bool RELU>
+__device__ __forceinline__ void epi_next_xyz(uint32_t taddr, const float4 *__restrict__ wb, float dx, float dy, float dz,
+                                             int chunk0, int cb0, int cb1, int next_k16, uint32_t out_buf,
+                                             uint32_t row_base, int r7) {
+#pragma unroll 1
+  for (int cb = cb0; cb < cb1; cb += 16) {
+    const int ch0 = chunk0 + cb;
+    uint32_t r[16];
+    float4 w4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w4[i] = __ldg(wb + ch0 + i);
+    tmem_ld16(taddr + cb, r);
+    if (ch0 >= next_k16) continue;
+    float v[16];
+#pragma unroll
+    for (int i4 = 0; i4 < 4; ++i4) {          // four rows at a time: 16 registers of weights in flight, not 64
+      float4 nx[4];
+      if (i4 < 3) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) nx[i] = __ldg(wb + ch0 + (i4 + 1) * 4 + i);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float t = fmaf(w4[i].z, dz, fmaf(w4[i].y, dy, fmaf(w4[i].x, dx, __uint_as_float(r[i4 * 4 + i]) + w4[i].w)));
+        v[i4 * 4 + i] = RELU ? fmaxf(t, 0.f) : t;
+      }
+      if (i4 < 3) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w4[i] = nx[i];
+      }
+    }
+    uint32_t H[8], Lo[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) split2(v[2 * i], v[2 * i + 1], H[i], Lo[i]);
+    const uint32_t base = out_buf + part_base<128>(ch0 >> 6, 0) + row_base;
+    const int c8 = (ch0 & 63) >> 3;
+    const uint32_t a0 = base + (((c8) ^ r7) << 4), a1 = base + (((c8 + 1) ^ r7) << 4);
+    st_shared_v4(a0, H[0], H[1], H[2], H[3]);
+    st_shared_v4(a1, H[4], H[5], H[6], H[7]);
+    st_shared_v4(a0 + 128 * 128, Lo[0], Lo[1], Lo[2], Lo[3]);
+    st_shared_v4(a1 + 128 * 128, Lo[4], Lo[5], Lo[6], Lo[7]);
+  }
+}
+
+// Max-pool of the LAST layer.  Its MMAs run with the operand roles swapped (weights = A, M = 128 channels; the tile's
+// 128 points = B, N = 128 columns), so the accumulator has channels on the TMEM lanes and points along the columns: a
+// thread pools its channel over each group of `pool_g` consecutive columns in registers -- no cross-lane reduction, no
+// shared memory, no atomics -- and, bias and ReLU being monotone and per channel, applies them once per group to the
+// pooled RAW accumulator (max_cols relu(acc + b) == relu(max_cols(acc) + b) exactly).  Lanes = consecutive channels:
+// the store is one coalesced line per warp.  taddr = the warp's lane quarter at column 0 of the chunk's accumulator.
+__device__ __forceinline__ void epi_pool_cols(uint32_t taddr, int col_begin, int pool_g, float bias, bool relu,
+                                              float *__restrict__ out /* group's row + channel */, bool ch_ok) {
+  float mx = -INFINITY;
+#pragma unroll 1
+  for (int cb = 0; cb < pool_g; cb += 16) {
+    uint32_t r[16];
+    tmem_ld16(taddr + col_begin + cb, r);
+    float m4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      m4[i] = fmaxf(fmaxf(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1])),
+                    fmaxf(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])));
+    mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+  }
+  float v = mx + bias;
+  if (relu) v = fmaxf(v, 0.f);
+  if (ch_ok) *out = v;
+}
+
+// bias + (ReLU) -> this row of the staged output tile (row stride row_ls floats, see the copy-out in the kernel)
+template <bool RELU>
+__device__ __forceinline__ void epi_rows_staged(uint32_t taddr, const float *__restrict__ bias, int chunk0, int cb0, int cb1,
+                                                float *s_row) {
+#pragma unroll 1
+  for (int cb = cb0; cb < cb1; cb += 16) {
+    const int ch0 = chunk0 + cb;
+    uint32_t r[16];
+    float4 b4[4];
+#pragma unroll
+    for (int i4 = 0; i4 < 4; ++i4) b4[i4] = __ldg(reinterpret_cast<const float4 *>(bias + ch0) + i4);
+    tmem_ld16(taddr + cb, r);
+    float4 *dst = reinterpret_cast<float4 *>(s_row + ch0);
+#pragma unroll
+    for (int i4 = 0; i4 < 4; ++i4) {
+      float4 o = make_float4(__uint_as_float(r[i4 * 4]) + b4[i4].x, __uint_as_float(r[i4 * 4 + 1]) + b4[i4].y,
+                             __uint_as_float(r[i4 * 4 + 2]) + b4[i4].z, __uint_as_float(r[i4 * 4 + 3]) + b4[i4].w);
+      if (RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+      dst[i4] = o;
+    }
+  }
 }
 
 // Single-tile form of the points-as-M kernel (8 epilogue warps, each lane quarter's two warps share a
@@ -771,7 +923,8 @@ mlp_chain_pm1_kernel(const __grid_constant__ ChainP p) {
             for (int m = 0; m < mc; ++m) {
               const uint32_t d_tmem = tmem_base + m * 128;
               const int nch = min(128, cout16 - (m0 + m) * 128);
-              const uint32_t idesc = idesc0 | (static_cast<uint32_t>(nch >> 3) << 17);
+              const bool swap = p.pool_fast && l == p.n_layers - 1;        // pooled last layer: channels on the TMEM lanes
+              const uint32_t idesc = idesc0 | (static_cast<uint32_t>((swap ? 128 : nch) >> 3) << 17);
               for (int j = 0; j < L.cin_atoms; ++j) {
                 const int ks = min(4, L.ksteps - 4 * j);
                 const uint32_t a_hi = in_buf + part_base<NT>(j, 0), a_lo = a_hi + NT * 128;
@@ -779,20 +932,26 @@ mlp_chain_pm1_kernel(const __grid_constant__ ChainP p) {
                 mbar_wait(full + stage, phase, p.wait_hint);            // W_hi block
                 pf.stop(1);
                 tc_fence_after();
-                uint32_t w_base = smem_u32(ring + stage * kStageBytes);
-                for (int kk = 0; kk < ks; ++kk) {
-                  umma_bf16(d_tmem, make_desc(a_hi + kk * 32), make_desc(w_base + kk * 32), idesc, (j | kk) != 0 ? 1u : 0u, leader);
-                  umma_bf16(d_tmem, make_desc(a_lo + kk * 32), make_desc(w_base + kk * 32), idesc, 1u, leader);
-                }
+                const uint64_t d_ahi = make_desc(a_hi), d_alo = make_desc(a_lo);
+                uint64_t d_w = make_desc(smem_u32(ring + stage * kStageBytes));
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                  if (kk < ks) {
+                    umma_bf16(d_tmem, swap ? d_w + 2 * kk : d_ahi + 2 * kk, swap ? d_ahi + 2 * kk : d_w + 2 * kk, idesc,
+                              (j | kk) != 0 ? 1u : 0u, leader);
+                    umma_bf16(d_tmem, swap ? d_w + 2 * kk : d_alo + 2 * kk, swap ? d_alo + 2 * kk : d_w + 2 * kk, idesc, 1u, leader);
+                  }
                 umma_commit(empty + stage, leader);
                 if (++stage == p.nstage) { stage = 0; phase ^= 1; }
                 pf.start();
                 mbar_wait(full + stage, phase, p.wait_hint);            // W_lo block
                 pf.stop(1);
                 tc_fence_after();
-                w_base = smem_u32(ring + stage * kStageBytes);
-                for (int kk = 0; kk < ks; ++kk)
-                  umma_bf16(d_tmem, make_desc(a_hi + kk * 32), make_desc(w_base + kk * 32), idesc, 1u, leader);
+                d_w = make_desc(smem_u32(ring + stage * kStageBytes));
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                  if (kk < ks)
+                    umma_bf16(d_tmem, swap ? d_w + 2 * kk : d_ahi + 2 * kk, swap ? d_ahi + 2 * kk : d_w + 2 * kk, idesc, 1u, leader);
                 umma_commit(empty + stage, leader);
                 if (++stage == p.nstage) { stage = 0; phase ^= 1; }
               }
@@ -827,12 +986,23 @@ mlp_chain_pm1_kernel(const __grid_constant__ ChainP p) {
       mbar_arrive(act_ready);
       pf.stop(0);
       pf.acc[2] += 1;
+      // position columns of layer 0 as an epilogue term: this row's recentred position (pointset_abstraction.py:62-63)
+      float d3x = 0.f, d3y = 0.f, d3z = 0.f;
+      if (p.xyz_w != nullptr && row_ok) {
+        const float *a = p.xyz + (cloud * p.a_rows + __ldg(p.idx + col)) * 3;
+        const float *ce = p.centers + (col / p.group_k) * 3;
+        d3x = __fsub_rn(__ldg(a), __ldg(ce)); d3y = __fsub_rn(__ldg(a + 1), __ldg(ce + 1)); d3z = __fsub_rn(__ldg(a + 2), __ldg(ce + 2));
+      }
       for (int l = 0; l < p.n_layers; ++l) {
         const LayerP &L = p.L[l];
         const bool last = (l == p.n_layers - 1);
+        const bool xyz_term = l == 0 && p.xyz_w != nullptr;
         const uint32_t out_buf = smem_u32(act0);
         const int cout_pad = L.cout_chunks * 128, cout16 = (L.cout + 15) & ~15;
         const bool slow = (L.mask_bits != nullptr) || (L.out_cm != nullptr);
+        const int row_ls = cout16 + 4;                  // staged output row stride (floats): conflict-free float4 stores
+        const bool stage_rows = last && p.out_mode == CPFN_MLP_OUT_ROWS && L.cout_chunks <= wave_max &&
+                                128 * row_ls * 4 <= p.act_bytes0;
         const float *bias_base = L.bias + (L.bias_per_cloud ? cloud * cout_pad : 0);
         uint4 mbits = make_uint4(~0u, ~0u, ~0u, ~0u);     // this point's keep bits (thread = point)
         if (L.mask_bits != nullptr && row_ok) {
@@ -847,27 +1017,62 @@ mlp_chain_pm1_kernel(const __grid_constant__ ChainP p) {
           pf.start();
           mbar_wait(acc_full, acc_phase, p.wait_hint);
           pf.stop(1);
+          pf.start();
           acc_phase ^= 1;
           tc_fence_after();
           for (int m = 0; m < mc; ++m) {
             const int chunk0 = (m0 + m) * 128;
             const int nch = min(128, cout16 - chunk0);
             const int split = ((nch / 16 + 1) / 2) * 16;     // the quarter's two warps share the chunk's channels
+            const int cb0 = half ? split : 0, cb1 = half ? nch : split;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + m * 128;
+            // the combinations the network runs: straight-line loops (see epi_next); everything else: the generic body
+            if (last && p.pool_fast) {
+              // (chunk, pooling group) items, shared between the quarter's two warps
+              const int n_groups = 128 / p.pool_g;
+              const int ch = chunk0 + wq * 32 + lane;
+              const bool ch_ok = ch < L.cout;
+              for (int gi = 0; gi < n_groups; ++gi) {
+                if ((((m0 + m) * n_groups + gi) & 1) != half) continue;
+                const long long gcol = col0 + static_cast<long long>(gi) * p.pool_g;
+                const float bias = ch_ok ? __ldg(L.bias + (L.bias_per_cloud ? (gcol / p.cols_per_cloud) * cout_pad : 0) + ch) : 0.f;
+                epi_pool_cols(taddr, gi * p.pool_g, p.pool_g, bias, L.relu != 0, p.out + (gcol / p.pool_g) * p.ldo + ch, ch_ok);
+              }
+              continue;
+            }
+            if (!last && !slow) {
+              if (xyz_term) {
+                if (L.relu) epi_next_xyz<true>(taddr, reinterpret_cast<const float4 *>(p.xyz_w), d3x, d3y, d3z, chunk0, cb0, cb1, L.next_k16, out_buf, row_base, r7);
+                else epi_next_xyz<false>(taddr, reinterpret_cast<const float4 *>(p.xyz_w), d3x, d3y, d3z, chunk0, cb0, cb1, L.next_k16, out_buf, row_base, r7);
+              } else {
+                if (L.relu) epi_next<true>(taddr, bias_base, chunk0, cb0, cb1, L.next_k16, out_buf, row_base, r7);
+                else epi_next<false>(taddr, bias_base, chunk0, cb0, cb1, L.next_k16, out_buf, row_base, r7);
+              }
+              continue;
+            }
+            if (stage_rows && !slow) {
+              float *s_row = reinterpret_cast<float *>(act0) + row * row_ls;
+              if (L.relu) epi_rows_staged<true>(taddr, bias_base, chunk0, cb0, cb1, s_row);
+              else epi_rows_staged<false>(taddr, bias_base, chunk0, cb0, cb1, s_row);
+              continue;
+            }
 #pragma unroll 1
-            for (int cb = half ? split : 0; cb < (half ? nch : split); cb += 16) {
+            for (int cb = cb0; cb < cb1; cb += 16) {
               const int ch0 = chunk0 + cb;
               uint32_t r[16];
-              float4 b4[4];                            // the bias loads are in flight while the accumulators arrive
-#pragma unroll
-              for (int i4 = 0; i4 < 4; ++i4) b4[i4] = __ldg(reinterpret_cast<const float4 *>(bias_base + ch0) + i4);
-              tmem_ld16(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + m * 128 + cb, r);
               float v[16];
+              {
+                float4 b4[4];                            // the bias loads are in flight while the accumulators arrive
 #pragma unroll
-              for (int i4 = 0; i4 < 4; ++i4) {
-                v[i4 * 4] = __uint_as_float(r[i4 * 4]) + b4[i4].x;
-                v[i4 * 4 + 1] = __uint_as_float(r[i4 * 4 + 1]) + b4[i4].y;
-                v[i4 * 4 + 2] = __uint_as_float(r[i4 * 4 + 2]) + b4[i4].z;
-                v[i4 * 4 + 3] = __uint_as_float(r[i4 * 4 + 3]) + b4[i4].w;
+                for (int i4 = 0; i4 < 4; ++i4) b4[i4] = __ldg(reinterpret_cast<const float4 *>(bias_base + ch0) + i4);
+                tmem_ld16(taddr + cb, r);
+#pragma unroll
+                for (int i4 = 0; i4 < 4; ++i4) {
+                  v[i4 * 4] = __uint_as_float(r[i4 * 4]) + b4[i4].x;
+                  v[i4 * 4 + 1] = __uint_as_float(r[i4 * 4 + 1]) + b4[i4].y;
+                  v[i4 * 4 + 2] = __uint_as_float(r[i4 * 4 + 2]) + b4[i4].z;
+                  v[i4 * 4 + 3] = __uint_as_float(r[i4 * 4 + 3]) + b4[i4].w;
+                }
               }
               if (L.relu) {
 #pragma unroll
@@ -902,7 +1107,14 @@ mlp_chain_pm1_kernel(const __grid_constant__ ChainP p) {
                   st_shared_v4(a1 + NT * 128, Lo[4], Lo[5], Lo[6], Lo[7]);
                 }
               } else if (p.out_mode == CPFN_MLP_OUT_ROWS) {
-                if (row_ok) {
+                if (stage_rows) {
+                  // a thread owns a ROW: writing it straight to global memory is 32 scattered 4-byte stores per warp
+                  // instruction (the last, 35-channel layer of the heads chain cost more than a 128-channel one); the
+                  // tile's rows go through the (now free) operand tile instead and leave as coalesced stores below
+                  float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<float *>(act0) + row * row_ls + ch0);
+#pragma unroll
+                  for (int i4 = 0; i4 < 4; ++i4) dst[i4] = make_float4(v[i4 * 4], v[i4 * 4 + 1], v[i4 * 4 + 2], v[i4 * 4 + 3]);
+                } else if (row_ok) {
                   float *o = p.out + col * p.ldo + ch0;
 #pragma unroll
                   for (int i = 0; i < 16; ++i)
@@ -921,12 +1133,28 @@ mlp_chain_pm1_kernel(const __grid_constant__ ChainP p) {
               }
             }
           }
+          if (stage_rows && m0 + wave_max >= L.cout_chunks) {
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const long long left = p.cols - col0;
+            const int nr = left < 128 ? static_cast<int>(left) : 128;
+            const float *s_out = reinterpret_cast<const float *>(act0);
+            float *g_out = p.out + col0 * p.ldo;
+            const int t = w8 * 32 + lane, dr = 256 / L.cout, dc = 256 % L.cout;
+            int r = t / L.cout, c = t % L.cout;
+            while (r < nr) {
+              g_out[static_cast<long long>(r) * p.ldo + c] = s_out[r * row_ls + c];
+              r += dr; c += dc;
+              if (c >= L.cout) { c -= L.cout; ++r; }
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");      // the next tile's loader overwrites the operand tile
+          }
           tc_fence_before();
           const bool final_wave = last && (m0 + wave_max >= L.cout_chunks);
           if (!final_wave) {
             fence_proxy_async();
             mbar_arrive(act_ready);
           }
+          pf.lap(p, 10 + min(l, 5));
         }
       }
     }
@@ -1023,7 +1251,8 @@ mlp_chain_pm_kernel(const __grid_constant__ ChainP p) {
             for (int m = 0; m < L.cout_chunks; ++m) {
               const uint32_t d_tmem = tmem_base + g * sub_cols + m * 128;
               const int nch = min(128, cout16 - m * 128);
-              const uint32_t idesc = idesc0 | (static_cast<uint32_t>(nch >> 3) << 17);
+              const bool swap = p.pool_fast && l == p.n_layers - 1;        // pooled last layer: channels on the TMEM lanes
+              const uint32_t idesc = idesc0 | (static_cast<uint32_t>((swap ? 128 : nch) >> 3) << 17);
               for (int j = 0; j < L.cin_atoms; ++j) {
                 const int ks = min(4, L.ksteps - 4 * j);
                 const uint32_t a_hi = in_buf + part_base<NT>(j, 0), a_lo = a_hi + NT * 128;
@@ -1031,20 +1260,26 @@ mlp_chain_pm_kernel(const __grid_constant__ ChainP p) {
                 mbar_wait(full + stage, phase, p.wait_hint);            // W_hi block
                 pf.stop(1);
                 tc_fence_after();
-                uint32_t w_base = smem_u32(ring + stage * kStageBytes);
-                for (int kk = 0; kk < ks; ++kk) {
-                  umma_bf16(d_tmem, make_desc(a_hi + kk * 32), make_desc(w_base + kk * 32), idesc, (j | kk) != 0 ? 1u : 0u, leader);
-                  umma_bf16(d_tmem, make_desc(a_lo + kk * 32), make_desc(w_base + kk * 32), idesc, 1u, leader);
-                }
+                const uint64_t d_ahi = make_desc(a_hi), d_alo = make_desc(a_lo);
+                uint64_t d_w = make_desc(smem_u32(ring + stage * kStageBytes));
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                  if (kk < ks) {
+                    umma_bf16(d_tmem, swap ? d_w + 2 * kk : d_ahi + 2 * kk, swap ? d_ahi + 2 * kk : d_w + 2 * kk, idesc,
+                              (j | kk) != 0 ? 1u : 0u, leader);
+                    umma_bf16(d_tmem, swap ? d_w + 2 * kk : d_alo + 2 * kk, swap ? d_alo + 2 * kk : d_w + 2 * kk, idesc, 1u, leader);
+                  }
                 umma_commit(empty + stage, leader);
                 if (++stage == p.nstage) { stage = 0; phase ^= 1; }
                 pf.start();
                 mbar_wait(full + stage, phase, p.wait_hint);            // W_lo block
                 pf.stop(1);
                 tc_fence_after();
-                w_base = smem_u32(ring + stage * kStageBytes);
-                for (int kk = 0; kk < ks; ++kk)
-                  umma_bf16(d_tmem, make_desc(a_hi + kk * 32), make_desc(w_base + kk * 32), idesc, 1u, leader);
+                d_w = make_desc(smem_u32(ring + stage * kStageBytes));
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                  if (kk < ks)
+                    umma_bf16(d_tmem, swap ? d_w + 2 * kk : d_ahi + 2 * kk, swap ? d_ahi + 2 * kk : d_w + 2 * kk, idesc, 1u, leader);
                 umma_commit(empty + stage, leader);
                 if (++stage == p.nstage) { stage = 0; phase ^= 1; }
               }
@@ -1101,42 +1336,35 @@ mlp_chain_pm_kernel(const __grid_constant__ ChainP p) {
         pf.start();
         mbar_wait(acc_full + g, acc_phase, p.wait_hint);
         pf.stop(1);
+        pf.start();
         acc_phase ^= 1;
         tc_fence_after();
         if (last && p.pool_fast) {
-          // Max-pool of the last layer without atomics and without touching bias / ReLU per element: both are
-          // monotone and the bias is per channel, so max_rows relu(acc + b) == relu(max_rows(acc) + b) exactly.  Every warp
-          // reduces its 32 rows per channel with one CREDUX on the raw accumulators, the four warps of the sub-tile meet in
-          // shared memory, and thread c finishes channel c of every pooling group of the tile with a plain store.
-          float *s_pool = reinterpret_cast<float *>(s_brow);                 // [4][cout16] (no interpolation rows here)
-#pragma unroll 1
-          for (int ch0 = 0; ch0 < cout16; ch0 += 16) {
-            uint32_t r[16];
-            tmem_ld16(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + g * sub_cols + ch0, r);
-            float m[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) m[i] = warp_max_f32(__uint_as_float(r[i]));
-            if (lane == 0) {
-              float4 *dst = reinterpret_cast<float4 *>(s_pool + wq * cout16 + ch0);
-#pragma unroll
-              for (int i4 = 0; i4 < 4; ++i4) dst[i4] = make_float4(m[i4 * 4], m[i4 * 4 + 1], m[i4 * 4 + 2], m[i4 * 4 + 3]);
+          // pooled last layer: channels on the TMEM lanes, points along the columns (see epi_pool_cols)
+          const int n_groups = 128 / p.pool_g;
+          for (int m = 0; m < L.cout_chunks; ++m) {
+            const int ch = m * 128 + wq * 32 + lane;
+            const bool ch_ok = ch < L.cout;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + g * sub_cols + m * 128;
+            for (int gi = 0; gi < n_groups; ++gi) {
+              const long long gcol = col0 + static_cast<long long>(gi) * p.pool_g;
+              const float bias = ch_ok ? __ldg(L.bias + (L.bias_per_cloud ? (gcol / p.cols_per_cloud) * cout_pad : 0) + ch) : 0.f;
+              epi_pool_cols(taddr, gi * p.pool_g, p.pool_g, bias, L.relu != 0, p.out + (gcol / p.pool_g) * p.ldo + ch, ch_ok);
             }
           }
           tc_fence_before();
-          asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(128) : "memory");
-          const int wpg = p.pool_g >> 5, n_groups = 128 / p.pool_g;
-          const long long group0 = col0 / p.pool_g;
-          for (int c = row; c < L.cout; c += 128) {
-            for (int gi = 0; gi < n_groups; ++gi) {
-              float mx = s_pool[(gi * wpg) * cout16 + c];
-              for (int w = 1; w < wpg; ++w) mx = fmaxf(mx, s_pool[(gi * wpg + w) * cout16 + c]);
-              const long long gcloud = (col0 + static_cast<long long>(gi) * p.pool_g) / p.cols_per_cloud;
-              float v = mx + __ldg(L.bias + (L.bias_per_cloud ? gcloud * cout_pad : 0) + c);
-              if (L.relu) v = fmaxf(v, 0.f);
-              p.out[(group0 + gi) * p.ldo + c] = v;
-            }
-          }
+          pf.lap(p, 10 + min(l, 5));
           continue;      // last layer: nothing to publish (the next tile's loader meets this sub-tile's warps at its barrier)
+        }
+        if (!last && !slow) {           // the common layer: straight-line loop (see epi_next)
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + g * sub_cols;
+          if (L.relu) epi_next<true>(taddr, bias_base, 0, 0, cout16, L.next_k16, my_act, row_base, r7);
+          else epi_next<false>(taddr, bias_base, 0, 0, cout16, L.next_k16, my_act, row_base, r7);
+          tc_fence_before();
+          fence_proxy_async();
+          mbar_arrive(act_ready + g);
+          pf.lap(p, 10 + min(l, 5));
+          continue;
         }
 #pragma unroll 1
         for (int ch0 = 0; ch0 < cout16; ch0 += 16) {
@@ -1209,6 +1437,7 @@ mlp_chain_pm_kernel(const __grid_constant__ ChainP p) {
           fence_proxy_async();
           mbar_arrive(act_ready + g);
         }
+        pf.lap(p, 10 + min(l, 5));
       }
     }
     if (pf.on) {
@@ -1291,6 +1520,13 @@ int launch_chain(const cpfn_mlp_chain_t *c, cudaStream_t st) {
   p.l0_w = c->l0_w; p.l0_b = c->l0_b; p.l0_cout = c->l0_cout;
   p.in_bias = c->in_bias;
   if (c->in_bias != nullptr && c->in_mode != CPFN_MLP_IN_INTERP) return CPFN_EINVAL;
+  p.xyz_w = c->xyz_w;
+  if (c->xyz_w != nullptr) {
+    if (NT != 128 || c->in_mode != CPFN_MLP_IN_GROUP || c->a_ch <= 0 || c->l0_w != nullptr || c->layers[0].bias_per_cloud ||
+        c->layers[0].mask_bits || c->layers[0].out_cm || c->n_layers < 2)
+      return CPFN_EINVAL;
+    width = c->a_ch;
+  }
   if (c->l0_w != nullptr) {
     if (c->in_mode != CPFN_MLP_IN_GROUP || c->a_ch != 0 || !c->l0_b || c->l0_cout <= 0 || (c->l0_cout & 3)) return CPFN_EINVAL;
     width = c->l0_cout;
@@ -1308,12 +1544,11 @@ int launch_chain(const cpfn_mlp_chain_t *c, cudaStream_t st) {
     if (c->pool_g <= 0 || (c->pool_g % 32) != 0 || !c->layers[c->n_layers - 1].relu ||
         (c->cols_per_cloud % c->pool_g) != 0) return CPFN_EINVAL;
     atomic_pool = true;
-    // ... unless whole pooling groups sit inside full tiles: then the sub-tile's warps meet in shared memory (no atomics,
-    // no zero fill).  Decided after the kernel variant is known (two-sub-tile kernel only).
+    // ... unless whole pooling groups sit inside full tiles: then the last layer runs with the operand roles swapped
+    // and every thread pools its own channel over the group's columns (epi_pool_cols: no atomics, no zero fill)
     const cpfn_mlp_layer_t &last = c->layers[c->n_layers - 1];
     const long long span = c->win_cols > 0 ? c->win_cols : c->cols_per_cloud;
-    if ((c->pool_g == 32 || c->pool_g == 64 || c->pool_g == 128) && (span % 128) == 0 && c->in_mode != CPFN_MLP_IN_INTERP &&
-        ((last.cout + 15) & ~15) <= 192 && !last.mask_bits && !last.out_cm)
+    if ((c->pool_g == 32 || c->pool_g == 64 || c->pool_g == 128) && (span % 128) == 0 && !last.mask_bits && !last.out_cm)
       p.pool_fast = 1;
   } else if (c->out_mode == CPFN_MLP_OUT_POOL) {
     if (c->pool_g <= 0 || (c->pool_g % 16) != 0 || !c->layers[c->n_layers - 1].relu) return CPFN_EINVAL;
@@ -1336,6 +1571,7 @@ int launch_chain(const cpfn_mlp_chain_t *c, cudaStream_t st) {
   if (NT == 128 && 2 * act_need[0] + overhead > max_smem / 2 - 1024 && act_need[0] + overhead <= max_smem / 2 - 1024 &&
       pow2_at_least(128 * max_chunks) <= 256)
     two_sub = false;
+  if (NT == 128 && c->xyz_w != nullptr) two_sub = false;       // the position term lives in the one-tile kernel's epilogue
   p.tmem_cols = NT == 128 ? (two_sub ? 2 : 1) * pow2_at_least(128 * max_chunks)
                           : pow2_at_least(NT * (max_chunks < 512 / NT ? max_chunks : 512 / NT));
   p.act_bytes0 = static_cast<int>(act_need[0]);
@@ -1359,7 +1595,8 @@ int launch_chain(const cpfn_mlp_chain_t *c, cudaStream_t st) {
   const size_t smem = fixed + static_cast<size_t>(nstage) * kStageBytes;
   void (*kern)(ChainP) = mlp_chain_kernel<NT>;
   if (NT == 128) kern = two_sub ? mlp_chain_pm_kernel : mlp_chain_pm1_kernel;
-  if (!(NT == 128 && two_sub)) p.pool_fast = 0;
+  if (NT != 128) p.pool_fast = 0;
+  if (p.pool_fast && !two_sub && p.L[c->n_layers - 1].cout_chunks * 128 > p.tmem_cols) p.pool_fast = 0;   // one TMEM wave
   if (p.pool_fast) atomic_pool = false;
   CPFN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const int sms = sm_count() > 0 ? sm_count() : 148;

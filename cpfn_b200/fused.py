@@ -42,7 +42,8 @@ class _Chain(ctypes.Structure):
                 ("pool_g", ctypes.c_int32), ("split_cout", ctypes.c_int32),
                 ("l0_w", ctypes.c_void_p), ("l0_b", ctypes.c_void_p), ("l0_cout", ctypes.c_int32),
                 ("in_bias", ctypes.c_void_p), ("out_prezeroed", ctypes.c_int32),
-                ("win_cols", ctypes.c_int32), ("win_off", ctypes.c_int32), ("max_ctas", ctypes.c_int32)]
+                ("win_cols", ctypes.c_int32), ("win_off", ctypes.c_int32), ("max_ctas", ctypes.c_int32),
+                ("xyz_w", ctypes.c_void_p)]
 
 
 def available():
@@ -105,7 +106,7 @@ class PackedChain:
 def run_chain(pc, B, cols_per_cloud, out, ldo, tile_cols=128, in_mode=IN_DENSE, a_src=None, a_ch=0, a_rows=0,
               idx=None, xyz=None, centers=None, group_k=0, b_src=None, b_ch=0, b_rows=0, nn_w=None,
               out_mode=OUT_ROWS, pool_g=0, biases=None, bias_per_cloud=(), masks=None, out_cm=None, split_cout=False,
-              l0=None, in_bias=None, out_prezeroed=False, window=None, max_ctas=0):
+              l0=None, in_bias=None, out_prezeroed=False, window=None, max_ctas=0, xyz_w=None):
     """Enqueue one fused chain on torch's current stream.  ``window`` = (first column, columns) of every cloud."""
     c = _Chain()
     c.n_layers = len(pc.dims)
@@ -135,6 +136,8 @@ def run_chain(pc, B, cols_per_cloud, out, ldo, tile_cols=128, in_mode=IN_DENSE, 
     if window is not None:
         c.win_off, c.win_cols = int(window[0]), int(window[1])
     c.max_ctas = int(max_ctas)
+    if xyz_w is not None:       # GROUP + features: the position columns of layer 0 as an epilogue term ([cout_pad, 4] fp32)
+        c.xyz_w = xyz_w.data_ptr()
     with torch.cuda.device(out.device):
         _lib.check(_lib.lib().cpfn_mlp_chain(ctypes.byref(c), torch.cuda.current_stream(out.device).cuda_stream),
                    "mlp_chain")
@@ -165,7 +168,7 @@ def _pick_tile(dims, cols_per_cloud, need_cloud_aligned=False, prefer=128):
             need *= 2
         elif any((cout + 127) // 128 > 512 // tile for _, cout, _ in dims[:-1]):
             continue
-        if need + 1024 + 8192 + 3 * 16384 <= 227 * 1024:
+        if need + 1024 + 10240 + 3 * 16384 <= 227 * 1024:
             return tile
     raise RuntimeError("cpfn_b200.fused: chain does not fit shared memory: %r" % (dims,))
 
@@ -188,6 +191,8 @@ def run_layerwise(pc, B, cols_per_cloud, out, first, out_mode=OUT_ROWS, pool_g=0
         tile = 64 if cols_per_cloud % 64 == 0 else 32
         if (c.dims[0][0] + 63) // 64 * 2 * tile * 128 + 5120 + 3 * 16384 > 227 * 1024:
             tile = 32
+        if os.environ.get("CPFN_TILE_LAYERWISE"):
+            tile = int(os.environ["CPFN_TILE_LAYERWISE"])
         run_chain(c, B, cols_per_cloud, dst, cout, tile_cols=tile, split_cout=True,
                   out_mode=(out_mode if last else OUT_ROWS), pool_g=(pool_g if last else 0),
                   out_prezeroed=(out_prezeroed and last), **x_kwargs, **extra)
@@ -347,6 +352,19 @@ def _sa_chain(module, device):
             l0 = (torch.from_numpy(np.ascontiguousarray(w0)).to(device), torch.from_numpy(np.ascontiguousarray(b0)).to(device))
         pc = PackedChain(layers, device)
         pc.l0 = l0
+        pc.alt = None
+        w0, b0, _ = layers[0]
+        D = w0.shape[1] - 3
+        if l0 is None and not module.group_all and D > 0 and D % 64 == 0 and len(layers) > 1:
+            # features + positions: the three position columns of layer 0 leave the tensor-core operand (they would cost a
+            # whole 64-channel K atom of shared memory, which is what keeps 128-column tiles from fitting) and come back
+            # as an fp32 term of layer 0's epilogue: rows (wx, wy, wz, bias) per output channel (cpfn_mlp_chain_t.xyz_w)
+            rows = np.zeros(((w0.shape[0] + 127) // 128 * 128, 4), dtype=np.float32)
+            rows[:w0.shape[0], :3] = w0[:, D:D + 3]
+            rows[:w0.shape[0], 3] = b0
+            alt = PackedChain([(np.ascontiguousarray(w0[:, :D]), b0, True)] + layers[1:], device)
+            alt.xyz_w = torch.from_numpy(rows).to(device)
+            pc.alt = alt
         _store(module, _CACHE_ATTR, pc, sources, device)
     return pc
 
@@ -485,6 +503,16 @@ def sa_forward_pm(module, xyz, feats_pm, indices=None, out=None):
     pre = out is not None
     if not pre:
         out = torch.empty(B, S, cout, dtype=torch.float32, device=dev)
+    alt = getattr(pc, "alt", None)
+    if (alt is not None and D > 0 and (S * K) % 128 == 0 and K in (32, 64, 128) and cout <= 256
+            and os.environ.get("CPFN_SA_XYZ_EPILOGUE", "1") != "0"
+            and max((cin + 63) // 64 for cin, _, _ in alt.dims) * 2 * 128 * 128 + 12288 + 2 * 16384 <= 113 * 1024):
+        # 128-column tiles on the points-as-M kernel (half the epilogue instructions per element of the 64-column,
+        # channels-as-M kernel), positions as an epilogue term, pooled through shared memory
+        run_chain(alt, B, S * K, out, cout, tile_cols=128, in_mode=IN_GROUP, a_src=feats_pm, a_ch=D, a_rows=N,
+                  idx=group_idx, xyz=xyz, centers=new_xyz, group_k=K, out_mode=OUT_POOL, pool_g=K, xyz_w=alt.xyz_w,
+                  out_prezeroed=pre)
+        return new_xyz, out
     run_chain(pc, B, S * K, out, cout, tile_cols=pick_tile(pc.dims, S * K, name=('SA1' if D == 0 else 'SA2'), prefer=(128 if D == 0 else 64)), in_mode=IN_GROUP, a_src=feats_pm, a_ch=D, a_rows=N,
               idx=group_idx, xyz=xyz, centers=new_xyz, group_k=K, out_mode=OUT_POOL, pool_g=K, l0=getattr(pc, "l0", None),
               out_prezeroed=pre)

@@ -258,6 +258,12 @@ typedef struct {
   /* > 0: upper bound on the number of (persistent) CTAs of the launch, for a chain that shares the GPU with another
    * kernel which must keep its SMs (the CTAs loop over the tiles, so any number works). */
   int32_t max_ctas;
+  /* GROUP mode with features (a_ch > 0), tile_cols 128: layer 0's three position columns kept OUT of the tensor-core
+   * operand.  xyz_w = [128 * ceil(cout0 / 128)][4] fp32 rows (wx, wy, wz, bias) of layer 0; layers[0].cin is then a_ch
+   * (no position columns, no K atom of padding for them) and layer 0's epilogue adds
+   * wx * dx + wy * dy + wz * dz + bias in fp32, (dx, dy, dz) = xyz[idx] - centre as in pointset_abstraction.py:62-63.
+   * layers[0].bias is ignored.  NULL: the position columns are the last three input channels of layer 0. */
+  const float *xyz_w;
 } cpfn_mlp_chain_t;
 
 /* Replaces the conv+BN+ReLU(+max) chains of pointset_abstraction.py:61-74,

@@ -200,6 +200,42 @@ def test_layerwise_equals_fused_chain(cuda_dev):
     assert _rel(o[:, :40], g @ w.t() + bb) < 1e-5 and float(o[:, 40:].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("feat_ch,K,S,cout", [(128, 64, 24, 256), (64, 32, 28, 128), (128, 128, 5, 200)])
+def test_positions_as_epilogue_term(cuda_dev, feat_ch, K, S, cout):
+    """GROUP mode with features on 128-column tiles: the three position columns of layer 0 enter as an fp32 term of
+    its epilogue (cpfn_mlp_chain_t.xyz_w) and the pooled output leaves through shared memory -- same result as the
+    reference composition and as the 64-column kernel with the positions inside the operand."""
+    rng = np.random.default_rng(feat_ch + K + S)
+    B, N = 2, 600
+    dims = [feat_ch + 3, 128, 128, cout]
+    pc, layers = _chain(dims, rng, cuda_dev)
+    w0, b0, _ = layers[0]
+    alt = fused.PackedChain([(np.ascontiguousarray(w0[:, :feat_ch]), b0, True)] + layers[1:], cuda_dev)
+    rows = np.zeros((128, 4), dtype=np.float32)
+    rows[:, :3], rows[:, 3] = w0[:, feat_ch:], b0
+    xyz_w = torch.from_numpy(rows).to(cuda_dev)
+    xyz = torch.from_numpy(rng.normal(size=(B, N, 3)).astype(np.float32)).to(cuda_dev)
+    feats = torch.from_numpy(rng.normal(size=(B, N, feat_ch)).astype(np.float32)).to(cuda_dev)
+    centers = torch.from_numpy(rng.normal(size=(B, S, 3)).astype(np.float32)).to(cuda_dev)
+    idx = torch.from_numpy(rng.integers(0, N, size=(B, S, K)).astype(np.int32)).to(cuda_dev)
+    out = torch.full((B, S, cout), float("nan"), device=cuda_dev)
+    fused.run_chain(alt, B, S * K, out, cout, tile_cols=128, in_mode=fused.IN_GROUP, a_src=feats, a_ch=feat_ch, a_rows=N,
+                    idx=idx, xyz=xyz, centers=centers, group_k=K, out_mode=fused.OUT_POOL, pool_g=K, xyz_w=xyz_w)
+    old = torch.full((B, S, cout), float("nan"), device=cuda_dev)
+    fused.run_chain(pc, B, S * K, old, cout, tile_cols=64, in_mode=fused.IN_GROUP, a_src=feats, a_ch=feat_ch, a_rows=N,
+                    idx=idx, xyz=xyz, centers=centers, group_k=K, out_mode=fused.OUT_POOL, pool_g=K)
+    li = idx.long()
+    g_xyz = torch.gather(xyz, 1, li.reshape(B, S * K, 1).expand(-1, -1, 3)).reshape(B, S, K, 3) - centers[:, :, None, :]
+    g_f = torch.gather(feats, 1, li.reshape(B, S * K, 1).expand(-1, -1, feat_ch)).reshape(B, S, K, feat_ch)
+    ref = _ref(torch.cat([g_f, g_xyz], dim=3), layers).max(dim=2)[0]
+    assert torch.isfinite(out).all()
+    assert _rel(out, ref) < TOL, _rel(out, ref)
+    assert _rel(out, old) < TOL, _rel(out, old)
+    with pytest.raises(RuntimeError):                     # the term belongs to the 128-column kernel
+        fused.run_chain(alt, B, S * K, out, cout, tile_cols=64, in_mode=fused.IN_GROUP, a_src=feats, a_ch=feat_ch,
+                        a_rows=N, idx=idx, xyz=xyz, centers=centers, group_k=K, out_mode=fused.OUT_POOL, pool_g=K, xyz_w=xyz_w)
+
+
 def test_first_layer_on_cuda_cores(cuda_dev):
     """GROUP mode on bare positions with the 3 -> 64 first layer evaluated in fp32 by the tile builder."""
     rng = np.random.default_rng(21)

@@ -40,9 +40,9 @@ def main():
         r = a[i]
         ct = max(r[8], 1.0)
         k = lambda v: v / ct / 1e3
-        print("%-2d %-12s %6.0f %8.2f | %10.1f %10.1f %8.1f | %8.1f %8.1f | %8.1f %8.1f %8.1f" % (
+        print("%-2d %-12s %6.0f %8.2f | %10.1f %10.1f %8.1f | %8.1f %8.1f | %8.1f %8.1f %8.1f | epilogue per layer: %s" % (
             i, names[i] if per == len(names) else "", r[8], r[9] / ct, k(r[0]), k(r[1]), k(r[2]), k(r[3]), k(r[4]),
-            k(r[5]), k(r[6]), k(r[7])))
+            k(r[5]), k(r[6]), k(r[7]), " ".join("%.1f" % k(v) for v in r[10:16] if v > 0)))
 
 
 if __name__ == "__main__":
