@@ -299,7 +299,11 @@ __device__ void load_tile(const ChainP &p, uint32_t buf, long long col0, int w8,
       float d3[3];
 #pragma unroll
       for (int q = 0; q < 3; ++q) d3[q] = valid ? __fsub_rn(__ldg(a + q), __ldg(ce + q)) : 0.f;
-      if (p.l0_w != nullptr) {
+      if (p.l0_w != nullptr && NW == 4 && p.l0_cout == 64) {
+        // 64-channel first layer, four loader warps: the rows only leave their recentred positions here; the layer
+        // itself runs below with the weights in registers (lane = 4 channels)
+        reinterpret_cast<float4 *>(s_brow)[t] = make_float4(d3[0], d3[1], d3[2], 0.f);
+      } else if (p.l0_w != nullptr) {
         // first shared-MLP layer (3 input channels) in fp32 on the CUDA cores: relu(W0 d + b0); a K = 3
         // contraction would waste 13/16 of a tensor-core pass and a whole MMA / epilogue round trip
         for (int c4 = 0; c4 < (p.l0_cout >> 2); ++c4) {
@@ -330,6 +334,33 @@ __device__ void load_tile(const ChainP &p, uint32_t buf, long long col0, int w8,
     for (int ch = pad_from; ch < k16; ++ch) store_scalar<NT>(buf, t, ch, 0.f);   // K padding must be finite zeros
   }
   asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(NW * 32) : "memory");
+  if (p.in_mode == CPFN_MLP_IN_GROUP && p.l0_w != nullptr && NW == 4 && p.l0_cout == 64) {
+    // relu(W0 d + b0) for the tile, lane = 4 output channels whose 12 weights + 4 biases stay in registers (the per-row
+    // version re-loaded all 256 of them for every row: 64 uniform loads per row).  A warp covers rows
+    // (lane >> 4) + 2 * warp + 8 * it: (row & 7) is fixed per thread, so the swizzled store offset is a constant plus
+    // 1024 bytes per step and the 16 steps unroll into immediate offsets.  Same arithmetic, bit for bit, as the loop above.
+    const int q = lane & 15, r7 = (lane >> 4) + 2 * w8;
+    const float4 wa = __ldg(reinterpret_cast<const float4 *>(p.l0_w) + q * 3);
+    const float4 wb = __ldg(reinterpret_cast<const float4 *>(p.l0_w) + q * 3 + 1);
+    const float4 wc = __ldg(reinterpret_cast<const float4 *>(p.l0_w) + q * 3 + 2);
+    const float4 bb = __ldg(reinterpret_cast<const float4 *>(p.l0_b) + q);
+    const uint32_t o_hi = buf + static_cast<uint32_t>(r7 * 128) + static_cast<uint32_t>((((q >> 1) ^ r7) << 4) | ((q & 1) << 3));
+    const float4 *sd = reinterpret_cast<const float4 *>(s_brow) + r7;
+#pragma unroll
+    for (int it = 0; it < NT / 8; ++it) {
+      const float4 d = sd[8 * it];
+      const float o0 = fmaxf(fmaf(wa.z, d.z, fmaf(wa.y, d.y, fmaf(wa.x, d.x, bb.x))), 0.f);
+      const float o1 = fmaxf(fmaf(wb.y, d.z, fmaf(wb.x, d.y, fmaf(wa.w, d.x, bb.y))), 0.f);
+      const float o2 = fmaxf(fmaf(wc.x, d.z, fmaf(wb.w, d.y, fmaf(wb.z, d.x, bb.z))), 0.f);
+      const float o3 = fmaxf(fmaf(wc.w, d.z, fmaf(wc.z, d.y, fmaf(wc.y, d.x, bb.w))), 0.f);
+      uint32_t H01, L01, H23, L23;
+      split2(o0, o1, H01, L01);
+      split2(o2, o3, H23, L23);
+      st_shared_v2(o_hi + it * 1024, H01, H23);
+      st_shared_v2(o_hi + it * 1024 + NT * 128, L01, L23);
+    }
+    return;
+  }
   constexpr int RB = 8;
   const int nA4 = p.a_ch >> 2;
   if (nA4 > 0) {
