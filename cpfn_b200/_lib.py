@@ -28,6 +28,8 @@ SIGNATURES = {
     "cpfn_sm_count": (c_int, []),
     "cpfn_debug_fps_profile": (c_int, [c_void_p]),
     "cpfn_debug_chain_profile": (c_int, [c_void_p, c_int, c_int]),
+    "cpfn_sym_eigh_small": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_void_p]),
+    "cpfn_small_solve": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, c_void_p, c_void_p]),
     "cpfn_fps_rounds_supported": (c_int, [c_int, c_int]),
     "cpfn_furthest_point_sampling_rounds": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                                     c_size_t, c_size_t, c_void_p]),

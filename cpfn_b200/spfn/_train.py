@@ -4,7 +4,9 @@ The O(B*N*K) work -- every sum over the points the reference's fitters take -- i
 the raw weighted moments M[b,k,:] = sum_n w[b,n,k] * psi(P[b,n], X[b,n]) (psi: monomials up to third
 order, 32 features), computed by the CUDA kernel ``cpfn_weighted_moments`` with fp64 accumulation;
 its backward (dW, dX) is ``cpfn_weighted_moments_grad``.  Everything after that is algebra on
-[B,K,3,3]-sized tensors, done here in float64 torch so that autograd differentiates it:
+[B,K,3,3]-sized tensors in float64: the eigen-decompositions and the linear solves are the batched one-thread-per-
+matrix kernels of csrc/small_linalg.cu (``cpfn_sym_eigh_small``, ``cpfn_small_solve``; no cuSOLVER / MAGMA call and no
+host synchronisation on the path), the identities around them element-wise torch so that autograd differentiates them:
   * ``svd_v_last_column``: forward = eigenvector of the eigenvalue smallest in magnitude (what
     ``torch.svd(M)[2][:, :, -1]`` is for a symmetric M); backward = the reference's analytic formula
     with its guarded 1/(s_i^2 - s_j^2) matrix (SPFN/differentiable_tls.py:8-17, 45-53, 123-143);
@@ -94,6 +96,58 @@ def _t3(m10):
     return m10[..., idx]
 
 
+def sym_eigh(M, vectors=True):
+    """Symmetric [*,D,D] float64 (D = 2, 3) -> (eigenvalues ascending [*,D], eigenvectors in columns [*,D,D] | None),
+    the contract of torch.linalg.eigh, through cpfn_sym_eigh_small.  Not differentiable (callers detach or carry their
+    own backward).  CPU tensors raise: there is no CPU path."""
+    if not M.is_cuda:
+        raise RuntimeError("CPU not supported")
+    D = M.shape[-1]
+    A = M.detach().to(torch.float64).contiguous()
+    n = A.numel() // (D * D)
+    lam = torch.empty(A.shape[:-1], dtype=torch.float64, device=A.device)
+    Q = torch.empty_like(A) if vectors else None
+    with torch.cuda.device(A.device):
+        _lib.check(_lib.lib().cpfn_sym_eigh_small(A.data_ptr(), n, D, lam.data_ptr(), Q.data_ptr() if vectors else None,
+                                                  torch.cuda.current_stream(A.device).cuda_stream), "sym_eigh_small")
+    cuda_ops.count_launches(1)
+    return lam, Q
+
+
+def _solve_raw(A, b, transpose):
+    D = A.shape[-1]
+    A = A.detach().to(torch.float64).contiguous()
+    b = b.detach().to(torch.float64).contiguous()
+    x = torch.empty_like(b)
+    with torch.cuda.device(A.device):
+        _lib.check(_lib.lib().cpfn_small_solve(A.data_ptr(), b.data_ptr(), b.numel() // D, D, int(transpose), x.data_ptr(),
+                                               torch.cuda.current_stream(A.device).cuda_stream), "small_solve")
+    cuda_ops.count_launches(1)
+    return x
+
+
+class _SmallSolve(torch.autograd.Function):
+    """x = A^-1 b for [*,D,D], [*,D] (D <= 3) through cpfn_small_solve; backward: db = A^-T g, dA = -db x^T."""
+
+    @staticmethod
+    def forward(ctx, A, b):
+        if not A.is_cuda:
+            raise RuntimeError("CPU not supported")
+        x = _solve_raw(A, b, False)
+        ctx.save_for_backward(A.detach(), x)
+        return x
+
+    @staticmethod
+    def backward(ctx, g):
+        A, x = ctx.saved_tensors
+        gb = _solve_raw(A, g, True)
+        return -gb.unsqueeze(-1) * x.unsqueeze(-2), gb
+
+
+def small_solve(A, b):
+    return _SmallSolve.apply(A, b)
+
+
 def guard_one_over_matrix(M, min_abs_value=1e-10):
     """SPFN/differentiable_tls.py:8-17."""
     n = M.shape[-1]
@@ -108,7 +162,7 @@ class _SvdVLastColumn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, M):
-        lam, Q = torch.linalg.eigh(M)                       # symmetric: singular values = |eigenvalues|
+        lam, Q = sym_eigh(M)                                # symmetric: singular values = |eigenvalues|
         s = lam.abs()
         order = torch.argsort(s, dim=-1, descending=True, stable=True)
         s = torch.gather(s, -1, order)
@@ -144,12 +198,12 @@ def guarded_solve(AtA, Atb, condition_number_cap=1e5, ls_l2_regularizer=1e-8):
     """Normal-equation form of guarded_matrix_solve_ls (SPFN/geometry_utils.py:131-141).
     AtA [*,D,D], Atb [*,D] -> x [*,D]."""
     D = AtA.shape[-1]
-    s = torch.linalg.eigvalsh(AtA.detach()).abs()
+    s = sym_eigh(AtA, vectors=False)[0].abs()
     mask = ((s.max(dim=-1)[0] / s.min(dim=-1)[0]) < condition_number_cap).to(AtA.dtype)
     eye = torch.eye(D, dtype=AtA.dtype, device=AtA.device)
     A = AtA * mask[..., None, None] + ls_l2_regularizer * eye
     b = Atb * mask[..., None]
-    return torch.linalg.solve(A, b.unsqueeze(-1)).squeeze(-1)
+    return small_solve(A, b)
 
 
 def compute_consistent_plane_frame(normal):

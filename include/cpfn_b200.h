@@ -199,6 +199,18 @@ CPFN_API int cpfn_weighted_moments(const float *P, const float *X, const float *
 CPFN_API int cpfn_weighted_moments_grad(const float *P, const float *X, const float *Wt, const double *dM,
                                         int B, int N, int K, float *dWt, float *dX, cpfn_stream_t stream);
 
+/* Batched tiny linear algebra of the differentiable fitters, fp64, one thread per matrix (csrc/small_linalg.cu).
+ * Replaces the torch.svd of Custom_svd_v_colum (SPFN/differentiable_tls.py:123-143; symmetric operands, so the
+ * singular vectors are the eigenvectors) and the torch.solve of guarded_matrix_solve_ls
+ * (SPFN/geometry_utils.py:131-141, normal equations) on [B*K, D, D]-sized batches.
+ *   cpfn_sym_eigh_small: A [n, D, D] symmetric, D = 2 or 3 -> lam [n, D] ascending, Q [n, D, D] eigenvectors in the
+ *                        columns (Q may be NULL: eigenvalues only)
+ *   cpfn_small_solve:    A [n, D, D], b [n, D], D <= 3 -> x [n, D] with A x = b (transpose != 0: A^T x = b),
+ *                        Gaussian elimination with partial pivoting */
+CPFN_API int cpfn_sym_eigh_small(const double *A, long long n, int D, double *lam, double *Q, cpfn_stream_t stream);
+CPFN_API int cpfn_small_solve(const double *A, const double *b, long long n, int D, int transpose, double *x,
+                              cpfn_stream_t stream);
+
 /* ---------------------------------------------------------------------------
  * Fused shared-MLP chains (set abstraction, feature propagation, heads) on the
  * tcgen05 tensor cores.  Inference only: BatchNorm is folded into the weights.

@@ -132,15 +132,15 @@ def fitter_loss(params, W_np, torch):
     total = 0.0
     for key in sorted(params):
         v = params[key]
-        mask = torch.as_tensor(fit_mask("grad", key, W_np).astype(np.float32), device=v.device)
+        mask = torch.as_tensor(fit_mask("grad", key, W_np).astype(np.float32), device=v.device).to(v.dtype)
         if key in ("plane_normal", "cylinder_axis"):
-            G = torch.as_tensor(rng.normal(size=(3, 3)).astype(np.float32), device=v.device)
+            G = torch.as_tensor(rng.normal(size=(3, 3)).astype(np.float32), device=v.device).to(v.dtype)
             total = total + (mask * torch.einsum("bki,ij,bkj->bk", v, G, v)).sum()
         elif key == "plane_center":
             g = float(rng.normal())
             total = total + (mask * g * v * v).sum()
         else:
-            G = torch.as_tensor(rng.normal(size=tuple(v.shape)).astype(np.float32), device=v.device)
+            G = torch.as_tensor(rng.normal(size=tuple(v.shape)).astype(np.float32), device=v.device).to(v.dtype)
             m = mask if v.dim() == 2 else mask.unsqueeze(-1)
             total = total + (m * G * v).sum()
     return total
