@@ -61,6 +61,7 @@ SIGNATURES = {
     "cpfn_weighted_moments_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                            c_void_p, c_void_p]),
     "cpfn_three_nn_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "cpfn_three_nn_weights_sorted": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "cpfn_linear_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "cpfn_gather_xyz": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "cpfn_normalise_patches": (c_int, [c_void_p, ctypes.c_longlong, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -68,8 +68,14 @@ three_nn_weights_kernel(const float *__restrict__ unknown, const float *__restri
 // candidates per query instead of all m.  Every CTA builds the grid once and answers kNnGridQ queries per thread.
 constexpr int kNnGridQ = 2;
 
+// `sorted_q` (optional): the queries as (x, y, z, index bits) records in a spatially sorted order -- the cell-ordered
+// copy of the cloud that the ball-query grid of the same cloud already holds (cpfn_ball_query_grid_build).  Thread j
+// then answers record j and writes the result at the record's own index: the 32 queries of a warp sit in one or two
+// cells of that grid, walk the same cells of the known cloud's grid and load the same records (broadcasts) instead of
+// diverging over the whole cloud.  Same result, query by query.
 __global__ void __launch_bounds__(kGlueThreads)
-three_nn_weights_grid_kernel(const float *__restrict__ unknown, const float *__restrict__ known, int n, int m,
+three_nn_weights_grid_kernel(const float *__restrict__ unknown, const float4 *__restrict__ sorted_q,
+                             const float *__restrict__ known, int n, int m,
                              float *__restrict__ weight, int32_t *__restrict__ idx) {
   extern __shared__ __align__(16) unsigned char s_grid_raw[];
   const int b = blockIdx.y;
@@ -79,10 +85,18 @@ three_nn_weights_grid_kernel(const float *__restrict__ unknown, const float *__r
   nn_grid_build(known + static_cast<size_t>(b) * m * 3, m, s_grid_raw, g, recs, cell_start);
 #pragma unroll 1
   for (int q = 0; q < kNnGridQ; ++q) {
-    const int j = (blockIdx.x * kNnGridQ + q) * kGlueThreads + threadIdx.x;
+    int j = (blockIdx.x * kNnGridQ + q) * kGlueThreads + threadIdx.x;
     if (j >= n) continue;
-    const float *u = unknown + (static_cast<size_t>(b) * n + j) * 3;
-    const Nn3 r = nn_grid_query(__ldg(u), __ldg(u + 1), __ldg(u + 2), g, recs, cell_start);
+    float ux, uy, uz;
+    if (sorted_q != nullptr) {
+      const float4 rec = __ldg(sorted_q + static_cast<size_t>(b) * n + j);
+      ux = rec.x; uy = rec.y; uz = rec.z;
+      j = __float_as_int(rec.w);
+    } else {
+      const float *u = unknown + (static_cast<size_t>(b) * n + j) * 3;
+      ux = __ldg(u); uy = __ldg(u + 1); uz = __ldg(u + 2);
+    }
+    const Nn3 r = nn_grid_query(ux, uy, uz, g, recs, cell_start);
     const float r1 = __frcp_rn(__fadd_rn(__fsqrt_rn(r.d1), 1e-8f));
     const float r2 = __frcp_rn(__fadd_rn(__fsqrt_rn(r.d2), 1e-8f));
     const float r3 = __frcp_rn(__fadd_rn(__fsqrt_rn(r.d3), 1e-8f));
@@ -460,12 +474,27 @@ extern "C" int cpfn_three_nn_weights(const float *unknown, const float *known, i
     if (gsmem > 48 * 1024)
       CPFN_CUDA_TRY(cudaFuncSetAttribute(three_nn_weights_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(gsmem)));
     dim3 ggrid((n + kGlueThreads * kNnGridQ - 1) / (kGlueThreads * kNnGridQ), B);
-    three_nn_weights_grid_kernel<<<ggrid, kGlueThreads, gsmem, as_stream(stream)>>>(unknown, known, n, m, weight, idx);
+    three_nn_weights_grid_kernel<<<ggrid, kGlueThreads, gsmem, as_stream(stream)>>>(unknown, nullptr, known, n, m, weight, idx);
     return check_launch();
   }
   dim3 grid((n + kGlueThreads - 1) / kGlueThreads, B);
   const size_t smem = sizeof(float4) * static_cast<size_t>(m < kNnTile ? (m > 0 ? m : 1) : kNnTile);
   three_nn_weights_kernel<<<grid, kGlueThreads, smem, as_stream(stream)>>>(unknown, known, n, m, weight, idx);
+  return check_launch();
+}
+
+extern "C" int cpfn_three_nn_weights_sorted(const void *sorted_queries, const float *known, int B, int n, int m,
+                                            float *weight, int32_t *idx, cpfn_stream_t stream) {
+  using namespace cpfn;
+  if (B < 0 || n < 0 || m < 0) return CPFN_EINVAL;
+  if (B == 0 || n == 0) return CPFN_OK;
+  if (!sorted_queries || !known || !weight || !idx || B > 65535 || m < kNnGridMin || m > kNnGridMax) return CPFN_EINVAL;
+  const size_t gsmem = nn_grid_smem_bytes(m);
+  if (gsmem > 48 * 1024)
+    CPFN_CUDA_TRY(cudaFuncSetAttribute(three_nn_weights_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(gsmem)));
+  dim3 ggrid((n + kGlueThreads * kNnGridQ - 1) / (kGlueThreads * kNnGridQ), B);
+  three_nn_weights_grid_kernel<<<ggrid, kGlueThreads, gsmem, as_stream(stream)>>>(
+      nullptr, static_cast<const float4 *>(sorted_queries), known, n, m, weight, idx);
   return check_launch();
 }
 

@@ -23,71 +23,74 @@ constexpr int kSegThreads = 256;
 constexpr int kSegMaxK = 64;
 
 // grid (chunks, B).  Thread t owns slot k = t % K and point lane t / K; a point lane adds w into ITS OWN row table
-// s_tab[lane][g][k], so no two threads ever touch the same word.
+// s_tab[lane][g][k], so no two threads ever touch the same word.  Column K of a row counts the lane's points with that
+// label (added by the lane's k = 0 thread; exact in fp32: a lane sees far fewer than 2^24 points).
 template <typename IndexT>
 __global__ void __launch_bounds__(kSegThreads)
 seg_sums_kernel(const float *__restrict__ W, const IndexT *__restrict__ I, int N, int K, int G, int per_cta,
                 double *__restrict__ part, int *__restrict__ n_gt) {
-  extern __shared__ float s_tab[];                        // [lanes][G + 1][K]  (row G: points without a label)
+  extern __shared__ float s_tab[];                        // [lanes][G + 1][K + 1]  (row G: points without a label)
   const int b = blockIdx.y, t = threadIdx.x;
+  const int K1 = K + 1;
   const int lanes = kSegThreads / K;
   const bool active = t < lanes * K;
   const int k = active ? t % K : 0, lane = t / K;
-  for (int i = t; i < lanes * (G + 1) * K; i += kSegThreads) s_tab[i] = 0.f;
+  for (int i = t; i < lanes * (G + 1) * K1; i += kSegThreads) s_tab[i] = 0.f;
   __syncthreads();
   const int n0 = blockIdx.x * per_cta, n1 = min(N, n0 + per_cta);
   int top = -1;
   if (active) {
-    float *tab = s_tab + static_cast<size_t>(lane) * (G + 1) * K + k;
+    float *tab = s_tab + static_cast<size_t>(lane) * (G + 1) * K1 + k;
+    float *cnt = s_tab + static_cast<size_t>(lane) * (G + 1) * K1 + K;
     const float *w = W + (static_cast<size_t>(b) * N) * K + k;
     const IndexT *lab = I + static_cast<size_t>(b) * N;
     for (int n = n0 + lane; n < n1; n += lanes) {
       const long long g = static_cast<long long>(lab[n]);
       top = max(top, static_cast<int>(g));
       const int row = (g >= 0 && g < G) ? static_cast<int>(g) : G;
-      tab[row * K] += __ldg(w + static_cast<size_t>(n) * K);
+      tab[row * K1] += __ldg(w + static_cast<size_t>(n) * K);
+      if (k == 0) cnt[row * K1] += 1.f;
     }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) top = max(top, __shfl_xor_sync(0xffffffffu, top, o));
   if ((t & 31) == 0 && top >= 0) atomicMax(n_gt + b, top + 1);
   __syncthreads();
-  // fixed-order fp64 combination of the point lanes -> this CTA's partial [G + 1][K]
-  double *out = part + (static_cast<size_t>(b) * gridDim.x + blockIdx.x) * (G + 1) * K;
-  for (int i = t; i < (G + 1) * K; i += kSegThreads) {
+  // fixed-order fp64 combination of the point lanes -> this CTA's partial [G + 1][K + 1]
+  double *out = part + (static_cast<size_t>(b) * gridDim.x + blockIdx.x) * (G + 1) * K1;
+  for (int i = t; i < (G + 1) * K1; i += kSegThreads) {
     double s = 0.0;
-    for (int l = 0; l < lanes; ++l) s += static_cast<double>(s_tab[static_cast<size_t>(l) * (G + 1) * K + i]);
+    for (int l = 0; l < lanes; ++l) s += static_cast<double>(s_tab[static_cast<size_t>(l) * (G + 1) * K1 + i]);
     out[i] = s;
   }
 }
 
-// S[b,g,k] (g < G), colsum[b,k] = sum over ALL points, count[b,g] = points with label g  (fp32 outputs)
-template <typename IndexT>
+// S[b,g,k] (g < G), colsum[b,k] = sum over ALL points, count[b,g] = points with label g  (fp32 outputs): the chunks'
+// partial tables added in a fixed order.  (Round 2: the label counts come from the tables too -- one CTA per cloud
+// counting the labels again with shared-memory atomics took 2-3 ms on a 1 M-point cloud.)
 __global__ void __launch_bounds__(kSegThreads)
-seg_finish_kernel(const double *__restrict__ part, const IndexT *__restrict__ I, int N, int K, int G, int chunks,
+seg_finish_kernel(const double *__restrict__ part, int K, int G, int chunks,
                   float *__restrict__ S, float *__restrict__ colsum, float *__restrict__ count) {
   const int b = blockIdx.x, t = threadIdx.x;
-  __shared__ int s_count[kSegMaxK + 1];
-  for (int i = t; i <= G; i += kSegThreads) s_count[i] = 0;
-  __syncthreads();
-  for (int n = t; n < N; n += kSegThreads) {
-    const long long g = static_cast<long long>(I[static_cast<size_t>(b) * N + n]);
-    if (g >= 0 && g < G) atomicAdd(&s_count[g], 1);
-  }
-  for (int i = t; i < (G + 1) * K; i += kSegThreads) {
+  const int K1 = K + 1;
+  extern __shared__ double s_tot[];                       // [(G + 1)][K + 1]
+  const double *pb = part + static_cast<size_t>(b) * chunks * (G + 1) * K1;
+  for (int i = t; i < (G + 1) * K1; i += kSegThreads) {
     double s = 0.0;
-    for (int c = 0; c < chunks; ++c) s += part[(static_cast<size_t>(b) * chunks + c) * (G + 1) * K + i];
-    if (i < G * K) S[static_cast<size_t>(b) * G * K + i] = static_cast<float>(s);
-    // column sums: all rows of the table, added in a second sweep below (needs every row)
+    for (int c = 0; c < chunks; ++c) s += pb[static_cast<size_t>(c) * (G + 1) * K1 + i];
+    s_tot[i] = s;
+    const int g = i / K1, kk = i - g * K1;
+    if (g < G) {
+      if (kk < K) S[(static_cast<size_t>(b) * G + g) * K + kk] = static_cast<float>(s);
+      else count[static_cast<size_t>(b) * G + g] = static_cast<float>(s);
+    }
   }
   __syncthreads();
   for (int kk = t; kk < K; kk += kSegThreads) {
     double s = 0.0;
-    for (int g = 0; g <= G; ++g)
-      for (int c = 0; c < chunks; ++c) s += part[(static_cast<size_t>(b) * chunks + c) * (G + 1) * K + g * K + kk];
+    for (int g = 0; g <= G; ++g) s += s_tot[g * K1 + kk];
     colsum[static_cast<size_t>(b) * K + kk] = static_cast<float>(s);
   }
-  for (int g = t; g < G; g += kSegThreads) count[static_cast<size_t>(b) * G + g] = static_cast<float>(s_count[g]);
 }
 
 // One warp per sample; lane j = column j (K <= 32).  scipy/optimize/rectangular_lsap (maximize=True => cost negated).
@@ -200,7 +203,7 @@ extern "C" size_t cpfn_seg_workspace_bytes(int B, int N, int K, int G) {
   int chunks = (2 * sms + B - 1) / B;
   if (chunks > (N + 255) / 256) chunks = (N + 255) / 256;
   if (chunks < 1) chunks = 1;
-  return sizeof(double) * static_cast<size_t>(B) * chunks * (G + 1) * K + 256;
+  return sizeof(double) * static_cast<size_t>(B) * chunks * (G + 1) * (K + 1) + 256;
 }
 
 extern "C" int cpfn_label_membership_sums(const float *W, const void *labels, int labels_are_int64, int B, int N, int K,
@@ -217,17 +220,18 @@ extern "C" int cpfn_label_membership_sums(const float *W, const void *labels, in
   if (chunks < 1) chunks = 1;
   const int per_cta = (N + chunks - 1) / chunks;
   const int lanes = kSegThreads / K;
-  const size_t smem = sizeof(float) * static_cast<size_t>(lanes) * (G + 1) * K;
+  const size_t smem = sizeof(float) * static_cast<size_t>(lanes) * (G + 1) * (K + 1);
+  const size_t fsmem = sizeof(double) * static_cast<size_t>(G + 1) * (K + 1);
   double *part = static_cast<double *>(workspace);
   CPFN_CUDA_TRY(cudaMemsetAsync(n_gt, 0, sizeof(int32_t) * B, st));
   if (labels_are_int64) {
     if (smem > 48 * 1024) CPFN_CUDA_TRY(cudaFuncSetAttribute(seg_sums_kernel<long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     seg_sums_kernel<long long><<<dim3(chunks, B), kSegThreads, smem, st>>>(W, static_cast<const long long *>(labels), N, K, G, per_cta, part, n_gt);
-    seg_finish_kernel<long long><<<B, kSegThreads, 0, st>>>(part, static_cast<const long long *>(labels), N, K, G, chunks, S, colsum, count);
+    seg_finish_kernel<<<B, kSegThreads, fsmem, st>>>(part, K, G, chunks, S, colsum, count);
   } else {
     if (smem > 48 * 1024) CPFN_CUDA_TRY(cudaFuncSetAttribute(seg_sums_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     seg_sums_kernel<int32_t><<<dim3(chunks, B), kSegThreads, smem, st>>>(W, static_cast<const int32_t *>(labels), N, K, G, per_cta, part, n_gt);
-    seg_finish_kernel<int32_t><<<B, kSegThreads, 0, st>>>(part, static_cast<const int32_t *>(labels), N, K, G, chunks, S, colsum, count);
+    seg_finish_kernel<<<B, kSegThreads, fsmem, st>>>(part, K, G, chunks, S, colsum, count);
   }
   return check_launch();
 }

@@ -222,15 +222,22 @@ def _stream(t):
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
-def three_nn_weights(unknown, known):
+def three_nn_weights(unknown, known, sorted_queries=None):
     """unknown [B,n,3], known [B,m,3] -> (weights f32 [B,n,3], idx int32 [B,n,3]): three_nn + sqrt +
-    normalised inverse-distance weights in one kernel."""
+    normalised inverse-distance weights in one kernel.  ``sorted_queries``: a ball-query grid workspace of ``unknown``
+    (cpfn_ball_query_grid_build) -- the queries are then answered in its cell order (same result, coherent warps)."""
     B, n, _ = unknown.shape
+    m = known.shape[1]
     w = torch.empty(B, n, 3, dtype=torch.float32, device=unknown.device)
     idx = torch.empty(B, n, 3, dtype=torch.int32, device=unknown.device)
     with torch.cuda.device(unknown.device):
-        _lib.check(_lib.lib().cpfn_three_nn_weights(unknown.data_ptr(), known.data_ptr(), B, n, known.shape[1],
-                                                    w.data_ptr(), idx.data_ptr(), _stream(unknown)), "three_nn_weights")
+        if sorted_queries is not None and 384 <= m <= 2048 and os.environ.get("CPFN_NN_SORTED", "1") != "0":
+            _lib.check(_lib.lib().cpfn_three_nn_weights_sorted(sorted_queries.data_ptr(), known.data_ptr(), B, n, m,
+                                                               w.data_ptr(), idx.data_ptr(), _stream(unknown)),
+                       "three_nn_weights_sorted")
+        else:
+            _lib.check(_lib.lib().cpfn_three_nn_weights(unknown.data_ptr(), known.data_ptr(), B, n, m,
+                                                        w.data_ptr(), idx.data_ptr(), _stream(unknown)), "three_nn_weights")
     cuda_ops.count_launches(1)
     return w, idx
 
@@ -376,7 +383,7 @@ def sa_indices(module, xyz):
     return new_xyz, cuda_ops.ball_query(new_xyz, xyz, module.radius_list[0], module.num_samples_list[0])
 
 
-def sa_indices_overlapped(module, xyz, side):
+def sa_indices_overlapped(module, xyz, side, return_grid=False):
     """``sa_indices`` with the ball query's uniform grid -- which depends on the cloud and the radius, not on the
     centroids -- built on ``side`` while farthest point sampling runs on the current stream (FPS leaves more than
     half of the SMs idle).  Same result as ``sa_indices``."""
@@ -385,7 +392,7 @@ def sa_indices_overlapped(module, xyz, side):
     radius, K = float(module.radius_list[0]), int(module.num_samples_list[0])
     L = _lib.lib()
     if side is None or not (2048 <= N <= 32768) or radius <= 0 or os.environ.get("CPFN_BQ_NO_GRID"):
-        return sa_indices(module, xyz)
+        return sa_indices(module, xyz) + ((None,) if return_grid else ())
     main = torch.cuda.current_stream(dev)
     nbytes = L.cpfn_ball_query_grid_workspace_bytes(B, N)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
@@ -406,6 +413,8 @@ def sa_indices_overlapped(module, xyz, side):
         _lib.check(L.cpfn_ball_query_grid_query(new_xyz.data_ptr(), xyz.data_ptr(), B, N, S, radius, K, idx.data_ptr(),
                                                 ws.data_ptr(), nbytes, main.cuda_stream), "ball_query_grid_query")
     cuda_ops.count_launches(2)
+    if return_grid:
+        return new_xyz, idx, ws
     return new_xyz, idx
 
 
@@ -718,14 +727,15 @@ def pointnet2_forward(model, P, dropout=True, rng_slot=0):
     if piped is not None:
         l1_xyz, l1, l1_done = piped
     else:
-        idx1 = sa_indices_overlapped(model.sa1, P, side if side is not main else None)
+        # (the grid workspace starts with the cloud in cell order: FP3's 3-NN answers its queries in that order)
+        *idx1, grid_ws = sa_indices_overlapped(model.sa1, P, side if side is not main else None, return_grid=True)
         l1_xyz = idx1[0]
     fork = torch.cuda.Event()
     fork.record(main)
     with torch.cuda.stream(side):
         side.wait_event(fork)
         idx2 = sa_indices(model.sa2, l1_xyz)
-        nn3 = three_nn_weights(P, l1_xyz)
+        nn3 = three_nn_weights(P, l1_xyz, sorted_queries=grid_ws if piped is None else None)
         nn2 = three_nn_weights(l1_xyz, idx2[0])
         # the reference's always-on dropout (pn2_network.py:63): same generator, same mask, as 1 bit per element.
         # (Not under the sampling: its CTAs would share the sampling SMs and stretch every round -- measured.)
@@ -741,6 +751,8 @@ def pointnet2_forward(model, P, dropout=True, rng_slot=0):
     if side is not main:
         for t in (*idx2, *nn3, *nn2) + ((mask[0],) if mask is not None else ()):
             t.record_stream(main)
+        if piped is None and grid_ws is not None:
+            grid_ws.record_stream(side)
     l2_xyz, l2 = sa_forward_pm(model.sa2, l1_xyz, l1, indices=idx2)
     _, l3 = sa_forward_pm(model.sa3, l2_xyz, l2)
     l4 = fp_forward_pm(model.sfp1, l2_xyz, None, l2, l3)

@@ -293,6 +293,13 @@ CPFN_API int cpfn_mlp_chain(const cpfn_mlp_chain_t *chain, cpfn_stream_t stream)
  * (pointset_feature_propagation.py:38-42).  weight, idx: [B,n,3]. */
 CPFN_API int cpfn_three_nn_weights(const float *unknown, const float *known, int B, int n, int m,
                                    float *weight, int32_t *idx, cpfn_stream_t stream);
+/* The same for queries given as (x, y, z, index bits) float4 records in a spatially sorted order: the first B * n
+ * records of a cpfn_ball_query_grid_build workspace of the SAME cloud (cell order).  Thread j answers record j and
+ * writes weight / idx at the record's own index, so the result equals cpfn_three_nn_weights on the original order
+ * while a warp's queries share their candidate cells.  384 <= m <= 2048 (the shared-memory grid of the known
+ * cloud); other sizes: CPFN_EINVAL (use cpfn_three_nn_weights). */
+CPFN_API int cpfn_three_nn_weights_sorted(const void *sorted_queries, const float *known, int B, int n, int m,
+                                          float *weight, int32_t *idx, cpfn_stream_t stream);
 
 /* new_xyz[b,s,:] = xyz[b, idx[b,s], :] (select_point_subset on positions,
  * pointset_abstraction.py:50).  xyz [B,N,3], idx [B,S] -> out [B,S,3]. */

@@ -285,3 +285,25 @@ def test_three_nn_grid_equals_scan(cuda_dev, oracle_ops, name):
     assert torch.equal(iw_grid, iw_scan) and torch.equal(w_grid, w_scan)
     d_ref, i_ref = oracle_ops.three_nn(u, k)
     assert np.array_equal(i_grid.cpu().numpy(), i_ref) and np.array_equal(d_grid.cpu().numpy(), d_ref)
+
+
+@pytest.mark.parametrize("B,n,m,radius", [(3, 8192, 512, 0.2), (2, 5000, 384, 0.1), (1, 2048, 2048, 0.3)])
+def test_three_nn_weights_on_cell_sorted_queries(cuda_dev, B, n, m, radius):
+    """cpfn_three_nn_weights_sorted: the queries taken from the cell-ordered copy of the cloud that the ball-query grid
+    holds (coherent warps) -- weights and indices identical, query by query, to the kernel on the original order."""
+    from cpfn_b200 import _lib, fused, synth
+    P = torch.from_numpy(synth.shape_batch(B, n, seed=n + m)[0]).to(cuda_dev)
+    known = fused.gather_xyz(P, cuda_ops.farthest_point_sampling(P, m))
+    L = _lib.lib()
+    nbytes = L.cpfn_ball_query_grid_workspace_bytes(B, n)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=cuda_dev)
+    _lib.check(L.cpfn_ball_query_grid_build(P.data_ptr(), B, n, radius, ws.data_ptr(), nbytes,
+                                            torch.cuda.current_stream(cuda_dev).cuda_stream), "grid_build")
+    w0, i0 = fused.three_nn_weights(P, known)
+    w1, i1 = fused.three_nn_weights(P, known, sorted_queries=ws)
+    assert torch.equal(i0, i1) and torch.equal(w0, w1)
+    recs = ws[: B * n * 16].view(torch.float32).reshape(B, n, 4)
+    order = recs[:, :, 3].contiguous().view(torch.int32).long()
+    assert torch.equal(order.sort(dim=1)[0], torch.arange(n, device=cuda_dev).expand(B, n))     # a permutation per cloud
+    assert torch.equal(torch.gather(P, 1, order.unsqueeze(-1).expand(-1, -1, 3)), recs[:, :, :3])
+
