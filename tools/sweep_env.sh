@@ -7,9 +7,9 @@ d=json.loads(sys.stdin.read().strip().splitlines()[-1])
 print('%-40s pipelined %.4f  sequential %.4f  e2e %.4f ms  fps %.1f us' % ('$*', d['ms_per_step'], d['sequential_ms_per_step'], 16*8192/d['e2e']['value']*1e3, d['roofline']['kernel_us']))"
 }
 run A=0
-run CPFN_FPS_CLUSTER=2
 run CPFN_TILE_LAYERWISE=32
-run CPFN_LANES=4
-run CPFN_LANES=8
-run CPFN_LANES=8 CPFN_FPS_CLUSTER=2
 run A=1
+run CPFN_TILE_LAYERWISE=32
+run CPFN_LANES=8
+run CPFN_LANES=10
+run A=2
