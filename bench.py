@@ -474,9 +474,17 @@ def run_ours(args):
         assert n_done == args.steps
 
     barrier()
-    cascade = cascade_bench(dev, rank, world) if not os.environ.get("CPFN_BENCH_NO_CASCADE") else []
+    # sub-records (evidence beside the headline metric): a failure in one of them must not take the line down
+    try:
+        cascade = cascade_bench(dev, rank, world) if not os.environ.get("CPFN_BENCH_NO_CASCADE") else []
+    except Exception as e:
+        cascade = [{"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}]
     barrier()
-    training = training_bench(dev, rank, world) if not os.environ.get("CPFN_BENCH_NO_TRAIN") else {"unavailable": "skipped"}
+    try:
+        training = (training_bench(dev, rank, world) if not os.environ.get("CPFN_BENCH_NO_TRAIN")
+                    else {"unavailable": "skipped"})
+    except Exception as e:
+        training = {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
     barrier()
     t = torch.tensor([dev_ms, e2e_s * 1e3, lat_s * 1e3, seq_ms], dtype=torch.float64, device=dev)
     if world > 1:

@@ -99,3 +99,13 @@ def test_argument_validation_needs_no_gpu(built_lib):
     assert L.cpfn_fps_dense_workspace_bytes() > 0
     assert L.cpfn_heuristic_merging_host(null, null, 0, null, 4, null) == -1
     assert L.cpfn_merge_solve_host_f32(null, 4, 0.0, null, null) == -1
+    # round-2 entry points
+    assert L.cpfn_three_nn_weights_sorted(one, one, 2, 100, 128, one, one, null) == -1         # m below the grid range
+    assert L.cpfn_three_nn_weights_sorted(null, one, 2, 100, 512, one, one, null) == -1
+    assert L.cpfn_sym_eigh_small(one, 4, 4, one, one, null) == -1                               # D = 2 or 3 only
+    assert L.cpfn_sym_eigh_small(null, 4, 3, one, one, null) == -1
+    assert L.cpfn_small_solve(one, one, 4, 4, 0, one, null) == -1                               # D <= 3
+    assert L.cpfn_small_solve(one, null, 4, 3, 0, one, null) == -1
+    assert L.cpfn_debug_chain_profile(null, 4, 0) == -1                                         # profiling not enabled
+    assert L.cpfn_seg_workspace_bytes(2, 1000, 28, 28) >= 2 * 29 * 29 * 8
+    assert L.cpfn_seg_workspace_bytes(2, 1000, 80, 28) == 0                                      # > 64 slots
