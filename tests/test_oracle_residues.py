@@ -39,11 +39,13 @@ def test_non_hot_path_names_come_from_the_reference(built_lib):
         from SPFN import losses_implementation, metric_implementation
         import cpfn_b200.spfn as ours
         assert losses_implementation is ours.losses_implementation
-        fn = losses_implementation.hungarian_matching                     # not restated here: the reference's own
+        fn = losses_implementation.compute_normal_loss                    # not restated here: the reference's own
         assert fn.__module__.startswith("cpfn_b200.spfn._ref_") and "SPFN/losses_implementation.py" in fn.__code__.co_filename
         # ... and inside the reference's module the hot-path functions are this package's
         ref = ours._reference.load("losses_implementation", {})
         assert ref.compute_parameters is ours.losses_implementation.compute_parameters
+        assert ref.hungarian_matching is ours.losses_implementation.hungarian_matching        # device matching (row f3)
+        assert ref.compute_miou_loss is ours.losses_implementation.compute_miou_loss
         assert ref.plane_fitter is ours.plane_fitter
         assert callable(metric_implementation.compute_Sk_coverage)
         with pytest.raises(AttributeError):
