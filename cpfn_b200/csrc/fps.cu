@@ -338,17 +338,30 @@ fps_cluster_kernel(const float *__restrict__ xyz, float *__restrict__ new_xyz, i
 #define FPS_MARK(i) if (PROFILE) { const long long c1 = clock64(); pt[i] += c1 - c0; c0 = c1; }
   if (PROFILE) c0 = clock64();
   for (int j = max(1, j_begin); j < j_end; ++j) {
-    float best = -1.0f;
-    uint32_t bc = 0u;
+    // running minima, then the thread's arg-max in the reference's order (even i first, then odd i: increasing
+    // reference rank; of equal distances the earlier one wins).  "Later wins only if strictly greater" is associative,
+    // so the scan is a balanced tree over that order: 3 dependent compare / select levels for 8 points instead of 8.
+    float dv[PPT];
+    uint32_t cv[PPT];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int q = 0; q < PPT; ++q) {
+      const int i = (q < (PPT + 1) / 2) ? 2 * q : 2 * (q - (PPT + 1) / 2) + 1;
+      const float d2 = fminf(sqdist3(px[i], py[i], pz[i], cx, cy, cz), tmp[i]);
+      tmp[i] = d2;
+      dv[q] = d2;
+      cv[q] = code[i];
+    }
 #pragma unroll
-      for (int i = h; i < PPT; i += 2) {     // even i first, then odd i: increasing reference rank
-        const float d2 = fminf(sqdist3(px[i], py[i], pz[i], cx, cy, cz), tmp[i]);
-        tmp[i] = d2;
-        if (d2 > best) { best = d2; bc = code[i]; }
+    for (int w = 1; w < PPT; w <<= 1) {
+#pragma unroll
+      for (int q = 0; q + w < PPT; q += 2 * w) {
+        const bool later = dv[q + w] > dv[q];
+        dv[q] = later ? dv[q + w] : dv[q];
+        cv[q] = later ? cv[q + w] : cv[q];
       }
     }
+    const float best = dv[0] > -1.0f ? dv[0] : -1.0f;      // all points dead (-1): no candidate, as the scan from -1
+    const uint32_t bc = dv[0] > -1.0f ? cv[0] : 0u;
     uint32_t hi = 0u, lo = 0u;
     if (best >= 0.0f) {
       hi = __float_as_uint(best);
