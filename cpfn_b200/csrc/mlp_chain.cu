@@ -10,21 +10,28 @@
 //
 // One CTA owns a tile of NT columns (grouped samples, or points) and carries it through
 // EVERY layer of the chain without leaving the SM:
-//   8 worker warps build the input tile [NT x Cin] in shared memory (gather by ball-query index
+//   worker warps  build the input tile [NT x Cin] in shared memory (gather by ball-query index
 //                 and recentre / 3-point weighted interpolation + skip concat / dense rows) in the
 //                 canonical K-major 128-byte-swizzled UMMA layout;
-//   MMA thread    for each layer issues tcgen05.mma.kind::f16 (M = 128 output channels, N = NT
-//                 columns, K = 16 per instruction): D[ch, col] += W[ch, k] * A[col, k], with the
-//                 fp32 accumulators in TMEM;
+//   MMA warp      for each layer issues tcgen05.mma.kind::f16 (K = 16 per instruction) with the fp32
+//                 accumulators in TMEM.  The warp runs its loops warp-uniformly and predicates only the
+//                 tcgen05 instructions on elect.sync, so descriptors and addresses live in uniform
+//                 registers (inside an `if (lane == 0)` ptxas wrapped every UTCHMMA in an ELECT /
+//                 R2UR.BROADCAST / BRA.U.ANY loop: ~200 cycles per MMA issued);
 //   producer      streams the BN-folded, pre-swizzled weight blocks (16 KB = 128 ch x 64 k bf16)
 //                 through an mbarrier ring with cp.async.bulk (TMA bulk copy), running ahead
 //                 across layer boundaries;
-//   worker warps  read the accumulators back (tcgen05.ld, thread = channel), add the folded
-//                 bias, apply ReLU (and the dropout mask), and write the activations as the NEXT
-//                 layer's operand tile straight into shared memory -- or, after the last layer,
-//                 max-pool over each group of columns in registers / store the rows.
+//   worker warps  read the accumulators back (tcgen05.ld), add the folded bias, apply ReLU (and the
+//                 dropout bits), and write the activations as the NEXT layer's operand tile straight
+//                 into shared memory -- or, after the last layer, max-pool over each group of columns
+//                 in registers / store the rows.
+// Two operand orientations: channels = M (mlp_chain_kernel<64|32>: thread = channel in the epilogue) and
+// points = M (mlp_chain_pm_kernel / mlp_chain_pm1_kernel: thread = point, half the epilogue instructions per
+// element); the points-as-M kernels switch to channels = M for a POOLED last layer (weights as the A
+// operand), so that the pooling is an in-register max over TMEM columns (epi_pool_cols).
 // The grouped tensor, the interpolated tensor and all intermediate activations never exist in
-// HBM.
+// HBM.  CPFN_CHAIN_PROFILE=1 makes every launch record where its MMA warp, its producer and a worker
+// warp spend their cycles (Prof, cpfn_debug_chain_profile).
 //
 // Arithmetic: split-bf16 ("bf16x3").  Every fp32 operand x is held as hi = bf16(x) and
 // lo = bf16(x - hi) (together 16 mantissa bits) and each product is accumulated in fp32 as
