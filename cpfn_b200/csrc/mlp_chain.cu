@@ -737,16 +737,11 @@ mlp_chain_kernel(const __grid_constant__ ChainP p) {
 // consecutive channels per tcgen05.ld, so the (hi, lo) split packs 8 channels into one 16-byte
 // shared-memory store with no cross-lane traffic (about half the instructions per element of the
 // channels-as-M kernel above, no padding of 64-wide layers to 128), the channel-major copy and the
-// dropout mask are coalesced across the warp, and the max-pool is one REDUX per channel.
+// dropout mask are coalesced across the warp.  A pooled LAST layer swaps the operand roles (see epi_pool_cols);
+// ragged tiles fall back to one REDUX per channel + atomicMax.
 // =================================================================================================
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-// max over the warp's 32 lanes of a (signed) float: CREDUX.MAX.F32, result in a uniform register
-__device__ __forceinline__ float warp_max_f32(float v) {
-  float r;
-  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
-  return r;
 }
 
 // ---- specialised epilogue loops of the points-as-M kernels (thread = point) ---------------------------------
